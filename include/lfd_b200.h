@@ -1,0 +1,162 @@
+/* lfd_b200.h -- C-ABI of liblfd_b200.so: the B200 (sm_100a) implementation of the LFD dense-conv hot path.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, explicit shapes, a cudaStream_t passed as void*; no torch / C++ types.
+ *   - nothing is allocated inside: the caller supplies outputs and workspaces (sizes via the *_bytes queries).
+ *   - every function returns 0 (LFD_OK) or an lfd_status; lfd_last_error() gives a thread-local message.
+ *     No exceptions cross the boundary.  Calls are asynchronous on the given stream unless stated otherwise.
+ *   - there is no CPU fallback: every entry point launches CUDA kernels and fails if no sm_100 device is present.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   lfd_plan_*                     LFD.forward                         lfd/model/lfd.py:511-542
+ *                                  (LFDResNet.forward lfd/model/backbone/lfd_resnet.py:488-501,
+ *                                   SimpleNeck.forward lfd/model/neck/simple_neck.py:67-74,
+ *                                   LFDHead.forward    lfd/model/head/lfd_head.py:164-185)
+ *   lfd_postprocess                LFD._get_results_for_single_image   lfd/model/lfd.py:434-509, predict path :577-641,
+ *                                  multiclass_nms / batched_nms        lfd/model/utils/nms.py:119-220
+ *   lfd_nms                        nms_ext.nms                         lfd/model/utils/build/nms/src/nms_ext.cpp:18-29,
+ *                                                                      cpu/nms_cpu.cpp:8-75, cuda/nms_kernel.cu:71-138
+ *   lfd_sigmoid_focal_loss_forward sigmoid_focal_loss_ext.forward      lfd/model/losses/build/sigmoid_focal_loss/src/sigmoid_focal_loss_ext.cpp:19-34
+ *   lfd_sigmoid_focal_loss_backward sigmoid_focal_loss_ext.backward    same file :36-50
+ *   lfd_assign_targets             LFD.annotation_to_target            lfd/model/lfd.py:109-259
+ *   lfd_detection_loss             LFD.get_loss (loss + d loss/d outputs) lfd/model/lfd.py:284-395 with
+ *                                  FocalLoss / CrossEntropyLoss / IoULoss lfd/model/losses/{focal_loss,cross_entropy_loss,iou_loss}.py
+ */
+#ifndef LFD_B200_H_
+#define LFD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFD_B200_ABI_VERSION 1
+#define LFD_MAX_LEVELS 8
+
+typedef enum lfd_status {
+    LFD_OK = 0,
+    LFD_ERR_INVALID = 1,      /* bad argument / unsupported shape */
+    LFD_ERR_CUDA = 2,         /* a CUDA runtime call failed (message has the CUDA error string) */
+    LFD_ERR_UNSUPPORTED = 3,  /* configuration outside the implemented hot path */
+    LFD_ERR_CAPACITY = 4      /* caller-provided capacity too small */
+} lfd_status;
+
+typedef void* lfd_stream; /* cudaStream_t */
+typedef struct lfd_plan lfd_plan;
+
+int lfd_abi_version(void);
+const char* lfd_last_error(void);
+/* number of SMs of the current device (0 + error when there is no usable device) */
+int lfd_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------ forward plan */
+enum { LFD_OP_STEM0 = 0, LFD_OP_CONV = 1, LFD_OP_GN_APPLY = 2, LFD_OP_HEAD_FINAL = 3 };
+enum { LFD_INPUT_F32_NCHW = 0, LFD_INPUT_U8_NHWC = 1 };
+enum { LFD_CONV_UMMA = 0, LFD_CONV_SIMT = 1 }; /* SIMT = cross-check kernel, validation only */
+
+/* One fused layer.  Activations are bf16 NHWC at byte offsets into the caller's workspace.
+ *   STEM0      3x3/s2 conv on the 3-channel image + scale/shift (+ReLU); in_off ignored (reads the external input);
+ *              weight = float[27][Cout] (k = tap*3 + ci, bf16-representable values).
+ *   CONV       ksize in {1,3}, stride in {1,2}, pad = ksize/2; y = conv(x)*scale + shift (+res) (ReLU) -> bf16;
+ *              weight = bf16 packed [Cin/cc][ksize^2][cc/8][Cout][8] with cc from lfd_conv_query;
+ *              gn_groups > 0: also accumulates sum / sum-of-squares of the stored output per (image, group)
+ *              into double[N][gn_groups][2] at stats_off (group size must be 8).
+ *   GN_APPLY   y = relu(gamma * (x - mean) * rstd + beta) from the statistics at stats_off, bf16 -> bf16.
+ *   HEAD_FINAL GN_APPLY (as above, rounded to bf16) followed by the final 1x1 convs of one level: outputs
+ *              [0, n_cls) -> cls[n][point_off + pixel][.] and [n_cls, n_cls + n_reg) -> reg[n][point_off + pixel][.];
+ *              weight = float[n_cls + n_reg][Cin]; scale/shift = per-output scale and (scale * bias).
+ */
+typedef struct lfd_op {
+    int32_t kind;
+    int32_t N, H, W, Cin, Ho, Wo, Cout;
+    int32_t ksize, stride, relu, gn_groups;
+    int32_t n_cls, n_reg, point_off, cc;
+    int64_t in_off, out_off, res_off, stats_off; /* bytes; -1 = unused */
+    const void* weight;
+    const float* scale;
+    const float* shift;
+    const float* gamma;
+    const float* beta;
+} lfd_op;
+
+/* Tile / pipeline configuration the tcgen05 kernel will use for a conv (host only, no launch).
+ * cc = input-channel chunk the weights must be packed with. */
+int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int* cc, int* stages,
+                   int* weights_resident, int* num_tiles, int64_t* smem_bytes);
+
+/* The plan copies the op list.  stats_off/stats_bytes: region of the workspace zeroed at the start of each forward. */
+int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int cls_channels, int64_t stats_off, int64_t stats_bytes,
+                    int64_t workspace_bytes, int conv_impl, lfd_plan** out);
+int lfd_plan_destroy(lfd_plan* plan);
+int lfd_plan_num_launches(const lfd_plan* plan); /* kernels launched per forward */
+/* cls_out float[N][P][cls_channels], reg_out float[N][P][4].  use_graph != 0: the launch sequence is captured into a
+ * CUDA graph on first use for this (input, workspace, cls_out, reg_out) tuple and replayed afterwards. */
+int lfd_plan_forward(lfd_plan* plan, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
+                     int use_graph, lfd_stream stream);
+/* run a single op (tests / debugging) */
+int lfd_run_op(const lfd_op* op, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out, int P,
+               int cls_channels, int conv_impl, lfd_stream stream);
+
+/* ------------------------------------------------------------------------------------------ post-process */
+enum { LFD_CLS_SIGMOID = 0, LFD_CLS_SOFTMAX = 1 };
+enum { LFD_BBOX_SIGMOID = 0, LFD_BBOX_EXP = 1, LFD_BBOX_INDEPENDENT = 2 };
+
+typedef struct lfd_post_cfg {
+    int32_t N, P, C;            /* C = number of foreground classes */
+    int32_t cls_channels;       /* C (sigmoid) or C + 1 (softmax, background last) */
+    int32_t cls_mode, bbox_mode, class_agnostic;
+    int32_t num_levels;
+    int32_t level_off[LFD_MAX_LEVELS], level_w[LFD_MAX_LEVELS], level_stride[LFD_MAX_LEVELS];
+    float level_hi[LFD_MAX_LEVELS]; /* upper end of the level's regression range */
+    float score_thr, iou_thr;
+    int32_t cap;                /* per-image capacity for candidates and outputs */
+} lfd_post_cfg;
+
+size_t lfd_postprocess_workspace_bytes(const lfd_post_cfg* cfg);
+/* img_w / img_h / resize_scale: device float[N].  Outputs (device): dets float[N][cap][5] = x1,y1,x2,y2,score in
+ * score-descending kept order; labels int[N][cap]; src int[N][cap] = point * C + class; count int[N];
+ * overflow int[1] set to 1 if an image produced more than cap candidates. */
+int lfd_postprocess(const lfd_post_cfg* cfg, const float* cls, const float* reg, const float* img_w, const float* img_h,
+                    const float* resize_scale, void* workspace, float* dets, int32_t* labels, int32_t* src, int32_t* count,
+                    int32_t* overflow, lfd_stream stream);
+
+size_t lfd_nms_workspace_bytes(int n);
+/* dets device float[n][5]; keep device int64[n] (first *n_keep valid, score-descending); n_keep device int32[1]. */
+int lfd_nms(const float* dets, int n, float iou_thr, void* workspace, int64_t* keep, int32_t* n_keep, lfd_stream stream);
+
+/* ------------------------------------------------------------------------------------------ training losses */
+typedef struct lfd_levels {
+    int32_t num_levels;
+    int32_t off[LFD_MAX_LEVELS], w[LFD_MAX_LEVELS], stride[LFD_MAX_LEVELS];
+    float lo[LFD_MAX_LEVELS], hi[LFD_MAX_LEVELS];   /* regression range of the level */
+    float glo[LFD_MAX_LEVELS], ghi[LFD_MAX_LEVELS]; /* gray range (after int() truncation, lfd.py:49-50) */
+} lfd_levels;
+
+enum { LFD_ASSIGN_DIST = 0, LFD_ASSIGN_LONGER = 1, LFD_ASSIGN_SHORTER = 2 };
+
+/* gt_boxes device float[N][gmax][4] (x,y,w,h), gt_labels int[N][gmax], gt_count int[N].
+ * cls_target float[N][P][C], reg_target float[N][P][4], label int[N][P] (-1 ignore, C background),
+ * counters int[2] = {n_pos, n_valid} (zeroed inside). */
+int lfd_assign_targets(const lfd_levels* lv, int N, int P, int C, int gmax, int assign_mode, int independent,
+                       const float* gt_boxes, const int32_t* gt_labels, const int32_t* gt_count, float* cls_target,
+                       float* reg_target, int32_t* label, int32_t* counters, lfd_stream stream);
+
+/* loss_sums double[2] = {sum of element-wise cls loss over valid rows, sum of -log(IoU) over positives} (zeroed inside);
+ * the reference's normalisation is loss = sums[0]/(n_pos+1) + sums[1]/n_pos.  grad_cls / grad_reg (optional) receive
+ * d loss / d cls_logits and d loss / d reg with that normalisation and the loss weights applied. */
+int lfd_detection_loss(const lfd_levels* lv, int N, int P, int C, int cls_mode, int bbox_mode, float gamma, float alpha,
+                       float iou_eps, float cls_weight, float reg_weight, const float* cls_logits, const float* reg,
+                       const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls,
+                       float* grad_reg, double* loss_sums, lfd_stream stream);
+
+int lfd_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, int M, int C, float gamma, float alpha,
+                                   float* losses, lfd_stream stream);
+int lfd_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets, const float* d_losses, int M, int C,
+                                    float gamma, float alpha, float* d_logits, lfd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFD_B200_H_ */

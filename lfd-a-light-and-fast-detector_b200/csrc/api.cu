@@ -1,0 +1,449 @@
+// api.cu -- the extern "C" boundary of liblfd_b200.so (declared in include/lfd_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <vector>
+
+#include "../../include/lfd_b200.h"
+#include "conv_common.cuh"
+#include "kernels.cuh"
+
+using namespace lfd;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(LFD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+static int sm_count() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached = n;
+    return n;
+}
+
+struct PlannedOp {
+    lfd_op op;
+    UmmaConvParams cp;  // CONV via tcgen05
+    size_t smem;
+    int grid;
+};
+
+struct lfd_plan {
+    std::vector<PlannedOp> ops;
+    int N, P, cls_channels, conv_impl;
+    int64_t stats_off, stats_bytes, workspace_bytes;
+    // CUDA graph cache
+    cudaGraphExec_t exec;
+    const void* g_input;
+    void* g_ws;
+    float* g_cls;
+    float* g_reg;
+    int g_fmt;
+};
+
+extern "C" int lfd_abi_version(void) { return LFD_B200_ABI_VERSION; }
+extern "C" const char* lfd_last_error(void) { return g_err; }
+extern "C" int lfd_device_sm_count(void) {
+    int n = sm_count();
+    if (n <= 0) fail(LFD_ERR_CUDA, "no usable CUDA device");
+    return n;
+}
+
+static ConvGeom geom_of(const lfd_op& o) {
+    ConvGeom g;
+    g.N = o.N; g.H = o.H; g.W = o.W; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.ksize = o.ksize; g.stride = o.stride;
+    return g;
+}
+
+extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int* cc, int* stages,
+                              int* weights_resident, int* num_tiles, int64_t* smem_bytes) {
+    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride};
+    UmmaConvParams p;
+    size_t smem = 0;
+    int grid = 0;
+    int rc = umma_conv_configure(g, 148, &p, &smem, &grid);
+    if (rc) return fail(LFD_ERR_UNSUPPORTED, "conv %dx%d s%d Cin=%d Cout=%d not supported by the tcgen05 kernel (rc=%d)", ksize, ksize, stride, Cin, Cout, rc);
+    if (cc) *cc = p.Cc;
+    if (stages) *stages = p.stages;
+    if (weights_resident) *weights_resident = p.b_resident;
+    if (num_tiles) *num_tiles = p.num_tiles;
+    if (smem_bytes) *smem_bytes = (int64_t)smem;
+    return LFD_OK;
+}
+
+static int check_op(const lfd_op& o) {
+    const int eh = (o.H + 2 * (o.ksize / 2) - o.ksize) / (o.stride > 0 ? o.stride : 1) + 1;
+    const int ew = (o.W + 2 * (o.ksize / 2) - o.ksize) / (o.stride > 0 ? o.stride : 1) + 1;
+    switch (o.kind) {
+        case LFD_OP_STEM0:
+            if (o.Cin != 3 || o.ksize != 3 || o.stride != 2) return fail(LFD_ERR_UNSUPPORTED, "stem0 supports 3x3/s2 on 3 input channels only (got Cin=%d k=%d s=%d)", o.Cin, o.ksize, o.stride);
+            if (o.Cout != 16 && o.Cout != 32 && o.Cout != 64) return fail(LFD_ERR_UNSUPPORTED, "stem0 Cout must be 16/32/64 (got %d)", o.Cout);
+            if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "stem0 output size mismatch");
+            break;
+        case LFD_OP_CONV:
+            if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "conv output size mismatch (%dx%d vs %dx%d)", o.Ho, o.Wo, eh, ew);
+            if (o.gn_groups && (o.Cout != o.gn_groups * 8 || o.gn_groups != 16)) return fail(LFD_ERR_UNSUPPORTED, "fused GroupNorm statistics need 16 groups of 8 channels (Cout=%d groups=%d)", o.Cout, o.gn_groups);
+            if (o.cc <= 0 || o.Cin % o.cc) return fail(LFD_ERR_INVALID, "conv cc=%d does not divide Cin=%d", o.cc, o.Cin);
+            break;
+        case LFD_OP_GN_APPLY:
+        case LFD_OP_HEAD_FINAL:
+            if (o.Cin != o.gn_groups * 8) return fail(LFD_ERR_UNSUPPORTED, "GroupNorm needs groups of 8 channels (C=%d groups=%d)", o.Cin, o.gn_groups);
+            break;
+        default:
+            return fail(LFD_ERR_INVALID, "unknown op kind %d", o.kind);
+    }
+    return LFD_OK;
+}
+
+static int plan_op(const lfd_op& o, int conv_impl, PlannedOp* out) {
+    int rc = check_op(o);
+    if (rc) return rc;
+    out->op = o;
+    out->smem = 0;
+    out->grid = 0;
+    if (o.kind == LFD_OP_CONV) {
+        rc = umma_conv_configure(geom_of(o), sm_count() > 0 ? sm_count() : 148, &out->cp, &out->smem, &out->grid);
+        if (rc) return fail(LFD_ERR_UNSUPPORTED, "conv %dx%d s%d Cin=%d Cout=%d unsupported (rc=%d)", o.ksize, o.ksize, o.stride, o.Cin, o.Cout, rc);
+        if (out->cp.Cc != o.cc) return fail(LFD_ERR_INVALID, "weights packed with cc=%d but the kernel needs cc=%d", o.cc, out->cp.Cc);
+    }
+    (void)conv_impl;
+    return LFD_OK;
+}
+
+static int launch_op(const PlannedOp& po, const void* input, int input_format, uint8_t* ws, float* cls, float* reg, int P,
+                     int cls_channels, int conv_impl, cudaStream_t st) {
+    const lfd_op& o = po.op;
+    switch (o.kind) {
+        case LFD_OP_STEM0: {
+            Stem0Params p;
+            p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
+            p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
+            p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu;
+            if (!input) return fail(LFD_ERR_INVALID, "stem0 needs the external input pointer");
+            CUDA_TRY(stem0_launch(p, st));
+            break;
+        }
+        case LFD_OP_CONV: {
+            const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off);
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
+            const __nv_bfloat16* res = o.res_off >= 0 ? reinterpret_cast<const __nv_bfloat16*>(ws + o.res_off) : nullptr;
+            double* stats = o.gn_groups ? reinterpret_cast<double*>(ws + o.stats_off) : nullptr;
+            if (conv_impl == LFD_CONV_SIMT) {
+                CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight), o.scale,
+                                          o.shift, stats, o.gn_groups, o.relu, st));
+            } else {
+                UmmaConvParams p = po.cp;
+                p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
+                p.scale = o.scale; p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
+                CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
+            }
+            break;
+        }
+        case LFD_OP_GN_APPLY: {
+            GnApplyParams p;
+            p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off); p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
+            p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
+            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f;
+            CUDA_TRY(gn_apply_launch(p, sm_count(), st));
+            break;
+        }
+        case LFD_OP_HEAD_FINAL: {
+            HeadFinalParams p;
+            p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off);
+            p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
+            p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
+            p.cls = o.n_cls ? cls : nullptr; p.reg = o.n_reg ? reg : nullptr;
+            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.n_out = o.n_cls + o.n_reg; p.n_cls = o.n_cls;
+            p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f;
+            if ((o.n_cls && !cls) || (o.n_reg && !reg)) return fail(LFD_ERR_INVALID, "head_final needs cls/reg output pointers");
+            if (o.n_reg && o.n_reg != 4) return fail(LFD_ERR_INVALID, "head_final n_reg must be 0 or 4");
+            CUDA_TRY(head_final_launch(p, st));
+            break;
+        }
+    }
+    return LFD_OK;
+}
+
+extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int cls_channels, int64_t stats_off, int64_t stats_bytes,
+                               int64_t workspace_bytes, int conv_impl, lfd_plan** out) {
+    if (!ops || n_ops <= 0 || !out) return fail(LFD_ERR_INVALID, "lfd_plan_create: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_plan_create: no CUDA device (there is no CPU fallback)");
+    lfd_plan* pl = new lfd_plan();
+    pl->N = N; pl->P = P; pl->cls_channels = cls_channels; pl->conv_impl = conv_impl;
+    pl->stats_off = stats_off; pl->stats_bytes = stats_bytes; pl->workspace_bytes = workspace_bytes;
+    pl->exec = nullptr; pl->g_input = nullptr; pl->g_ws = nullptr; pl->g_cls = nullptr; pl->g_reg = nullptr; pl->g_fmt = -1;
+    for (int i = 0; i < n_ops; ++i) {
+        PlannedOp po;
+        int rc = plan_op(ops[i], conv_impl, &po);
+        if (rc) { delete pl; return rc; }
+        pl->ops.push_back(po);
+    }
+    *out = pl;
+    return LFD_OK;
+}
+
+extern "C" int lfd_plan_destroy(lfd_plan* plan) {
+    if (!plan) return LFD_OK;
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    delete plan;
+    return LFD_OK;
+}
+
+extern "C" int lfd_plan_num_launches(const lfd_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+
+static int enqueue_all(lfd_plan* pl, const void* input, int fmt, uint8_t* ws, float* cls, float* reg, cudaStream_t st) {
+    if (pl->stats_bytes > 0) CUDA_TRY(cudaMemsetAsync(ws + pl->stats_off, 0, (size_t)pl->stats_bytes, st));
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+        int rc = launch_op(pl->ops[i], input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, st);
+        if (rc) return rc;
+    }
+    return LFD_OK;
+}
+
+extern "C" int lfd_plan_forward(lfd_plan* pl, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
+                                int use_graph, lfd_stream stream) {
+    if (!pl || !input || !workspace || !cls_out || !reg_out) return fail(LFD_ERR_INVALID, "lfd_plan_forward: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    if (!use_graph) return enqueue_all(pl, input, input_format, ws, cls_out, reg_out, st);
+    const bool hit = pl->exec && pl->g_input == input && pl->g_ws == workspace && pl->g_cls == cls_out && pl->g_reg == reg_out &&
+                     pl->g_fmt == input_format;
+    if (!hit) {
+        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
+        // one eager pass first: sets function attributes outside of capture and surfaces launch errors directly
+        int rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, st);
+        if (rc) return rc;
+        cudaStream_t cap;
+        CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, cap);
+        cudaError_t ce = cudaStreamEndCapture(cap, &graph);
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cap);
+            return rc ? rc : fail(LFD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(&pl->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        if (ce != cudaSuccess) { pl->exec = nullptr; return fail(LFD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
+        pl->g_input = input; pl->g_ws = workspace; pl->g_cls = cls_out; pl->g_reg = reg_out; pl->g_fmt = input_format;
+        return LFD_OK;  // the eager pass above already produced this call's outputs
+    }
+    CUDA_TRY(cudaGraphLaunch(pl->exec, st));
+    return LFD_OK;
+}
+
+extern "C" int lfd_run_op(const lfd_op* op, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
+                          int P, int cls_channels, int conv_impl, lfd_stream stream) {
+    if (!op || !workspace) return fail(LFD_ERR_INVALID, "lfd_run_op: null argument");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_run_op: no CUDA device (there is no CPU fallback)");
+    PlannedOp po;
+    int rc = plan_op(*op, conv_impl, &po);
+    if (rc) return rc;
+    return launch_op(po, input, input_format, reinterpret_cast<uint8_t*>(workspace), cls_out, reg_out, P, cls_channels, conv_impl,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ post-process
+static int pow2_at_least(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct PostLayout {
+    size_t box, score, src, count, scratch, scratch_stride, total;
+    int cap_pow2;
+};
+static PostLayout post_layout(int N, int cap) {
+    PostLayout L;
+    L.cap_pow2 = pow2_at_least(cap);
+    size_t o = 0;
+    L.box = o; o = align256(o + (size_t)N * cap * 16);
+    L.score = o; o = align256(o + (size_t)N * cap * 4);
+    L.src = o; o = align256(o + (size_t)N * cap * 4);
+    L.count = o; o = align256(o + (size_t)N * 4);
+    L.scratch_stride = nms_scratch_stride(cap, L.cap_pow2);
+    L.scratch = o; o = align256(o + (size_t)N * L.scratch_stride);
+    L.total = o;
+    return L;
+}
+
+extern "C" size_t lfd_postprocess_workspace_bytes(const lfd_post_cfg* cfg) {
+    if (!cfg || cfg->N <= 0 || cfg->cap <= 0) return 0;
+    return post_layout(cfg->N, cfg->cap).total;
+}
+
+extern "C" int lfd_postprocess(const lfd_post_cfg* c, const float* cls, const float* reg, const float* img_w, const float* img_h,
+                               const float* resize_scale, void* workspace, float* dets, int32_t* labels, int32_t* src, int32_t* count,
+                               int32_t* overflow, lfd_stream stream) {
+    if (!c || !cls || !reg || !img_w || !img_h || !resize_scale || !workspace || !dets || !labels || !src || !count || !overflow)
+        return fail(LFD_ERR_INVALID, "lfd_postprocess: null argument");
+    if (c->num_levels < 1 || c->num_levels > LFD_MAX_LEVELS || c->C < 1 || c->cap < 1) return fail(LFD_ERR_INVALID, "lfd_postprocess: bad config");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_postprocess: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const PostLayout L = post_layout(c->N, c->cap);
+    PostParams p;
+    p.cls = cls; p.reg = reg; p.img_w = img_w; p.img_h = img_h; p.resize_scale = resize_scale;
+    p.N = c->N; p.P = c->P; p.C = c->C; p.cls_stride = c->cls_channels; p.cls_mode = c->cls_mode; p.bbox_mode = c->bbox_mode;
+    p.num_levels = c->num_levels; p.cap = c->cap;
+    for (int l = 0; l < LFD_MAX_LEVELS; ++l) {
+        p.level_off[l] = c->level_off[l]; p.level_w[l] = c->level_w[l]; p.level_stride[l] = c->level_stride[l]; p.level_hi[l] = c->level_hi[l];
+    }
+    p.score_thr = c->score_thr;
+    p.cand_box = reinterpret_cast<float*>(ws + L.box); p.cand_score = reinterpret_cast<float*>(ws + L.score);
+    p.cand_src = reinterpret_cast<int*>(ws + L.src); p.cand_count = reinterpret_cast<int*>(ws + L.count);
+    CUDA_TRY(cudaMemsetAsync(p.cand_count, 0, (size_t)c->N * 4, st));
+    CUDA_TRY(cudaMemsetAsync(overflow, 0, 4, st));
+    CUDA_TRY(candidates_launch(p, st));
+    NmsParams q;
+    q.cand_box = p.cand_box; q.cand_score = p.cand_score; q.cand_src = p.cand_src; q.cand_count = p.cand_count;
+    q.scratch = ws + L.scratch; q.scratch_stride = L.scratch_stride; q.cap = c->cap; q.cap_pow2 = L.cap_pow2; q.C = c->C;
+    q.class_agnostic = c->class_agnostic; q.iou_thr = c->iou_thr;
+    q.out_dets = dets; q.out_label = labels; q.out_src = src; q.out_count = count; q.overflow = overflow;
+    CUDA_TRY(nms_launch(q, c->N, st));
+    return LFD_OK;
+}
+
+// standalone NMS on raw dets (mirror of nms_ext.nms)
+__global__ void nms_split_kernel(const float* dets, int n, float* box, float* score, int* src, int* count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = n;
+    if (i >= n) return;
+    reinterpret_cast<float4*>(box)[i] = make_float4(dets[i * 5], dets[i * 5 + 1], dets[i * 5 + 2], dets[i * 5 + 3]);
+    score[i] = dets[i * 5 + 4];
+    src[i] = i;
+}
+__global__ void nms_keep_kernel(const int* src, const int* count, long long* keep, int* n_keep) {
+    const int k = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) keep[i] = src[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_keep = k;
+}
+
+struct RawNmsLayout {
+    PostLayout base;
+    size_t dets, label, src, count, overflow, total;
+};
+static RawNmsLayout raw_layout(int n) {
+    RawNmsLayout R;
+    R.base = post_layout(1, n);
+    size_t o = R.base.total;
+    R.dets = o; o = align256(o + (size_t)n * 20);
+    R.label = o; o = align256(o + (size_t)n * 4);
+    R.src = o; o = align256(o + (size_t)n * 4);
+    R.count = o; o = align256(o + 4);
+    R.overflow = o; o = align256(o + 4);
+    R.total = o;
+    return R;
+}
+extern "C" size_t lfd_nms_workspace_bytes(int n) { return n > 0 ? raw_layout(n).total : 256; }
+
+extern "C" int lfd_nms(const float* dets, int n, float iou_thr, void* workspace, int64_t* keep, int32_t* n_keep, lfd_stream stream) {
+    if (!n_keep || n < 0) return fail(LFD_ERR_INVALID, "lfd_nms: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_nms: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(n_keep, 0, 4, st));
+        return LFD_OK;
+    }
+    if (!dets || !workspace || !keep) return fail(LFD_ERR_INVALID, "lfd_nms: null argument");
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const RawNmsLayout R = raw_layout(n);
+    NmsParams q;
+    q.cand_box = reinterpret_cast<float*>(ws + R.base.box); q.cand_score = reinterpret_cast<float*>(ws + R.base.score);
+    q.cand_src = reinterpret_cast<int*>(ws + R.base.src); q.cand_count = reinterpret_cast<int*>(ws + R.base.count);
+    q.scratch = ws + R.base.scratch; q.scratch_stride = R.base.scratch_stride; q.cap = n; q.cap_pow2 = R.base.cap_pow2; q.C = 1;
+    q.class_agnostic = 1; q.iou_thr = iou_thr;
+    q.out_dets = reinterpret_cast<float*>(ws + R.dets); q.out_label = reinterpret_cast<int*>(ws + R.label);
+    q.out_src = reinterpret_cast<int*>(ws + R.src); q.out_count = reinterpret_cast<int*>(ws + R.count);
+    q.overflow = reinterpret_cast<int*>(ws + R.overflow);
+    nms_split_kernel<<<(n + 255) / 256, 256, 0, st>>>(dets, n, const_cast<float*>(q.cand_box), const_cast<float*>(q.cand_score),
+                                                      const_cast<int*>(q.cand_src), const_cast<int*>(q.cand_count));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(nms_launch(q, 1, st));
+    nms_keep_kernel<<<(n + 255) / 256, 256, 0, st>>>(q.out_src, q.out_count, reinterpret_cast<long long*>(keep), n_keep);
+    CUDA_TRY(cudaGetLastError());
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+static void fill_levels(const lfd_levels* lv, LevelTable* t) {
+    t->num_levels = lv->num_levels;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        t->off[l] = lv->off[l]; t->w[l] = lv->w[l]; t->stride[l] = lv->stride[l];
+        t->lo[l] = lv->lo[l]; t->hi[l] = lv->hi[l]; t->glo[l] = lv->glo[l]; t->ghi[l] = lv->ghi[l];
+    }
+}
+
+extern "C" int lfd_assign_targets(const lfd_levels* lv, int N, int P, int C, int gmax, int assign_mode, int independent,
+                                  const float* gt_boxes, const int32_t* gt_labels, const int32_t* gt_count, float* cls_target,
+                                  float* reg_target, int32_t* label, int32_t* counters, lfd_stream stream) {
+    if (!lv || !gt_count || !cls_target || !reg_target || !label || !counters || (gmax > 0 && (!gt_boxes || !gt_labels)))
+        return fail(LFD_ERR_INVALID, "lfd_assign_targets: null argument");
+    if (lv->num_levels < 1 || lv->num_levels > LFD_MAX_LEVELS || N < 1 || P < 1 || C < 1) return fail(LFD_ERR_INVALID, "lfd_assign_targets: bad shape");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_assign_targets: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AssignParams p;
+    fill_levels(lv, &p.lv);
+    p.gt_boxes = gt_boxes; p.gt_labels = gt_labels; p.gt_count = gt_count;
+    p.N = N; p.P = P; p.C = C; p.gmax = gmax; p.assign_mode = assign_mode; p.independent = independent;
+    p.cls_target = cls_target; p.reg_target = reg_target; p.label = label; p.counters = counters;
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 8, st));
+    CUDA_TRY(assign_targets_launch(p, st));
+    return LFD_OK;
+}
+
+extern "C" int lfd_detection_loss(const lfd_levels* lv, int N, int P, int C, int cls_mode, int bbox_mode, float gamma, float alpha,
+                                  float iou_eps, float cls_weight, float reg_weight, const float* cls_logits, const float* reg,
+                                  const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls,
+                                  float* grad_reg, double* loss_sums, lfd_stream stream) {
+    if (!lv || !cls_logits || !reg || !reg_target || !label || !counters || !loss_sums) return fail(LFD_ERR_INVALID, "lfd_detection_loss: null argument");
+    if (bbox_mode != LFD_BBOX_SIGMOID && bbox_mode != LFD_BBOX_EXP) return fail(LFD_ERR_UNSUPPORTED, "lfd_detection_loss: only IoU-type (union) regression losses are implemented");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_detection_loss: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(loss_sums, 0, 16, st));
+    ClsLossParams c;
+    c.logits = cls_logits; c.label = label; c.counters = counters; c.grad = grad_cls; c.loss_sum = loss_sums;
+    c.N = N; c.P = P; c.C = C; c.cls_mode = cls_mode; c.gamma = gamma; c.alpha = alpha; c.loss_weight = cls_weight;
+    CUDA_TRY(cls_loss_launch(c, sm_count(), st));
+    RegLossParams r;
+    fill_levels(lv, &r.lv);
+    r.reg = reg; r.reg_target = reg_target; r.label = label; r.counters = counters; r.grad = grad_reg; r.loss_sum = loss_sums + 1;
+    r.N = N; r.P = P; r.C = C; r.bbox_mode = bbox_mode; r.eps = iou_eps; r.loss_weight = reg_weight;
+    CUDA_TRY(iou_loss_launch(r, sm_count(), st));
+    return LFD_OK;
+}
+
+extern "C" int lfd_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, int M, int C, float gamma, float alpha,
+                                              float* losses, lfd_stream stream) {
+    if (M < 0 || C < 1 || (M > 0 && (!logits || !targets || !losses))) return fail(LFD_ERR_INVALID, "lfd_sigmoid_focal_loss_forward: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "sigmoid focal loss: no CUDA device (the reference has no CPU path either, sigmoid_focal_loss_ext.cpp:32)");
+    CUDA_TRY(focal_forward_launch(logits, reinterpret_cast<const long long*>(targets), M, C, gamma, alpha, losses, reinterpret_cast<cudaStream_t>(stream)));
+    return LFD_OK;
+}
+extern "C" int lfd_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets, const float* d_losses, int M, int C,
+                                               float gamma, float alpha, float* d_logits, lfd_stream stream) {
+    if (M < 0 || C < 1 || (M > 0 && (!logits || !targets || !d_losses || !d_logits))) return fail(LFD_ERR_INVALID, "lfd_sigmoid_focal_loss_backward: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "sigmoid focal loss: no CUDA device");
+    CUDA_TRY(focal_backward_launch(logits, reinterpret_cast<const long long*>(targets), d_losses, M, C, gamma, alpha, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    return LFD_OK;
+}

@@ -1,0 +1,50 @@
+// conv_common.cuh -- shared declarations of the convolution kernels (internal, not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace lfd {
+
+enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3 };
+
+static constexpr int kMaxStages = 8;
+// dynamic shared memory map of conv_umma_kernel (bytes)
+static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
+static constexpr int kSmemScaleOff = 256;    // scale[128], shift[128] fp32
+static constexpr int kSmemTableOff = 1280;   // halo pixel table (<= 561 entries x 8 B)
+static constexpr int kSmemStagingOff = 6144; // epilogue staging tile 128 x Cout bf16
+
+struct ConvGeom {
+    int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
+};
+
+struct UmmaConvParams {
+    const __nv_bfloat16* in;
+    __nv_bfloat16* out;
+    const __nv_bfloat16* res;   // optional residual (same shape as out)
+    const __nv_bfloat16* w;     // packed [cc][tap][kc][Cout][8]
+    const float* scale;         // [Cout]
+    const float* shift;         // [Cout]
+    double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
+    int N, H, W, Cin, Ho, Wo, Cout;
+    int relu, gn_groups, mode;
+    int tiles_x, tiles_per_img, num_tiles;
+    int n_px;                   // halo pixels loaded per stage
+    int Cc, stages, b_resident;
+    uint32_t lbo_a, sbo_a;
+    uint32_t a_stage_bytes, b_slice_bytes, stage_bytes, w_total_bytes;
+    uint32_t smem_w_off, smem_ring_off;
+};
+
+// returns 0 when the geometry is supported by the tcgen05 kernel
+int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid);
+cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st);
+
+// SIMT cross-check kernel (same packed weights, same epilogue semantics); debugging / validation only.
+cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out,
+                             const __nv_bfloat16* res, const __nv_bfloat16* w, const float* scale, const float* shift,
+                             double* stats, int gn_groups, int relu, cudaStream_t st);
+
+}  // namespace lfd

@@ -1,0 +1,423 @@
+// conv_umma.cu -- implicit-GEMM convolution on 5th-gen tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Replaces, for the LFD hot path, every nn.Conv2d(+BatchNorm2d)(+residual)(+ReLU) of the reference's
+// backbone / neck / head towers (lfd/model/backbone/lfd_resnet.py:96-154,354-473,
+// lfd/model/neck/simple_neck.py:35-47, lfd/model/head/lfd_head.py:85-135), which the reference runs
+// as separate cuDNN / ATen kernels in NCHW fp32.
+//
+// Formulation (NHWC bf16 activations, fp32 accumulate in TMEM):
+//   D[128 output pixels, Cout] = sum over taps (kh,kw) and channel chunks of  A_tap[128, 16] * W_tap[16, Cout]
+//   * one CTA per SM, persistent over output tiles, warp-specialised:
+//       warps 0-3  epilogue   : TMEM -> regs -> scale/shift (+residual) (+ReLU) -> bf16 -> smem -> coalesced store
+//                               (+ optional GroupNorm partial statistics of the stored tensor)
+//       warp  4    MMA issuer : one elected lane issues tcgen05.mma, commits to mbarriers
+//       warps 5-8  producers  : cp.async (16 B, zero-fill = conv padding) of the input halo tile into the A ring
+//   * the input halo tile is loaded ONCE per (tile, channel-chunk) into "pixel planes"
+//       plane[k-chunk][pixel][8 channels = 16 B]
+//     which is exactly the UMMA K-major / no-swizzle canonical layout (8-row core matrices of 16 B rows,
+//     SBO between 8-row groups, LBO between 16-byte K chunks).  A 3x3 tap is then just a *shifted view*
+//     (start address += tap offset, SBO = halo row pitch), so the 9 taps re-read shared memory, never L2.
+//     Stride-2 convolutions de-interleave the halo into 4 row/column parity planes so that every tap is
+//     again a unit-stride view.
+//   * weights: pre-packed on the host in [channel-chunk][tap][k-chunk][Cout][8] order and brought in by
+//     the TMA engine as 1-D bulk copies (cp.async.bulk -> UBLKCP), either once (resident) or per stage
+//     (streamed, for 3x3x128x128 which does not fit next to the A ring).
+//   * two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "conv_common.cuh"
+#include "ptx.cuh"
+
+namespace lfd {
+
+static constexpr int kEpiThreads = 128;
+static constexpr int kMmaWarp = 4;
+static constexpr int kProdThreads = 128;
+static constexpr int kThreads = kEpiThreads + 32 + kProdThreads;  // 288
+static constexpr int kLag = 2;                                     // cp.async groups kept in flight per producer thread
+static constexpr int kTmemCols = 256;
+
+struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's input origin) and where it goes
+    int16_t dy, dx;
+    uint16_t slot;
+    uint16_t pad;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
+    uint64_t* empty = full + kMaxStages;
+    uint64_t* tfull = empty + kMaxStages;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* s_scale = reinterpret_cast<float*>(smem + kSmemScaleOff);
+    float* s_shift = s_scale + 128;
+    PxEntry* table = reinterpret_cast<PxEntry*>(smem + kSmemTableOff);
+    uint8_t* staging = smem + kSmemStagingOff;
+    uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
+    uint8_t* ring = smem + p.smem_ring_off;     // stages: [A chunk | B slice (streaming only)]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int SA = p.stages;
+    const int cpc = p.Cc >> 3;  // 16-byte chunks per pixel per stage
+
+    // ------------------------------------------------------------------ one-time setup
+    if (tid == 0) {
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(&full[i], kProdThreads + (p.b_resident ? 0 : 1));
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], kEpiThreads);
+        }
+        mbar_init(wbar, 1);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+    for (int c = tid; c < p.Cout; c += kThreads) {
+        s_scale[c] = p.scale[c];
+        s_shift[c] = p.shift[c];
+    }
+    // halo pixel table (tile independent)
+    for (int i = tid; i < p.n_px; i += kThreads) {
+        PxEntry e;
+        e.pad = 0;
+        if (MODE == MODE_FLAT) {
+            e.dy = 0; e.dx = (int16_t)i; e.slot = (uint16_t)i;
+        } else if (MODE == MODE_3X3S1) {
+            int r = i / 10, c = i % 10;
+            e.dy = (int16_t)(r - 1); e.dx = (int16_t)(c - 1); e.slot = (uint16_t)i;
+        } else if (MODE == MODE_1X1S2) {
+            int r = i >> 3, c = i & 7;
+            e.dy = (int16_t)(2 * r); e.dx = (int16_t)(2 * c); e.slot = (uint16_t)i;
+        } else {  // MODE_3X3S2: EE(16x8) | EO(16x9) | OE(17x8) | OO(17x9); all planes use pitch 9
+            int j = i, r, c, base, rodd, codd;
+            if (j < 128) { r = j >> 3; c = j & 7; base = 0; rodd = 0; codd = 0; }
+            else if ((j -= 128) < 144) { r = j / 9; c = j % 9; base = 144; rodd = 0; codd = 1; }
+            else if ((j -= 144) < 136) { r = j >> 3; c = j & 7; base = 288; rodd = 1; codd = 0; }
+            else { j -= 136; r = j / 9; c = j % 9; base = 441; rodd = 1; codd = 1; }
+            e.dy = (int16_t)(2 * r - rodd); e.dx = (int16_t)(2 * c - codd); e.slot = (uint16_t)(base + r * 9 + c);
+        }
+        table[i] = e;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int HW = p.H * p.W;
+    const int n_cc = p.Cin / p.Cc;
+    const int taps = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : 1;
+
+    if (warp < 4) {
+        // ============================================================== EPILOGUE
+        const int m = tid;  // D row == TMEM lane
+        const int cpr = p.Cout >> 3;          // 16 B chunks per staged row
+        const int row_bytes = p.Cout * 2;
+        const int rp128 = row_bytes >= 128 ? 1 : 128 / row_bytes;  // rows per 128 B (swizzle granularity)
+        const int swz_mask = (cpr < 8 ? cpr : 8) - 1;
+        const uint32_t stg = smem_u32(staging);
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            const int n = tile / p.tiles_per_img;
+            const int t = tile - n * p.tiles_per_img;
+            int oy0 = 0, ox0 = 0, p0 = 0;
+            if (MODE == MODE_FLAT) p0 = t * 128;
+            else { oy0 = (t / p.tiles_x) * 16; ox0 = (t % p.tiles_x) * 8; }
+            const size_t img_out = (size_t)n * p.Ho * p.Wo;
+            // pixel index (within the image) of staged row r, or -1 when outside the feature map
+            auto row_pixel = [&](int r) -> int {
+                if (MODE == MODE_FLAT) { int q = p0 + r; return q < p.Ho * p.Wo ? q : -1; }
+                int y = oy0 + (r >> 3), x = ox0 + (r & 7);
+                return (y < p.Ho && x < p.Wo) ? y * p.Wo + x : -1;
+            };
+            const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+            if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
+                for (int e = tid; e < 128 * cpr; e += kEpiThreads) {
+                    int r = e / cpr, c = e - r * cpr;
+                    int q = row_pixel(r);
+                    const __nv_bfloat16* src = p.res + ((img_out + (q < 0 ? 0 : q)) * p.Cout + c * 8);
+                    cp_async16(stg + r * row_bytes + ((c ^ ((r / rp128) & swz_mask)) << 4), src, q >= 0);
+                }
+                cp_async_commit();
+            }
+            mbar_wait(&tfull[a], aph);
+            tc_fence_after_sync();
+            if (p.res) {
+                cp_async_wait<0>();
+                named_bar_sync(1, kEpiThreads);
+            }
+            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * p.Cout;
+            uint8_t* my_row = staging + m * row_bytes;
+            const int my_swz = (m / rp128) & swz_mask;
+            for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int chunk = (c0 >> 3) + h;
+                    uint4* slot = reinterpret_cast<uint4*>(my_row + ((chunk ^ my_swz) << 4));
+                    float o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[h * 8 + j], s_scale[c0 + h * 8 + j], s_shift[c0 + h * 8 + j]);
+                    if (p.res) {
+                        uint4 rv = *slot;
+                        o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
+                        o[4] += bf16_lo(rv.z); o[5] += bf16_hi(rv.z); o[6] += bf16_lo(rv.w); o[7] += bf16_hi(rv.w);
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+                    }
+                    uint4 ov;
+                    ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+                    ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+                    *slot = ov;
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(&tempty[a]);  // accumulator stage may be overwritten by the next-but-one tile
+            named_bar_sync(1, kEpiThreads);
+            if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk
+                const int g = tid >> 3, sl = tid & 7;  // host guarantees Cout/groups == 8 and groups == 16
+                float s1 = 0.f, s2 = 0.f;
+                for (int r = sl; r < 128; r += 8) {
+                    if (row_pixel(r) < 0) continue;
+                    uint4 q = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((g ^ ((r / rp128) & swz_mask)) << 4));
+                    float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                                  bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (sl == 0) {
+                    double* dst = p.stats + ((size_t)n * p.gn_groups + g) * 2;
+                    atomicAdd(dst, (double)s1);
+                    atomicAdd(dst + 1, (double)s2);
+                }
+            }
+            for (int e = tid; e < 128 * cpr; e += kEpiThreads) {  // coalesced store
+                int r = e / cpr, c = e - r * cpr;
+                int q = row_pixel(r);
+                if (q < 0) continue;
+                uint4 val = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((c ^ ((r / rp128) & swz_mask)) << 4));
+                *reinterpret_cast<uint4*>(p.out + ((img_out + q) * p.Cout + c * 8)) = val;
+            }
+            named_bar_sync(1, kEpiThreads);  // staging free again
+        }
+    } else if (warp == kMmaWarp) {
+        // ============================================================== MMA ISSUER
+        const uint32_t idesc = umma_idesc_bf16(128, p.Cout);
+        const uint32_t lbo_a = p.lbo_a, sbo_a = p.sbo_a;
+        const uint32_t lbo_b = p.Cout * 16, sbo_b = 128;
+        if (p.b_resident) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(wbar, p.w_total_bytes);
+                for (uint32_t off = 0; off < p.w_total_bytes; off += 32768) {
+                    uint32_t n = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
+                    bulk_g2s(smem_u32(wres) + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wbar);
+                }
+            }
+            mbar_wait(wbar, 0);
+        }
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+            mbar_wait(&tempty[a], aph ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + a * p.Cout;
+            for (int cc = 0; cc < n_cc; ++cc, ++it) {
+                const uint32_t s = it % SA, ph = (it / SA) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after_sync();
+                fence_proxy_async_smem();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
+                    const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes
+                                                         : a_base + p.a_stage_bytes;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        uint32_t view = 0;
+                        if (MODE == MODE_3X3S1) view = (tap / 3) * 10 + (tap % 3);
+                        if (MODE == MODE_3X3S2) {
+                            const int kh = tap / 3, kw = tap % 3;
+                            const int base = (kh == 1 ? 0 : 288) + (kw == 1 ? 0 : (kh == 1 ? 144 : 153));
+                            view = base + (kh == 2 ? 9 : 0) + (kw == 2 ? 1 : 0);
+                        }
+                        for (int k16 = 0; k16 < p.Cc / 16; ++k16) {
+                            uint64_t ad = umma_smem_desc(a_base + view * 16 + 2 * k16 * lbo_a, lbo_a, sbo_a);
+                            uint64_t bd = umma_smem_desc(b_base + (tap * cpc + 2 * k16) * lbo_b, lbo_b, sbo_b);
+                            umma_bf16(d_tmem, ad, bd, idesc, (cc | tap | k16) != 0);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (cc == n_cc - 1) umma_commit(&tfull[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============================================================== PRODUCERS
+        const int ptid = tid - (kEpiThreads + 32);
+        const int n_el = p.n_px * cpc;
+        // A full-barrier arrival for stage-iteration j is made at the end of iteration j+lag; the empty wait of
+        // iteration j+SA must come later than that, hence lag <= SA-1.
+        const uint32_t lag = SA >= 3 ? (uint32_t)kLag : 1u;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int n = tile / p.tiles_per_img;
+            const int t = tile - n * p.tiles_per_img;
+            int iy0 = 0, ix0 = 0;
+            if (MODE == MODE_FLAT) ix0 = t * 128;
+            else {
+                int oy0 = (t / p.tiles_x) * 16, ox0 = (t % p.tiles_x) * 8;
+                iy0 = (MODE == MODE_3X3S1) ? oy0 : 2 * oy0;
+                ix0 = (MODE == MODE_3X3S1) ? ox0 : 2 * ox0;
+            }
+            const __nv_bfloat16* img = p.in + (size_t)n * HW * p.Cin;
+            for (int cc = 0; cc < n_cc; ++cc, ++it) {
+                const uint32_t s = it % SA, ph = (it / SA) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
+                if (!p.b_resident && ptid == 0) {
+                    mbar_arrive_expect_tx(&full[s], p.b_slice_bytes);
+                    bulk_g2s(a_base + p.a_stage_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)cc * p.b_slice_bytes,
+                             p.b_slice_bytes, &full[s]);
+                }
+                for (int e = ptid; e < n_el; e += kProdThreads) {
+                    const int pxi = e / cpc, ch = e - pxi * cpc;
+                    const PxEntry pe = table[pxi];
+                    bool ok;
+                    size_t pix;
+                    if (MODE == MODE_FLAT) {
+                        int q = ix0 + pe.dx;
+                        ok = q < HW;
+                        pix = ok ? q : 0;
+                    } else {
+                        int y = iy0 + pe.dy, x = ix0 + pe.dx;
+                        ok = (y >= 0) && (y < p.H) && (x >= 0) && (x < p.W);
+                        pix = ok ? (size_t)y * p.W + x : 0;
+                    }
+                    cp_async16(a_base + ch * p.lbo_a + pe.slot * 16, img + pix * p.Cin + cc * p.Cc + ch * 8, ok);
+                }
+                cp_async_commit();
+                if (it >= lag) {
+                    if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full[(it - lag) % SA]);
+                }
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        for (uint32_t k = (it > lag ? it - lag : 0); k < it; ++k) mbar_arrive(&full[k % SA]);
+    }
+
+    // ------------------------------------------------------------------ teardown
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid) {
+    UmmaConvParams p;
+    memset(&p, 0, sizeof(p));
+    int mode;
+    if (g.ksize == 1 && g.stride == 1) mode = MODE_FLAT;
+    else if (g.ksize == 3 && g.stride == 1) mode = MODE_3X3S1;
+    else if (g.ksize == 3 && g.stride == 2) mode = MODE_3X3S2;
+    else if (g.ksize == 1 && g.stride == 2) mode = MODE_1X1S2;
+    else return -1;
+    if (g.Cin % 16 || g.Cout % 16 || g.Cout > 128 || g.Cout < 16) return -1;
+    p.mode = mode;
+    p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Ho = g.Ho; p.Wo = g.Wo; p.Cout = g.Cout;
+    const int taps = g.ksize * g.ksize;
+    int px_slots;  // plane size in pixels (slots), n_px = pixels actually loaded
+    if (mode == MODE_FLAT) {
+        p.tiles_x = 0; p.tiles_per_img = (g.Ho * g.Wo + 127) / 128;
+        p.n_px = 128; px_slots = 128; p.sbo_a = 128;
+    } else {
+        p.tiles_x = (g.Wo + 7) / 8;
+        p.tiles_per_img = p.tiles_x * ((g.Ho + 15) / 16);
+        if (mode == MODE_3X3S1) { p.n_px = 180; px_slots = 180; p.sbo_a = 160; }
+        else if (mode == MODE_3X3S2) { p.n_px = 561; px_slots = 594; p.sbo_a = 144; }
+        else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }
+    }
+    p.lbo_a = px_slots * 16;
+    p.num_tiles = p.tiles_per_img * g.N;
+    const size_t staging = (size_t)128 * g.Cout * 2;
+    const size_t fixed = kSmemStagingOff + staging;
+    const size_t budget = 224 * 1024;
+    const size_t w_total = (size_t)taps * g.Cin * g.Cout * 2;
+    // choose channel chunk Cc, residency and stage count
+    int best_cc = 0, best_res = 0, best_st = 0;
+    const int cands[3] = {64, 32, 16};
+    for (int resident = 1; resident >= 0 && !best_cc; --resident) {
+        for (int ci = 0; ci < 3; ++ci) {
+            int cc = cands[ci];
+            if (g.Cin % cc) continue;
+            size_t a_stage = (size_t)px_slots * cc * 2;
+            size_t b_slice = (size_t)taps * cc * g.Cout * 2;
+            size_t stage = a_stage + (resident ? 0 : b_slice);
+            size_t avail = budget - fixed - (resident ? w_total : 0);
+            if (resident && w_total + fixed + 2 * a_stage > budget) continue;
+            int st = (int)(avail / stage);
+            int n_stage_units = (g.Cin / cc);
+            if (st > kMaxStages) st = kMaxStages;
+            if (st > 4 && a_stage >= 16384) st = 4;
+            if (st < 2) continue;
+            (void)n_stage_units;
+            best_cc = cc; best_res = resident; best_st = st;
+            break;
+        }
+    }
+    if (!best_cc) return -2;
+    p.Cc = best_cc; p.b_resident = best_res; p.stages = best_st;
+    p.a_stage_bytes = (uint32_t)((size_t)px_slots * best_cc * 2);
+    p.b_slice_bytes = (uint32_t)((size_t)taps * best_cc * g.Cout * 2);
+    p.stage_bytes = p.a_stage_bytes + (best_res ? 0 : p.b_slice_bytes);
+    p.w_total_bytes = (uint32_t)w_total;
+    p.smem_w_off = (uint32_t)fixed;
+    p.smem_ring_off = (uint32_t)(fixed + (best_res ? w_total : 0));
+    *smem_bytes = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
+    *grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    *out = p;
+    return 0;
+}
+
+template <int MODE>
+static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = 224 * 1024;
+    }
+    conv_umma_kernel<MODE><<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
+    switch (p.mode) {
+        case MODE_FLAT: return launch_mode<MODE_FLAT>(p, smem, grid, st);
+        case MODE_3X3S1: return launch_mode<MODE_3X3S1>(p, smem, grid, st);
+        case MODE_3X3S2: return launch_mode<MODE_3X3S2>(p, smem, grid, st);
+        case MODE_1X1S2: return launch_mode<MODE_1X1S2>(p, smem, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace lfd

@@ -1,0 +1,130 @@
+// kernels.cuh -- parameter blocks and launchers of the non-GEMM kernels (internal, not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace lfd {
+
+static constexpr int kMaxLevels = 8;
+
+struct Stem0Params {
+    const void* in;            // fp32 NCHW (input_format 0) or u8 NHWC (1)
+    __nv_bfloat16* out;        // bf16 NHWC
+    const float* w;            // [9*3][Cout] fp32 holding bf16-rounded values, k = tap*3 + ci
+    const float* scale;
+    const float* shift;
+    int input_format, N, H, W, Ho, Wo, Cout, relu;
+};
+cudaError_t stem0_launch(const Stem0Params& p, cudaStream_t st);
+
+struct GnApplyParams {
+    const __nv_bfloat16* in;
+    __nv_bfloat16* out;
+    const double* stats;       // [N][groups][2]
+    const float* gamma;
+    const float* beta;
+    int N, HW, C, groups;
+    float eps;
+};
+cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st);
+
+struct HeadFinalParams {
+    const __nv_bfloat16* in;   // pre-GN tower output [N][HW][C]
+    const double* stats;
+    const float* gamma;
+    const float* beta;
+    const float* w;            // [n_out][C] fp32 holding bf16-rounded values
+    const float* scale;        // [n_out]
+    const float* shift;        // [n_out]
+    float* cls;                // (N, P, cls_stride) or null
+    float* reg;                // (N, P, 4) or null
+    int N, HW, C, groups, n_out, n_cls, P, point_off, cls_stride;
+    float eps;
+};
+cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st);
+
+struct LevelTable {
+    int num_levels;
+    int off[kMaxLevels], w[kMaxLevels], stride[kMaxLevels];
+    float lo[kMaxLevels], hi[kMaxLevels], glo[kMaxLevels], ghi[kMaxLevels];
+};
+
+struct PostParams {
+    const float* cls;          // (N, P, cls_stride)
+    const float* reg;          // (N, P, 4)
+    const float* img_w;        // [N] clamp bounds (resized width / height), lfd.py:440-441
+    const float* img_h;
+    const float* resize_scale; // [N]
+    int N, P, C, cls_stride, cls_mode, bbox_mode, num_levels, cap;
+    int level_off[kMaxLevels], level_w[kMaxLevels], level_stride[kMaxLevels];
+    float level_hi[kMaxLevels];
+    float score_thr;
+    float* cand_box;           // [N][cap][4]
+    float* cand_score;         // [N][cap]
+    int* cand_src;             // [N][cap]
+    int* cand_count;           // [N]
+};
+cudaError_t candidates_launch(const PostParams& p, cudaStream_t st);
+
+struct NmsParams {
+    const float* cand_box;
+    const float* cand_score;
+    const int* cand_src;
+    const int* cand_count;
+    uint8_t* scratch;
+    size_t scratch_stride;
+    int cap, cap_pow2, C, class_agnostic;
+    float iou_thr;
+    float* out_dets;           // [N][cap][5]
+    int* out_label;            // [N][cap]
+    int* out_src;              // [N][cap]
+    int* out_count;            // [N]
+    int* overflow;             // single flag
+};
+size_t nms_scratch_stride(int cap, int cap_pow2);
+cudaError_t nms_launch(const NmsParams& p, int n_images, cudaStream_t st);
+
+struct AssignParams {
+    LevelTable lv;
+    const float* gt_boxes;     // [N][gmax][4] xywh
+    const int* gt_labels;      // [N][gmax]
+    const int* gt_count;       // [N]
+    int N, P, C, gmax, assign_mode, independent;
+    float* cls_target;         // [N][P][C]
+    float* reg_target;         // [N][P][4]
+    int* label;                // [N][P]  -1 ignore, C background
+    int* counters;             // [0] n_pos, [1] n_valid  (zeroed by the caller)
+};
+cudaError_t assign_targets_launch(const AssignParams& p, cudaStream_t st);
+
+cudaError_t focal_forward_launch(const float* logits, const long long* targets, int M, int C, float gamma, float alpha,
+                                 float* losses, cudaStream_t st);
+cudaError_t focal_backward_launch(const float* logits, const long long* targets, const float* d_losses, int M, int C,
+                                  float gamma, float alpha, float* d_logits, cudaStream_t st);
+
+struct ClsLossParams {
+    const float* logits;       // (N, P, C')
+    const int* label;
+    const int* counters;
+    float* grad;               // (N, P, C') or null
+    double* loss_sum;          // zeroed by the caller
+    int N, P, C, cls_mode;
+    float gamma, alpha, loss_weight;
+};
+cudaError_t cls_loss_launch(const ClsLossParams& p, int num_sms, cudaStream_t st);
+
+struct RegLossParams {
+    LevelTable lv;
+    const float* reg;          // (N, P, 4) raw outputs
+    const float* reg_target;
+    const int* label;
+    const int* counters;
+    float* grad;
+    double* loss_sum;
+    int N, P, C, bbox_mode;
+    float eps, loss_weight;
+};
+cudaError_t iou_loss_launch(const RegLossParams& p, int num_sms, cudaStream_t st);
+
+}  // namespace lfd

@@ -1,0 +1,246 @@
+// postprocess.cu -- score (sigmoid | softmax) + threshold + distance->box decode + class-aware greedy NMS.
+//
+// Replaces lfd/model/lfd.py:434-509 (`_get_results_for_single_image`), :577-641 (predict path),
+// lfd/model/utils/nms.py:119-220 (`batched_nms`, `multiclass_nms`) and the native
+// lfd/model/utils/build/nms/src/{cpu/nms_cpu.cpp:8-66, cuda/nms_kernel.cu:24-138}.
+// The reference's CUDA NMS copies an n x n/64 bitmask to the host and sweeps it on the CPU
+// (nms_kernel.cu:104-131); here everything stays on the device:
+//   candidates_kernel : one thread per point -- scores, strict `> thr` filter, decode, clamp, /resize_scale,
+//                       warp-aggregated append to the image's candidate list.
+//   nms_kernel        : one CTA per image, warp-cooperative -- class offsets (label * (max_coord + 1), added in
+//                       fp32 exactly like nms.py:145-150), bitonic sort by (score desc, source index asc),
+//                       greedy sweep with strict `iou > thr`, IoU without +1 / epsilon; writes kept rows in
+//                       score-descending order.
+// Arithmetic that decides kept indices is written with explicit _rn intrinsics so that nvcc cannot contract
+// it into FMAs (the reference computes every step in separately rounded fp32).
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace lfd {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 32-bit key that sorts ASCENDING when the float sorts DESCENDING (total order incl. negatives)
+__device__ __forceinline__ uint32_t desc_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ~u;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) candidates_kernel(const PostParams p) {
+    const int n = blockIdx.y;
+    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = pt < p.P;
+    int level = 0, local = 0;
+    if (active) {
+        for (int l = 1; l < p.num_levels; ++l)
+            if (pt >= p.level_off[l]) level = l;
+        local = pt - p.level_off[level];
+    }
+    float box[4] = {0, 0, 0, 0};
+    bool decoded = false;
+    const float* cls = p.cls + ((size_t)n * p.P + (active ? pt : 0)) * p.cls_stride;
+    float smax = 0.f, sden = 1.f;
+    if (active && p.cls_mode == 1) {  // softmax over C+1 logits, background (last) dropped (lfd.py:450-452)
+        smax = cls[0];
+        for (int c = 1; c <= p.C; ++c) smax = fmaxf(smax, cls[c]);
+        sden = 0.f;
+        for (int c = 0; c <= p.C; ++c) sden += expf(cls[c] - smax);
+    }
+    for (int c = 0; c < p.C; ++c) {
+        float score = 0.f;
+        bool pass = false;
+        if (active) {
+            score = p.cls_mode == 1 ? expf(cls[c] - smax) / sden : sigmoid_f(cls[c]);
+            pass = score > p.score_thr;
+        }
+        if (pass && !decoded) {
+            const float4 r = *reinterpret_cast<const float4*>(p.reg + ((size_t)n * p.P + pt) * 4);
+            const int W = p.level_w[level];
+            const float px = (float)((local % W) * p.level_stride[level]);
+            const float py = (float)((local / W) * p.level_stride[level]);
+            float d[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (p.bbox_mode == 0) d[k] = __fmul_rn(sigmoid_f(d[k]), p.level_hi[level]);   // lfd.py:481-486
+                else if (p.bbox_mode == 1) d[k] = expf(d[k]);                                  // :478-480
+                else d[k] = __fmul_rn(d[k], p.level_hi[level]);                                // 'independent' :468-476
+            }
+            const float iw = p.img_w[n], ih = p.img_h[n], rs = p.resize_scale[n];
+            box[0] = __fdiv_rn(fminf(fmaxf(__fsub_rn(px, d[0]), 0.f), iw), rs);
+            box[1] = __fdiv_rn(fminf(fmaxf(__fsub_rn(py, d[1]), 0.f), ih), rs);
+            box[2] = __fdiv_rn(fminf(fmaxf(__fadd_rn(px, d[2]), 0.f), iw), rs);
+            box[3] = __fdiv_rn(fminf(fmaxf(__fadd_rn(py, d[3]), 0.f), ih), rs);
+            decoded = true;
+        }
+        // warp-aggregated slot claim
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.cand_count + n, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (pass) {
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                if (slot < p.cap) {
+                    const size_t o = (size_t)n * p.cap + slot;
+                    reinterpret_cast<float4*>(p.cand_box)[o] = make_float4(box[0], box[1], box[2], box[3]);
+                    p.cand_score[o] = score;
+                    p.cand_src[o] = pt * p.C + c;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One CTA per image.
+//   cand_*   : unsorted candidates (count K, K <= cap)
+//   scratch  : per image  [cap_pow2] u64 keys | [cap_pow2] u32 payload | [cap] float4 sorted boxes | [cap] u8 flags
+//   outputs  : dets [cap][5], labels [cap], src [cap] (index into the (point, class) grid, or the input row for
+//              raw mode), count
+static constexpr int kNmsThreads = 1024;
+static constexpr int kNmsSmemSort = 4096;   // candidates sortable / sweepable entirely in shared memory
+
+__device__ __forceinline__ float iou_ref(const float4 a, const float aa, const float4 b, const float ab) {
+    const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));  // nms_cpu.cpp:57-61
+}
+
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
+    extern __shared__ __align__(16) uint8_t nsm[];
+    __shared__ float s_red[32];
+    __shared__ int s_keep;
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    int K = p.cand_count[n];
+    if (K > p.cap) {  // capacity overflow: report, process the first cap (host turns this into an error)
+        if (tid == 0) atomicExch(p.overflow, 1);
+        K = p.cap;
+    }
+    if (K == 0) {
+        if (tid == 0) p.out_count[n] = 0;
+        return;
+    }
+    int Kp = 1;
+    while (Kp < K) Kp <<= 1;
+    const bool in_smem = Kp <= kNmsSmemSort;
+    uint8_t* gscr = p.scratch + (size_t)n * p.scratch_stride;
+    unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(nsm)
+                                       : reinterpret_cast<unsigned long long*>(gscr);
+    uint32_t* pay = in_smem ? reinterpret_cast<uint32_t*>(nsm + (size_t)kNmsSmemSort * 8)
+                            : reinterpret_cast<uint32_t*>(gscr + (size_t)p.cap_pow2 * 8);
+    float4* sbox = in_smem ? reinterpret_cast<float4*>(nsm + (size_t)kNmsSmemSort * 12)
+                           : reinterpret_cast<float4*>(gscr + (size_t)p.cap_pow2 * 12);
+    uint8_t* removed = in_smem ? nsm + (size_t)kNmsSmemSort * 28 : gscr + (size_t)p.cap_pow2 * 12 + (size_t)p.cap * 16;
+    const float4* cbox = reinterpret_cast<const float4*>(p.cand_box) + (size_t)n * p.cap;
+    const float* cscore = p.cand_score + (size_t)n * p.cap;
+    const int* csrc = p.cand_src + (size_t)n * p.cap;
+
+    // 1. max coordinate over the candidate boxes (nms.py:148 `bboxes.max()`)
+    float mx = -3.4e38f;
+    if (!p.class_agnostic) {
+        for (int i = tid; i < K; i += kNmsThreads) {
+            const float4 b = cbox[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+        }
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+        __syncthreads();
+        mx = s_red[0];
+        for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
+    }
+    const float offmul = __fadd_rn(mx, 1.0f);
+
+    // 2. sort keys: score descending, source index ascending (deterministic total order)
+    for (int i = tid; i < Kp; i += kNmsThreads) {
+        unsigned long long k = ~0ull;
+        if (i < K) k = ((unsigned long long)desc_key(cscore[i]) << 32) | (unsigned)csrc[i];
+        keys[i] = k;
+        pay[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int size = 2; size <= Kp; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (Kp >> 1); i += kNmsThreads) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b; keys[hi] = a;
+                    const uint32_t t = pay[lo]; pay[lo] = pay[hi]; pay[hi] = t;
+                }
+            }
+            __syncthreads();
+        }
+
+    // 3. sorted, class-offset boxes
+    for (int i = tid; i < K; i += kNmsThreads) {
+        const int s = (int)pay[i];
+        float4 b = cbox[s];
+        if (!p.class_agnostic) {
+            const float off = __fmul_rn((float)(csrc[s] % p.C), offmul);
+            b.x = __fadd_rn(b.x, off); b.y = __fadd_rn(b.y, off); b.z = __fadd_rn(b.z, off); b.w = __fadd_rn(b.w, off);
+        }
+        sbox[i] = b;
+        removed[i] = 0;
+    }
+    if (tid == 0) s_keep = 0;
+    __syncthreads();
+
+    // 4. greedy sweep (whole CTA in lock step; `removed` is only written between barriers)
+    for (int i = 0; i < K; ++i) {
+        if (removed[i]) continue;  // uniform
+        const float4 bi = sbox[i];
+        const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+        if (tid == 0) {
+            const int k = s_keep++;
+            const int s = (int)pay[i];
+            const int src = csrc[s];
+            float4 ob = bi;
+            if (!p.class_agnostic) {  // nms.py:155 subtracts the offsets again (fp32 round trip kept)
+                const float off = __fmul_rn((float)(src % p.C), offmul);
+                ob.x = __fsub_rn(ob.x, off); ob.y = __fsub_rn(ob.y, off); ob.z = __fsub_rn(ob.z, off); ob.w = __fsub_rn(ob.w, off);
+            }
+            float* d = p.out_dets + ((size_t)n * p.cap + k) * 5;
+            d[0] = ob.x; d[1] = ob.y; d[2] = ob.z; d[3] = ob.w; d[4] = cscore[s];
+            p.out_label[(size_t)n * p.cap + k] = src % p.C;
+            p.out_src[(size_t)n * p.cap + k] = src;
+        }
+        for (int j = i + 1 + tid; j < K; j += kNmsThreads) {
+            if (removed[j]) continue;
+            const float4 bj = sbox[j];
+            const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+            if (iou_ref(bi, ai, bj, aj) > p.iou_thr) removed[j] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) p.out_count[n] = s_keep;
+}
+
+cudaError_t candidates_launch(const PostParams& p, cudaStream_t st) {
+    candidates_kernel<<<dim3((p.P + 255) / 256, p.N), 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+size_t nms_scratch_stride(int cap, int cap_pow2) {
+    size_t s = (size_t)cap_pow2 * 12 + (size_t)cap * 16 + (size_t)cap;
+    return (s + 255) & ~(size_t)255;
+}
+
+cudaError_t nms_launch(const NmsParams& p, int n_images, cudaStream_t st) {
+    const size_t smem = (size_t)kNmsSmemSort * 29 + 16;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    nms_kernel<<<n_images, kNmsThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace lfd

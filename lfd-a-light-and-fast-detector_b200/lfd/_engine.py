@@ -1,0 +1,370 @@
+# -*- coding: utf-8 -*-
+"""Layer-plan builder: walks an lfd.model.LFD module tree once per (batch, height, width), folds BatchNorm
+into per-channel scale/shift, packs conv weights into the tcgen05 kernel's operand order, lays the bf16 NHWC
+activations out in one workspace with liveness-based reuse, and hands the op list to liblfd_b200.so
+(lfd_plan_create / lfd_plan_forward).
+
+Replaces the module-by-module execution of LFD.forward (reference lfd/model/lfd.py:511-542).
+
+Rounding points of the bf16 pipeline (mirrored by oracle/lfd_oracle.py forward(emulate_bf16=True)):
+  R0  the input image is rounded to bf16 when the stem kernel loads it;
+  Rw  every conv weight is rounded to bf16 (BatchNorm scale/shift, biases, Scale stay fp32 and are applied
+      to the fp32 accumulator in the epilogue);
+  Ra  every fused layer output (after scale/shift, residual add, ReLU) is stored as bf16;
+  Rg  GroupNorm statistics are taken over the stored (bf16) tensor, the normalised+ReLU'd value is rounded
+      to bf16 again; the final cls / reg outputs are fp32.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+
+BN_TYPES = (nn.BatchNorm2d,)
+
+
+def _conv_out(size, k, s):
+    return (size + 2 * (k // 2) - k) // s + 1
+
+
+class _Arena(object):
+    """First-fit allocator with coalescing free list over one workspace (byte offsets, 256 B aligned)."""
+
+    def __init__(self, base=0):
+        self.top = base
+        self.free = []  # (off, size)
+
+    def alloc(self, size):
+        size = (size + 255) & ~255
+        best = None
+        for i, (o, s) in enumerate(self.free):
+            if s >= size and (best is None or s < self.free[best][1]):
+                best = i
+        if best is not None:
+            o, s = self.free.pop(best)
+            if s > size:
+                self.free.append((o + size, s - size))
+            return o
+        o = self.top
+        self.top += size
+        return o
+
+    def release(self, off, size):
+        size = (size + 255) & ~255
+        self.free.append((off, size))
+        self.free.sort()
+        merged = []
+        for o, s in self.free:
+            if merged and merged[-1][0] + merged[-1][1] == o:
+                merged[-1] = (merged[-1][0], merged[-1][1] + s)
+            else:
+                merged.append((o, s))
+        self.free = merged
+
+
+class InferencePlan(object):
+    """One native forward plan for a fixed input shape."""
+
+    def __init__(self, model, N, H, W, device, conv_impl=nat.CONV_UMMA):
+        self.N, self.H, self.W = N, H, W
+        self.device = device
+        self.conv_impl = conv_impl
+        self._f32, self._bf16 = [], []      # parameter staging (host tensors, concatenated at the end)
+        self._f32_n, self._bf16_n = 0, 0
+        self._ops = []                       # dicts; tensors referenced by name
+        self._tensors = {}                   # name -> bytes
+        self._build(model)
+        self._finalize()
+
+    # ------------------------------------------------------------------ parameter staging
+    def _add_f32(self, t):
+        t = t.detach().float().reshape(-1).cpu()
+        off = self._f32_n
+        self._f32.append(t)
+        self._f32_n += (t.numel() + 3) // 4 * 4
+        if t.numel() % 4:
+            self._f32.append(torch.zeros(4 - t.numel() % 4))
+        return off
+
+    def _add_bf16(self, t):
+        t = t.detach().to(torch.bfloat16).reshape(-1).cpu()
+        off = self._bf16_n
+        self._bf16.append(t)
+        self._bf16_n += (t.numel() + 7) // 8 * 8
+        if t.numel() % 8:
+            self._bf16.append(torch.zeros(8 - t.numel() % 8, dtype=torch.bfloat16))
+        return off
+
+    @staticmethod
+    def _fold(conv, norm):
+        """-> per-output-channel (scale, shift) fp32 such that y = conv_nobias(x) * scale + shift."""
+        cout = conv.out_channels
+        bias = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(cout)
+        if norm is None:
+            return torch.ones(cout), bias
+        if not isinstance(norm, BN_TYPES):
+            raise NotImplementedError('only BatchNorm2d can be folded into a conv epilogue (got %s)' % type(norm).__name__)
+        if norm.training and norm.track_running_stats is False:
+            raise NotImplementedError('BatchNorm2d without running statistics is not supported by the inference plan')
+        g = norm.weight.detach().float().cpu() if norm.weight is not None else torch.ones(cout)
+        b = norm.bias.detach().float().cpu() if norm.bias is not None else torch.zeros(cout)
+        scale = g / torch.sqrt(norm.running_var.detach().float().cpu() + norm.eps)
+        shift = b - norm.running_mean.detach().float().cpu() * scale + bias * scale
+        return scale, shift
+
+    def _tensor(self, name, n, h, w, c):
+        self._tensors[name] = n * h * w * c * 2
+        return name
+
+    # ------------------------------------------------------------------ op emitters
+    def _emit_stem0(self, conv, norm, relu, out_name, h, w):
+        if conv.in_channels != 3 or conv.kernel_size != (3, 3) or conv.stride != (2, 2):
+            raise NotImplementedError('the B200 stem kernel handles the 3x3/s2 conv on a 3-channel image only')
+        ho, wo = _conv_out(h, 3, 2), _conv_out(w, 3, 2)
+        scale, shift = self._fold(conv, norm)
+        wt = conv.weight.detach().float().cpu().to(torch.bfloat16).float()   # [Cout, 3, 3, 3] rounded (Rw)
+        wt = wt.permute(2, 3, 1, 0).reshape(27, conv.out_channels)           # k = (kh*3+kw)*3 + ci
+        self._ops.append(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
+                              relu=int(relu), out=self._tensor(out_name, self.N, ho, wo, conv.out_channels),
+                              w_f32=self._add_f32(wt), scale=self._add_f32(scale), shift=self._add_f32(shift)))
+        return ho, wo
+
+    def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None):
+        k, s = conv.kernel_size[0], conv.stride[0]
+        if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or s not in (1, 2) or conv.padding[0] != k // 2 \
+                or conv.groups != 1 or conv.dilation != (1, 1):
+            raise NotImplementedError('unsupported conv geometry for the B200 kernels: %r' % (conv,))
+        cin, cout = conv.in_channels, conv.out_channels
+        ho, wo = _conv_out(h, k, s), _conv_out(w, k, s)
+        q = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s)
+        cc = q['cc']
+        key = (id(conv), id(norm), cc)
+        if cache is not None and key in cache:
+            w_off, sc_off, sh_off = cache[key]
+        else:
+            if gn_groups:
+                if conv.bias is not None:
+                    raise NotImplementedError('conv followed by GroupNorm is expected to have no bias')
+                scale, shift = torch.ones(cout), torch.zeros(cout)
+            else:
+                scale, shift = self._fold(conv, norm)
+            wt = conv.weight.detach().float().cpu()                      # [Cout, Cin, k, k]
+            wt = wt.permute(2, 3, 1, 0).reshape(k * k, cin // cc, cc // 8, 8, cout)
+            wt = wt.permute(1, 0, 2, 4, 3).contiguous()                 # [cc][tap][kc][Cout][8]
+            w_off, sc_off, sh_off = self._add_bf16(wt), self._add_f32(scale), self._add_f32(shift)
+            if cache is not None:
+                cache[key] = (w_off, sc_off, sh_off)
+        op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
+                  gn_groups=gn_groups, cc=cc, inp=in_name, out=self._tensor(out_name, self.N, ho, wo, cout), res=res,
+                  w_bf16=w_off, scale=sc_off, shift=sh_off, query=q)
+        if gn_groups:
+            op['stats'] = len([o for o in self._ops if o.get('stats') is not None and o['kind'] == nat.OP_CONV])
+        self._ops.append(op)
+        return ho, wo
+
+    # ------------------------------------------------------------------ graph walk
+    def _build(self, model):
+        bb, neck, head = model._backbone, model._neck, model._head
+        h, w = self.H, self.W
+        cur = None
+        for i, (conv, norm, relu) in enumerate(bb.stem_layers()):
+            name = 'stem%d' % i
+            if i == 0:
+                h, w = self._emit_stem0(conv, norm, relu, name, h, w)
+            else:
+                h, w = self._emit_conv(conv, norm, relu, cur, name, h, w)
+            cur = name
+        feats = []
+        taps = list(bb._out_indices)
+        for si, stage in enumerate(bb.stages()):
+            for bi, block in enumerate(stage):
+                base = 's%db%d' % (si, bi)
+                identity = cur
+                if block._downsample is not None:
+                    ds = list(block._downsample)
+                    self._emit_conv(ds[0], ds[1] if len(ds) > 1 else None, False, cur, base + '_id', h, w)
+                    identity = base + '_id'
+                pairs = block.conv_norm_pairs()
+                x, hh, ww = cur, h, w
+                for li, (conv, norm) in enumerate(pairs):
+                    last = li == len(pairs) - 1
+                    name = base + ('_out' if last else '_c%d' % li)
+                    hh, ww = self._emit_conv(conv, norm, True, x, name, hh, ww, res=identity if last else None)
+                    x = name
+                cur, h, w = x, hh, ww
+                if (si, bi) in taps:
+                    feats.append((cur, h, w))
+        if len(feats) != head._num_heads:
+            raise ValueError('backbone taps (%d) and head levels (%d) differ' % (len(feats), head._num_heads))
+        self.level_sizes = [(fh, fw) for (_, fh, fw) in feats]
+        self.P = sum(fh * fw for (fh, fw) in self.level_sizes)
+        self.cls_channels = head.num_cls_channels
+        if not isinstance(make_norm_probe(head), nn.GroupNorm):
+            raise NotImplementedError('the B200 head kernels implement the GroupNorm towers of the shipped configs')
+        cache = {}
+        point_off = 0
+        for l, (fname, fh, fw) in enumerate(feats):
+            conv, norm = neck.level(l)
+            nk = 'neck%d' % l
+            self._emit_conv(conv, norm, True, fname, nk, fh, fw)
+            cls_tower, reg_tower, fin_cls, fin_reg = head.level_paths(l)
+            scale_l = float(head._scales[l]._scale.detach()) if head.uses_scale else 1.0
+
+            def run_tower(tower, tag):
+                x = nk
+                for ti, (tconv, tnorm) in enumerate(tower):
+                    if tconv.kernel_size != (1, 1):
+                        raise NotImplementedError('head towers with conv_kernel_size=3 are outside the implemented hot path')
+                    if not isinstance(tnorm, nn.GroupNorm) or tnorm.num_channels != tnorm.num_groups * 8:
+                        raise NotImplementedError('head towers need GroupNorm with 8 channels per group')
+                    raw = 'h%d%s_raw%d' % (l, tag, ti)
+                    self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
+                    stats_id = self._ops[-1]['stats']
+                    if ti == len(tower) - 1:
+                        return raw, stats_id, tnorm
+                    act = 'h%d%s_act%d' % (l, tag, ti)
+                    self._ops.append(dict(kind=nat.OP_GN_APPLY, H=fh, W=fw, Cin=tconv.out_channels, Ho=fh, Wo=fw,
+                                          Cout=tconv.out_channels, gn_groups=tnorm.num_groups, inp=raw,
+                                          out=self._tensor(act, self.N, fh, fw, tconv.out_channels), stats=stats_id,
+                                          gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
+                                          beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias)))
+                    x = act
+                raise ValueError('head tower without conv layers is not supported')
+
+            def final(raw, stats_id, tnorm, convs, n_cls, n_reg):
+                ws, scs, shs = [], [], []
+                for (fc, sc) in convs:
+                    ws.append(fc.weight.detach().float().cpu().reshape(fc.out_channels, -1).to(torch.bfloat16).float())
+                    b = fc.bias.detach().float().cpu() if fc.bias is not None else torch.zeros(fc.out_channels)
+                    scs.append(torch.full((fc.out_channels,), sc))
+                    shs.append(b * sc)
+                self._ops.append(dict(kind=nat.OP_HEAD_FINAL, H=fh, W=fw, Cin=ws[0].shape[1], Ho=fh, Wo=fw, Cout=n_cls + n_reg,
+                                      gn_groups=tnorm.num_groups, inp=raw, stats=stats_id, n_cls=n_cls, n_reg=n_reg,
+                                      point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
+                                      scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
+                                      gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
+                                      beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias)))
+
+            if cls_tower is reg_tower:
+                raw, sid, tn = run_tower(cls_tower, 'm')
+                final(raw, sid, tn, [(fin_cls, 1.0), (fin_reg, scale_l)], fin_cls.out_channels, 4)
+            else:
+                raw, sid, tn = run_tower(cls_tower, 'c')
+                final(raw, sid, tn, [(fin_cls, 1.0)], fin_cls.out_channels, 0)
+                raw, sid, tn = run_tower(reg_tower, 'r')
+                final(raw, sid, tn, [(fin_reg, scale_l)], 0, 4)
+            point_off += fh * fw
+
+    def _cached_f32(self, cache, key, t):
+        if key not in cache:
+            cache[key] = self._add_f32(t)
+        return cache[key]
+
+    # ------------------------------------------------------------------ memory plan + native plan
+    def _finalize(self):
+        dev = self.device
+        self.params_f32 = torch.cat(self._f32).to(dev) if self._f32 else torch.zeros(4, device=dev)
+        self.params_bf16 = torch.cat(self._bf16).to(dev) if self._bf16 else torch.zeros(8, dtype=torch.bfloat16, device=dev)
+        self._f32, self._bf16 = None, None
+        n_stats = len([o for o in self._ops if o['kind'] == nat.OP_CONV and o.get('gn_groups')])
+        stats_each = self.N * 16 * 2 * 8
+        self.stats_bytes = (n_stats * stats_each + 255) & ~255
+        arena = _Arena(base=self.stats_bytes)
+        last_use = {}
+        for i, op in enumerate(self._ops):
+            for k in ('inp', 'res'):
+                if op.get(k) is not None:
+                    last_use[op[k]] = i
+        offsets = {}
+        for i, op in enumerate(self._ops):
+            if op.get('out') is not None:
+                offsets[op['out']] = arena.alloc(self._tensors[op['out']])
+            for name, lu in list(last_use.items()):
+                if lu == i:
+                    arena.release(offsets[name], self._tensors[name])
+                    del last_use[name]
+            if op.get('out') is not None and op['out'] not in last_use:
+                # produced but never consumed by a later op (cannot happen for a well-formed graph) -- keep it
+                pass
+        self.workspace_bytes = max(arena.top, 256)
+        self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=dev)
+        self.activation_bytes = sum(self._tensors.values())
+        fb, bb = self.params_f32.data_ptr(), self.params_bf16.data_ptr()
+        arr = (nat.Op * len(self._ops))()
+        for i, op in enumerate(self._ops):
+            o = arr[i]
+            o.kind = op['kind']
+            o.N, o.H, o.W, o.Cin, o.Ho, o.Wo, o.Cout = self.N, op['H'], op['W'], op['Cin'], op['Ho'], op['Wo'], op['Cout']
+            o.ksize, o.stride, o.relu = op.get('ksize', 1), op.get('stride', 1), op.get('relu', 0)
+            o.gn_groups = op.get('gn_groups', 0)
+            o.n_cls, o.n_reg, o.point_off, o.cc = op.get('n_cls', 0), op.get('n_reg', 0), op.get('point_off', 0), op.get('cc', 0)
+            o.in_off = offsets[op['inp']] if op.get('inp') is not None else -1
+            o.out_off = offsets[op['out']] if op.get('out') is not None else -1
+            o.res_off = offsets[op['res']] if op.get('res') is not None else -1
+            o.stats_off = op['stats'] * stats_each if op.get('stats') is not None else -1
+            if 'w_bf16' in op:
+                o.weight = bb + 2 * op['w_bf16']
+            elif 'w_f32' in op:
+                o.weight = fb + 4 * op['w_f32']
+            o.scale = fb + 4 * op['scale'] if 'scale' in op else None
+            o.shift = fb + 4 * op['shift'] if 'shift' in op else None
+            o.gamma = fb + 4 * op['gamma'] if 'gamma' in op else None
+            o.beta = fb + 4 * op['beta'] if 'beta' in op else None
+        self._op_array = arr
+        self.cls_out = torch.empty((self.N, self.P, self.cls_channels), dtype=torch.float32, device=dev)
+        self.reg_out = torch.empty((self.N, self.P, 4), dtype=torch.float32, device=dev)
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            nat.check(nat.lib().lfd_plan_create(arr, len(self._ops), self.N, self.P, self.cls_channels, 0, self.stats_bytes,
+                                                self.workspace_bytes, self.conv_impl, C.byref(handle)))
+        self.handle = handle
+        self.num_launches = nat.lib().lfd_plan_num_launches(handle)
+        self.offsets = offsets
+
+    def forward(self, x, use_graph=True):
+        """x: cuda float32 [N,3,H,W] (contiguous) or uint8 [N,H,W,3].  Returns the plan-owned (cls, reg) buffers."""
+        if x.dtype == torch.float32:
+            fmt, ok = nat.INPUT_F32_NCHW, tuple(x.shape) == (self.N, 3, self.H, self.W)
+        elif x.dtype == torch.uint8:
+            fmt, ok = nat.INPUT_U8_NHWC, tuple(x.shape) == (self.N, self.H, self.W, 3)
+        else:
+            raise TypeError('input must be float32 NCHW or uint8 NHWC, got %s' % (x.dtype,))
+        if not ok or not x.is_cuda or not x.is_contiguous():
+            raise ValueError('input must be a contiguous CUDA tensor matching the plan shape N=%d H=%d W=%d (got %s)'
+                             % (self.N, self.H, self.W, tuple(x.shape)))
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().lfd_plan_forward(self.handle, nat.ptr(x), fmt, nat.ptr(self.workspace), nat.ptr(self.cls_out),
+                                                 nat.ptr(self.reg_out), int(bool(use_graph)), nat.stream_ptr()))
+        return self.cls_out, self.reg_out
+
+    def tensor(self, name):
+        """Debug view of an intermediate activation as NHWC bf16 (valid right after an eager forward only if
+        its buffer has not been reused by a later layer)."""
+        op = [o for o in self._ops if o.get('out') == name][0]
+        n = self.N * op['Ho'] * op['Wo'] * op['Cout']
+        raw = self.workspace[self.offsets[name]: self.offsets[name] + 2 * n]
+        return raw.view(torch.bfloat16).view(self.N, op['Ho'], op['Wo'], op['Cout'])
+
+    def describe(self):
+        names = {nat.OP_STEM0: 'stem0', nat.OP_CONV: 'conv', nat.OP_GN_APPLY: 'gn_apply', nat.OP_HEAD_FINAL: 'head_final'}
+        rows = []
+        for op in self._ops:
+            rows.append(dict(kind=names[op['kind']], H=op['H'], W=op['W'], Cin=op['Cin'], Ho=op['Ho'], Wo=op['Wo'], Cout=op['Cout'],
+                             ksize=op.get('ksize', 1), stride=op.get('stride', 1), res=op.get('res') is not None,
+                             out=op.get('out'), query=op.get('query')))
+        return rows
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                nat.lib().lfd_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def make_norm_probe(head):
+    """First norm module of the head tower (None when the head has no norm)."""
+    tower = head.level_paths(0)[0]
+    return tower[0][1] if tower else None

@@ -1,0 +1,64 @@
+# -*- coding: utf-8 -*-
+import os
+
+import numpy as np
+import torch
+
+import synth
+from oracle import lfd_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def build_model(cfg_name):
+    """The product's drop-in classes, constructed exactly like the reference config scripts do."""
+    from lfd.model.backbone import LFDResNet
+    from lfd.model.neck import SimpleNeck
+    from lfd.model.head import LFDHead
+    from lfd.model.losses import FocalLoss, IoULoss, CrossEntropyLoss
+    from lfd.model import LFD
+    cfg = orc.CONFIGS[cfg_name]
+    bb, hd, lc = cfg['backbone'], cfg['head'], cfg['lfd']
+    cls_loss = FocalLoss(use_sigmoid=True, gamma=2.0, alpha=0.25, reduction='mean', loss_weight=1.0) \
+        if hd['classification_loss_type'] == 'FocalLoss' else CrossEntropyLoss(reduction='mean', loss_weight=1.0)
+    reg_loss = IoULoss(eps=1e-6, reduction='mean', loss_weight=1.0)
+    backbone = LFDResNet(block_mode=bb['block_mode'], stem_mode=bb['stem_mode'], body_mode=None, input_channels=3,
+                         stem_channels=bb['stem_channels'], body_architecture=bb['body_architecture'],
+                         body_channels=bb['body_channels'], out_indices=bb['out_indices'], frozen_stages=-1,
+                         activation_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='BatchNorm2d'),
+                         init_with_weight_file=None, norm_eval=False)
+    neck = SimpleNeck(num_neck_channels=128, num_input_channels_list=backbone.num_output_channels_list,
+                      num_input_strides_list=backbone.num_output_strides_list, norm_cfg=dict(type='BatchNorm2d'),
+                      activation_cfg=dict(type='ReLU', inplace=True))
+    head = LFDHead(num_classes=hd['num_classes'], num_heads=len(neck.num_output_strides_list), num_input_channels=128,
+                   num_head_channels=128, num_conv_layers=2, activation_cfg=dict(type='ReLU', inplace=True),
+                   norm_cfg=dict(type='GroupNorm', num_groups=16), share_head_flag=hd['share_head_flag'],
+                   merge_path_flag=hd['merge_path_flag'], classification_loss_type=type(cls_loss).__name__,
+                   regression_loss_type=type(reg_loss).__name__)
+    return LFD(backbone=backbone, neck=neck, head=head, num_classes=lc['num_classes'], regression_ranges=lc['regression_ranges'],
+               gray_range_factors=lc['gray_range_factors'], range_assign_mode=lc['range_assign_mode'],
+               point_strides=neck.num_output_strides_list, classification_loss_func=cls_loss, regression_loss_func=reg_loss,
+               distance_to_bbox_mode=lc['distance_to_bbox_mode'])
+
+
+def synth_model(cfg_name, cls_bias=-1.0, seed=666):
+    model = build_model(cfg_name)
+    sd = synth.synth_state_dict(model.state_dict(), seed=seed, cls_bias=cls_bias)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, sd
+
+
+def rel_err(a, b):
+    """(max-abs error / max-abs reference, rms error / rms reference)"""
+    a, b = a.double(), b.double()
+    d = (a - b).abs()
+    return float(d.max() / b.abs().max().clamp(min=1e-30)), float(torch.sqrt((d ** 2).mean()) / torch.sqrt((b ** 2).mean()).clamp(min=1e-30))
+
+
+def rows_to_array(rows):
+    return np.asarray(rows, np.float64).reshape(-1, 6)

@@ -95,6 +95,10 @@ int lfd_plan_num_launches(const lfd_plan* plan); /* kernels launched per forward
  * CUDA graph on first use for this (input, workspace, cls_out, reg_out) tuple and replayed afterwards. */
 int lfd_plan_forward(lfd_plan* plan, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
                      int use_graph, lfd_stream stream);
+/* One eager forward with a CUDA event pair around every op: ms_per_op float[lfd_plan_num_launches()] (host).
+ * Synchronises the stream.  Used by bench.py for the live per-kernel roofline. */
+int lfd_plan_profile(lfd_plan* plan, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
+                     float* ms_per_op, lfd_stream stream);
 /* run a single op (tests / debugging) */
 int lfd_run_op(const lfd_op* op, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out, int P,
                int cls_channels, int conv_impl, lfd_stream stream);

@@ -46,14 +46,18 @@ struct lfd_plan {
     std::vector<PlannedOp> ops;
     int N, P, cls_channels, conv_impl;
     int64_t stats_off, stats_bytes, workspace_bytes;
-    // CUDA graph cache
-    cudaGraphExec_t exec;
-    const void* g_input;
-    void* g_ws;
-    float* g_cls;
-    float* g_reg;
-    int g_fmt;
+    // CUDA graph cache: one instantiated graph per (input, workspace, cls, reg, format) pointer tuple
+    struct GraphEntry {
+        cudaGraphExec_t exec;
+        const void* input;
+        void* ws;
+        float* cls;
+        float* reg;
+        int fmt;
+    };
+    std::vector<GraphEntry> graphs;
 };
+static constexpr size_t kMaxGraphs = 32;
 
 extern "C" int lfd_abi_version(void) { return LFD_B200_ABI_VERSION; }
 extern "C" const char* lfd_last_error(void) { return g_err; }
@@ -185,7 +189,6 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
     lfd_plan* pl = new lfd_plan();
     pl->N = N; pl->P = P; pl->cls_channels = cls_channels; pl->conv_impl = conv_impl;
     pl->stats_off = stats_off; pl->stats_bytes = stats_bytes; pl->workspace_bytes = workspace_bytes;
-    pl->exec = nullptr; pl->g_input = nullptr; pl->g_ws = nullptr; pl->g_cls = nullptr; pl->g_reg = nullptr; pl->g_fmt = -1;
     for (int i = 0; i < n_ops; ++i) {
         PlannedOp po;
         int rc = plan_op(ops[i], conv_impl, &po);
@@ -198,7 +201,7 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
 
 extern "C" int lfd_plan_destroy(lfd_plan* plan) {
     if (!plan) return LFD_OK;
-    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
     delete plan;
     return LFD_OK;
 }
@@ -220,35 +223,65 @@ extern "C" int lfd_plan_forward(lfd_plan* pl, const void* input, int input_forma
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
     if (!use_graph) return enqueue_all(pl, input, input_format, ws, cls_out, reg_out, st);
-    const bool hit = pl->exec && pl->g_input == input && pl->g_ws == workspace && pl->g_cls == cls_out && pl->g_reg == reg_out &&
-                     pl->g_fmt == input_format;
-    if (!hit) {
-        if (pl->exec) { cudaGraphExecDestroy(pl->exec); pl->exec = nullptr; }
-        // one eager pass first: sets function attributes outside of capture and surfaces launch errors directly
-        int rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, st);
-        if (rc) return rc;
-        cudaStream_t cap;
-        CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        cudaGraph_t graph = nullptr;
-        CUDA_TRY(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, cap);
-        cudaError_t ce = cudaStreamEndCapture(cap, &graph);
-        if (rc || ce != cudaSuccess) {
-            if (graph) cudaGraphDestroy(graph);
-            cudaStreamDestroy(cap);
-            return rc ? rc : fail(LFD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+    for (auto& g : pl->graphs)
+        if (g.input == input && g.ws == workspace && g.cls == cls_out && g.reg == reg_out && g.fmt == input_format) {
+            CUDA_TRY(cudaGraphLaunch(g.exec, st));
+            return LFD_OK;
         }
-        ce = cudaGraphInstantiate(&pl->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        cudaStreamDestroy(cap);
-        if (ce != cudaSuccess) { pl->exec = nullptr; return fail(LFD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
-        pl->g_input = input; pl->g_ws = workspace; pl->g_cls = cls_out; pl->g_reg = reg_out; pl->g_fmt = input_format;
-        return LFD_OK;  // the eager pass above already produced this call's outputs
+    // first use of this pointer tuple: one eager pass (sets function attributes outside of capture, surfaces launch
+    // errors directly and produces this call's outputs), then capture + instantiate for the following calls
+    int rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, st);
+    if (rc) return rc;
+    if (pl->graphs.size() >= kMaxGraphs) {
+        cudaGraphExecDestroy(pl->graphs.front().exec);
+        pl->graphs.erase(pl->graphs.begin());
     }
-    CUDA_TRY(cudaGraphLaunch(pl->exec, st));
+    cudaStream_t cap;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { cudaStreamDestroy(cap); return fail(LFD_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); }
+    rc = enqueue_all(pl, input, input_format, ws, cls_out, reg_out, cap);
+    ce = cudaStreamEndCapture(cap, &graph);
+    if (rc || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        return rc ? rc : fail(LFD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+    }
+    lfd_plan::GraphEntry e;
+    e.exec = nullptr; e.input = input; e.ws = workspace; e.cls = cls_out; e.reg = reg_out; e.fmt = input_format;
+    ce = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    if (ce != cudaSuccess) return fail(LFD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    pl->graphs.push_back(e);
     return LFD_OK;
 }
+
+extern "C" int lfd_plan_profile(lfd_plan* pl, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
+                                float* ms_per_op, lfd_stream stream) {
+    if (!pl || !input || !workspace || !cls_out || !reg_out || !ms_per_op) return fail(LFD_ERR_INVALID, "lfd_plan_profile: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const size_t n = pl->ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    if (pl->stats_bytes > 0) CUDA_TRY(cudaMemsetAsync(ws + pl->stats_off, 0, (size_t)pl->stats_bytes, st));
+    int rc = LFD_OK;
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    for (size_t i = 0; i < n && !rc; ++i) {
+        rc = launch_op(pl->ops[i], input, input_format, ws, cls_out, reg_out, pl->P, pl->cls_channels, pl->conv_impl, st);
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (!rc && ce == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(LFD_ERR_CUDA, "lfd_plan_profile: %s", cudaGetErrorString(ce));
+    return LFD_OK;
+}
+
 
 extern "C" int lfd_run_op(const lfd_op* op, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
                           int P, int cls_channels, int conv_impl, lfd_stream stream) {

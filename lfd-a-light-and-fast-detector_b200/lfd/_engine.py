@@ -15,6 +15,7 @@ Rounding points of the bf16 pipeline (mirrored by oracle/lfd_oracle.py forward(e
       to bf16 again; the final cls / reg outputs are fp32.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -26,6 +27,14 @@ BN_TYPES = (nn.BatchNorm2d,)
 
 def _conv_out(size, k, s):
     return (size + 2 * (k // 2) - k) // s + 1
+
+
+def pack_conv_weight(weight, cc):
+    """[Cout, Cin, k, k] float -> bf16 [Cin/cc][k*k][cc/8][Cout][8], the B-operand order of conv_umma.cu
+    (K-major, no-swizzle core matrices; one contiguous slice per channel chunk so that it can be bulk-copied)."""
+    cout, cin, k, _ = weight.shape
+    wt = weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(k * k, cin // cc, cc // 8, 8, cout)
+    return wt.permute(1, 0, 2, 4, 3).contiguous().to(torch.bfloat16)
 
 
 class _Arena(object):
@@ -66,8 +75,9 @@ class _Arena(object):
 class InferencePlan(object):
     """One native forward plan for a fixed input shape."""
 
-    def __init__(self, model, N, H, W, device, conv_impl=nat.CONV_UMMA):
+    def __init__(self, model, N, H, W, device, conv_impl=nat.CONV_UMMA, create_native=True):
         self.N, self.H, self.W = N, H, W
+        self.create_native = create_native   # False: host-side planning only (CPU tests of the planner)
         self.device = device
         self.conv_impl = conv_impl
         self._f32, self._bf16 = [], []      # parameter staging (host tensors, concatenated at the end)
@@ -149,10 +159,7 @@ class InferencePlan(object):
                 scale, shift = torch.ones(cout), torch.zeros(cout)
             else:
                 scale, shift = self._fold(conv, norm)
-            wt = conv.weight.detach().float().cpu()                      # [Cout, Cin, k, k]
-            wt = wt.permute(2, 3, 1, 0).reshape(k * k, cin // cc, cc // 8, 8, cout)
-            wt = wt.permute(1, 0, 2, 4, 3).contiguous()                 # [cc][tap][kc][Cout][8]
-            w_off, sc_off, sh_off = self._add_bf16(wt), self._add_f32(scale), self._add_f32(shift)
+            w_off, sc_off, sh_off = self._add_bf16(pack_conv_weight(conv.weight, cc)), self._add_f32(scale), self._add_f32(shift)
             if cache is not None:
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
@@ -281,7 +288,7 @@ class InferencePlan(object):
             if op.get('out') is not None:
                 offsets[op['out']] = arena.alloc(self._tensors[op['out']])
             for name, lu in list(last_use.items()):
-                if lu == i:
+                if lu == i and not os.environ.get('LFD_B200_NO_REUSE'):
                     arena.release(offsets[name], self._tensors[name])
                     del last_use[name]
             if op.get('out') is not None and op['out'] not in last_use:
@@ -314,13 +321,16 @@ class InferencePlan(object):
         self._op_array = arr
         self.cls_out = torch.empty((self.N, self.P, self.cls_channels), dtype=torch.float32, device=dev)
         self.reg_out = torch.empty((self.N, self.P, 4), dtype=torch.float32, device=dev)
+        self.offsets = offsets
+        self.handle = None
+        if not self.create_native:
+            return
         handle = C.c_void_p()
         with torch.cuda.device(dev):
             nat.check(nat.lib().lfd_plan_create(arr, len(self._ops), self.N, self.P, self.cls_channels, 0, self.stats_bytes,
                                                 self.workspace_bytes, self.conv_impl, C.byref(handle)))
         self.handle = handle
         self.num_launches = nat.lib().lfd_plan_num_launches(handle)
-        self.offsets = offsets
 
     def forward(self, x, use_graph=True):
         """x: cuda float32 [N,3,H,W] (contiguous) or uint8 [N,H,W,3].  Returns the plan-owned (cls, reg) buffers."""
@@ -330,6 +340,8 @@ class InferencePlan(object):
             fmt, ok = nat.INPUT_U8_NHWC, tuple(x.shape) == (self.N, self.H, self.W, 3)
         else:
             raise TypeError('input must be float32 NCHW or uint8 NHWC, got %s' % (x.dtype,))
+        if self.handle is None:
+            raise nat.LfdError('this plan was built for host-side inspection only (create_native=False)')
         if not ok or not x.is_cuda or not x.is_contiguous():
             raise ValueError('input must be a contiguous CUDA tensor matching the plan shape N=%d H=%d W=%d (got %s)'
                              % (self.N, self.H, self.W, tuple(x.shape)))

@@ -95,8 +95,9 @@ def bf16r(t):
 class _Net(object):
     """Walks the reference module graph from a state_dict (reference key names)."""
 
-    def __init__(self, cfg, sd, emulate_bf16):
+    def __init__(self, cfg, sd, emulate_bf16, trace=None):
         self.cfg, self.sd, self.emu = cfg, {k: v.detach().float() for k, v in sd.items()}, emulate_bf16
+        self.trace = trace  # optional dict: conv key -> stored NCHW output of that fused layer (debugging aid)
 
     def r(self, t):
         return bf16r(t) if self.emu else t
@@ -124,7 +125,10 @@ class _Net(object):
             y = y + residual
         if relu:
             y = F.relu(y)
-        return self.r(y)
+        y = self.r(y)
+        if self.trace is not None:
+            self.trace[ckey] = y
+        return y
 
     def stem(self, x):
         mode = self.cfg['backbone']['stem_mode']
@@ -171,14 +175,15 @@ class _Net(object):
         return outs
 
     def gn_relu(self, y, key, groups):
-        """nn.GroupNorm + ReLU; statistics from the fp32 conv result, applied to the stored (rounded) value."""
+        """nn.GroupNorm + ReLU.  In emulation mode the statistics are those of the STORED (bf16) conv output, i.e.
+        GroupNorm is applied to the tensor that exists in memory (rounding point Rg)."""
         n, c, h, w = y.shape
-        yg = y.reshape(n, groups, -1).double()
+        ys = self.r(y).reshape(n, groups, -1)
+        yg = ys.double()
         mean = yg.mean(dim=2)
         var = yg.var(dim=2, unbiased=False)
         rstd = (1.0 / torch.sqrt(var + GN_EPS)).float()
         mean = mean.float()
-        ys = self.r(y).reshape(n, groups, -1)
         out = ((ys - mean[:, :, None]) * rstd[:, :, None]).reshape(n, c, h, w)
         out = out * self.sd[key + '.weight'][None, :, None, None] + self.sd[key + '.bias'][None, :, None, None]
         return self.r(F.relu(out))
@@ -189,6 +194,9 @@ class _Net(object):
             y, b = self.conv(x, prefix + '.%d' % (3 * i), 1, 0)
             assert b is None  # bias=False when a norm follows (lfd_head.py:98)
             x = self.gn_relu(y, prefix + '.%d' % (3 * i + 1), hd['gn_groups'])
+            if self.trace is not None:
+                self.trace[prefix + '.%d' % (3 * i) + ':raw'] = self.r(y)
+                self.trace[prefix + '.%d' % (3 * i) + ':act'] = x
         return x
 
     def head_level(self, x, l):
@@ -223,10 +231,10 @@ class _Net(object):
         return torch.cat(cls_list, 1), torch.cat(reg_list, 1), sizes
 
 
-def forward(cfg, state_dict, x, emulate_bf16=False):
+def forward(cfg, state_dict, x, emulate_bf16=False, trace=None):
     """-> (cls [N,P,C'], reg [N,P,4], [(H_l, W_l)])  C' = C (sigmoid/focal) or C+1 (cross entropy)."""
     with torch.no_grad():
-        return _Net(cfg, state_dict, emulate_bf16).forward(x)
+        return _Net(cfg, state_dict, emulate_bf16, trace).forward(x)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,106 @@
+# -*- coding: utf-8 -*-
+"""CPU tests: the C-ABI library loads and exports every declared symbol; host-side planning (op list, weight packing,
+workspace liveness) is sound; entry points fail loudly without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import synth_model
+from lfd import _native as nat
+from lfd._engine import InferencePlan, pack_conv_weight, _Arena
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'lfd_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(lfd_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
+    lib = nat.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.lfd_abi_version() == 1
+
+
+def test_conv_query_is_host_only_and_rejects_unsupported():
+    q = nat.conv_query(8, 90, 160, 64, 90, 160, 64, 3, 1)
+    assert q['cc'] == 64 and q['weights_resident'] == 1 and q['stages'] >= 3 and q['num_tiles'] == 8 * 20 * 6
+    q = nat.conv_query(8, 12, 20, 128, 12, 20, 128, 3, 1)      # 3x3x128x128 weights do not fit: streamed per stage
+    assert q['weights_resident'] == 0 and q['stages'] >= 2 and q['smem_bytes'] <= 227 * 1024
+    q = nat.conv_query(8, 360, 640, 64, 180, 320, 64, 3, 2)
+    assert q['smem_bytes'] <= 227 * 1024 and q['stages'] >= 2
+    with pytest.raises(nat.LfdError):
+        nat.conv_query(1, 8, 8, 24, 8, 8, 64, 3, 1)            # Cin not a multiple of 16
+    with pytest.raises(nat.LfdError):
+        nat.conv_query(1, 8, 8, 64, 8, 8, 64, 5, 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_entry_points_fail_loudly_without_gpu():
+    lib = nat.lib()
+    op = nat.Op()
+    op.kind, op.N, op.H, op.W, op.Cin, op.Ho, op.Wo, op.Cout = nat.OP_GN_APPLY, 1, 4, 4, 128, 4, 4, 128
+    op.gn_groups = 16
+    h = C.c_void_p()
+    rc = lib.lfd_plan_create(C.byref(op), 1, 1, 16, 1, 0, 256, 4096, 0, C.byref(h))
+    assert rc == 2 and b'no CUDA device' in lib.lfd_last_error()
+    rc = lib.lfd_nms(None, 3, 0.5, None, None, C.c_void_p(1), None)
+    assert rc != 0
+    model, _ = synth_model('WIDERFACE_XS')
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 64, 64))
+
+
+def test_pack_conv_weight_layout():
+    cout, cin, k, cc = 32, 64, 3, 32
+    w = torch.arange(cout * cin * k * k, dtype=torch.float32).reshape(cout, cin, k, k) % 251
+    p = pack_conv_weight(w, cc).float()
+    assert tuple(p.shape) == (cin // cc, k * k, cc // 8, cout, 8)
+    for (c, tap, kc, n, j) in [(0, 0, 0, 0, 0), (1, 4, 3, 17, 5), (1, 8, 2, 31, 7), (0, 5, 1, 9, 3)]:
+        ci = c * cc + kc * 8 + j
+        assert p[c, tap, kc, n, j] == w[n, ci, tap // 3, tap % 3]
+
+
+def test_arena_reuses_and_coalesces():
+    a = _Arena(base=512)
+    o1, o2, o3 = a.alloc(1000), a.alloc(3000), a.alloc(100)
+    assert o1 == 512 and o2 == 512 + 1024 and o3 == o2 + 3072
+    a.release(o1, 1000)
+    a.release(o2, 3000)
+    assert a.alloc(4000) == 512          # coalesced block reused
+    assert a.alloc(10) == o3 + 256
+
+
+@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 3 + 2 * 11 + 4 + 5 + 10), ('TT100K_L', 1 + 2 * 12 + 4 + 4 + 16)])
+def test_planner_builds_expected_graph(name, n_conv):
+    model, _ = synth_model(name)
+    plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
+    rows = plan.describe()
+    kinds = [r['kind'] for r in rows]
+    assert kinds[0] == 'stem0' and kinds.count('stem0') == 1
+    assert kinds.count('conv') == n_conv
+    levels = len(plan.level_sizes)
+    merged = name.startswith('WIDERFACE')
+    assert kinds.count('head_final') == (levels if merged else 2 * levels)
+    assert kinds.count('gn_apply') == (levels if merged else 2 * levels)
+    # live ranges never overlap in the workspace
+    ops = plan._ops
+    last_use = {}
+    for i, op in enumerate(ops):
+        for k in ('inp', 'res'):
+            if op.get(k) is not None:
+                last_use[op[k]] = i
+    born = {op['out']: i for i, op in enumerate(ops) if op.get('out') is not None}
+    names = list(born)
+    for a in names:
+        for b in names:
+            if a >= b:
+                continue
+            if born[a] <= last_use.get(b, born[b]) and born[b] <= last_use.get(a, born[a]):   # lifetimes intersect
+                oa, ob = plan.offsets[a], plan.offsets[b]
+                assert oa + plan._tensors[a] <= ob or ob + plan._tensors[b] <= oa, (a, b)
+    assert plan.workspace_bytes < plan.activation_bytes + plan.stats_bytes + 4096

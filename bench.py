@@ -1,0 +1,330 @@
+# -*- coding: utf-8 -*-
+"""bench.py -- images/sec of the LFD hot path (forward + device post-process) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config WIDERFACE_S]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): WIDERFACE-S, 1280x720, batch 8 per GPU, bf16, synthetic frames and synthetic
+weights (tests/synth.py; no network for datasets / checkpoints).  One step = one batch: backbone + neck + head
+(CUDA-graph replay of the layer plan) + score / decode / NMS (lfd_postprocess).  Multi-GPU: the batch dimension
+shards across ranks, one process per GPU, no collective on the inference path (weak scaling: 8 frames per GPU).
+
+Prints ONE JSON line (rank 0).  `value` = images/s with the uint8 frames already resident in HBM; `e2e` = the same
+through StreamingDetector with HOST (pinned) frames in and HOST detections out; `roofline` = the dominant kernel of the
+step timed live with CUDA events; `cpu_baseline` = the oracle port (the reference's PyTorch CPU arithmetic) on a bounded
+sample.  --impl reference times that CPU path as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'lfd-a-light-and-fast-detector_b200'), os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    'WIDERFACE_S': dict(cfg='WIDERFACE_S', N=8, H=720, W=1280, name='WIDERFACE-S inference 1280x720 batch=8 per GPU'),
+    'WIDERFACE_XS': dict(cfg='WIDERFACE_XS', N=1, H=480, W=640, name='WIDERFACE-XS inference 640x480 batch=1'),
+    'TT100K_L': dict(cfg='TT100K_L', N=16, H=1080, W=1920, name='TT100K LFD_L inference 1920x1080 batch=16 per GPU'),
+}
+POOL = 8          # device-resident input batches rotated through (8 x 22 MB = 177 MB > 126 MB L2)
+IOU_THR = 0.3     # WIDERFACE_train/predict.py:22
+PASS_FRACTION = 0.005
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d['hbm_gbs']), bf16_tflops=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def op_algorithmic(row, N, input_bytes_per_px):
+    """(bytes, flops) one launch must move / compute: input once, output once, residual once, weights once."""
+    k, cin, cout = row['ksize'], row['Cin'], row['Cout']
+    px_in, px_out = N * row['H'] * row['W'], N * row['Ho'] * row['Wo']
+    if row['kind'] == 'stem0':
+        return px_in * input_bytes_per_px + px_out * cout * 2 + 27 * cout * 2, 2.0 * px_out * cout * 27
+    if row['kind'] == 'conv':
+        b = px_in * cin * 2 + px_out * cout * 2 * (2 if row['res'] else 1) + k * k * cin * cout * 2
+        return b, 2.0 * px_out * cout * cin * k * k
+    if row['kind'] == 'gn_apply':
+        return px_in * cin * 2 * 2, 0.0
+    return px_in * cin * 2 + px_out * cout * 4, 2.0 * px_out * cout * cin   # head_final
+
+
+def build_model(cfg_name):
+    from helpers import synth_model
+    model, sd = synth_model(cfg_name, cls_bias=-1.0)
+    return model, sd
+
+
+def cpu_leg(wl, sd, steps, warmup, frames_per_step, budget_s=25.0):
+    """The reference's CPU arithmetic (oracle port: same ATen conv / norm calls as the reference modules, fp32) +
+    oracle decode + NMS (the reference's own compiled nms_cpu.cpp from oracle/_ref when present)."""
+    import synth
+    from oracle import lfd_oracle as orc
+    cfg = orc.CONFIGS[wl['cfg']]
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = synth.synth_input(frames_per_step, wl['H'], wl['W'])
+    meta = [dict(resized_height=wl['H'], resized_width=wl['W'], resize_scale=1.0) for _ in range(frames_per_step)]
+
+    def step():
+        cls, reg, sizes = orc.forward(cfg, sd, x)
+        thr = float(torch.quantile(cls.sigmoid().flatten()[:200000], 1.0 - PASS_FRACTION)) if cfg['head']['classification_loss_type'] == 'FocalLoss' else 0.1
+        orc.get_results(cfg, cls, reg, sizes, meta, thr, IOU_THR)
+    for _ in range(warmup):
+        step()
+    t0 = time.time()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.time() - t0 > budget_s and done >= 2:
+            break
+    dt = time.time() - t0
+    return frames_per_step * done / dt, dt / done * 1e3, done
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='WIDERFACE_S', choices=sorted(WORKLOADS))
+    ap.add_argument('--conv-impl', default='umma', choices=['umma', 'simt'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-ops', action='store_true', help='print the per-op timing table to stderr')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.config]
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    warmup = max(args.warmup, 3)
+    metric = 'images/sec %s bf16' % wl['name']
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        model, sd = build_model(wl['cfg'])
+        frames = wl['N']
+        ips, ms, done = cpu_leg(wl, sd, args.steps, min(warmup, 1), frames, budget_s=150.0)
+        cores = torch.get_num_threads()
+        line = dict(metric=metric, value=ips, unit='images/s', n_gpus=args.gpus, steps=done, warmup=min(warmup, 1), ms_per_step=ms,
+                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                    config=dict(workload=wl['name'], note='CPU path of the reference (PyTorch fp32 forward + decode + CPU NMS) via the oracle port'),
+                    cpu_baseline=dict(value=ips, unit='images/s', cores=cores, kind='port', sample='%d frames per step, %d steps' % (frames, done)),
+                    e2e=dict(value=ips, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback for the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from lfd import _native as nat
+    from lfd.pipeline import StreamingDetector
+    import synth
+    model, sd = build_model(wl['cfg'])
+    model.to(dev)
+    model.conv_impl = nat.CONV_SIMT if args.conv_impl == 'simt' else nat.CONV_UMMA
+    model.use_cuda_graph = not args.no_graph
+    N, H, W = wl['N'], wl['H'], wl['W']
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(POOL)]
+    plan = model.inference_plan(N, H, W, dev)
+    for i, hw in enumerate(plan.level_sizes):
+        model._head_indexes_to_feature_map_sizes[i] = hw
+    post = model.post_plan(N, plan.level_sizes, dev)
+    post.set_meta([W] * N, [H] * N, [1.0] * N)
+    with torch.no_grad():
+        cls, _ = plan.forward(pool[0], use_graph=False)
+        scores = cls.sigmoid() if plan.cls_channels == model._num_classes else cls.softmax(-1)[..., :-1]
+        score_thr = float(torch.quantile(scores.flatten()[:2000000].float(), 1.0 - PASS_FRACTION))
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        c, r = plan.forward(pool[i % POOL], use_graph=model.use_cuda_graph)
+        post.run(c, r, score_thr, IOU_THR)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(warmup, POOL)):   # also instantiates one graph per pool buffer
+            step(i)
+        sync_all()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+        sync_all()
+        ms_total = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        counts = post.count.tolist()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host frames in, host detections out, copies inside the timed region
+    det = StreamingDetector(model, N, H, W, score_thr, IOU_THR, max_out=1024, device=dev)
+    with torch.no_grad():
+        for i in range(3):
+            det.infer(host_pool[i % 2])
+        sync_all()
+        t0 = time.perf_counter()
+        pending = None
+        for i in range(args.steps):
+            slot = det.submit(host_pool[i % 2])
+            if pending is not None:
+                det.collect(pending)
+            pending = slot
+        out = det.collect(pending)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * args.steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return 0
+
+    # ---- live per-op roofline (eager pass with an event pair around every launch)
+    pk = peaks()
+    n_ops = plan.num_launches
+    acc = np.zeros(n_ops, np.float64)
+    buf = (C.c_float * n_ops)()
+    reps = 5
+    with torch.no_grad():
+        for rep in range(reps + 1):
+            nat.check(nat.lib().lfd_plan_profile(plan.handle, nat.ptr(pool[rep % POOL]), nat.INPUT_U8_NHWC, nat.ptr(plan.workspace),
+                                                 nat.ptr(plan.cls_out), nat.ptr(plan.reg_out), buf, nat.stream_ptr()))
+            if rep:
+                acc += np.frombuffer(buf, dtype=np.float32)
+    per_op_ms = acc / reps
+    rows = plan.describe()
+    table = []
+    for row, ms in zip(rows, per_op_ms):
+        b, f = op_algorithmic(row, N, 3)
+        t_bound = max(b / (pk['hbm_gbs'] * 1e9), f / (pk['bf16_tflops'] * 1e12))
+        table.append(dict(row=row, ms=float(ms), bytes=b, flops=f, t_bound_ms=t_bound * 1e3))
+    table_sorted = sorted(table, key=lambda r: -r['ms'])
+    top = table_sorted[0]
+    hbm_bound = top['bytes'] / (pk['hbm_gbs'] * 1e9) >= top['flops'] / (pk['bf16_tflops'] * 1e12)
+    if hbm_bound:
+        achieved, peak, unit = top['bytes'] / (top['ms'] * 1e-3) / 1e9, pk['hbm_gbs'], 'GB/s'
+    else:
+        achieved, peak, unit = top['flops'] / (top['ms'] * 1e-3) / 1e12, pk['bf16_tflops'], 'TFLOP/s'
+    sum_ms = float(per_op_ms.sum())
+    conv_ms = float(sum(r['ms'] for r in table if r['row']['kind'] == 'conv'))
+    net_bound_ms = float(sum(r['t_bound_ms'] for r in table))
+    total_bytes, total_flops = sum(r['bytes'] for r in table), sum(r['flops'] for r in table)
+    roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=None,
+                    peak_source=pk['source'],
+                    kernel='%s %dx%d/s%d %d->%d @%dx%d' % (top['row']['kind'], top['row']['ksize'], top['row']['ksize'], top['row']['stride'],
+                                                           top['row']['Cin'], top['row']['Cout'], top['row']['Ho'], top['row']['Wo']),
+                    kernel_ms=top['ms'], kernel_share_of_step=top['ms'] / sum_ms, algorithmic_bytes=top['bytes'], algorithmic_flops=top['flops'],
+                    net=dict(layerwise_bound_ms=net_bound_ms, forward_ms_eager_sum=sum_ms, frac_of_layerwise_bound=net_bound_ms / sum_ms,
+                             conv_share=conv_ms / sum_ms, algorithmic_gb=total_bytes / 1e9, algorithmic_gflop=total_flops / 1e9,
+                             hbm_view=total_bytes / (ms_step * 1e-3) / 1e9 / pk['hbm_gbs'],
+                             tensor_view=total_flops / (ms_step * 1e-3) / 1e12 / pk['bf16_tflops']))
+    if args.profile_ops:
+        for r in table:
+            row = r['row']
+            sys.stderr.write('%-10s k%d s%d %3d->%3d %4dx%-4d res=%d  %8.3f ms  bound %7.3f ms  %5.1f%%  %7.1f GB/s %7.1f TF/s\n' % (
+                row['kind'], row['ksize'], row['stride'], row['Cin'], row['Cout'], row['Ho'], row['Wo'], int(row['res']), r['ms'], r['t_bound_ms'],
+                100 * r['t_bound_ms'] / max(r['ms'], 1e-9), r['bytes'] / (r['ms'] * 1e-3) / 1e9, r['flops'] / (r['ms'] * 1e-3) / 1e12))
+        sys.stderr.write('sum of ops %.3f ms; graph step (incl. post-process) %.3f ms\n' % (sum_ms, ms_step))
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms_cpu, done = cpu_leg(wl, sd, 50, 1, 1, budget_s=20.0)
+        cpu = dict(value=ips, unit='images/s', cores=torch.get_num_threads(), kind='port',
+                   sample='1 frame %dx%d per step, %d steps (forward fp32 + decode + NMS on the host)' % (W, H, done))
+    line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(warmup, POOL), ms_per_step=ms_step,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
+                config=dict(workload=wl['name'], input='uint8 BGR NHWC frames, normalisation fused into the stem kernel',
+                            weights='synthetic (tests/synth.py)', score_thr='%.4f (calibrated: %.1f%% of points pass)' % (score_thr, 100 * PASS_FRACTION),
+                            iou_thr=IOU_THR, detections_last_step=counts[:N], parallelism='batch-sharded replicas x%d, no collective' % world,
+                            l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
+                               % (POOL, POOL * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),
+                            cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl),
+                clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps,
+                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes,
+                         note='pinned host uint8 frames -> device -> detections -> pinned host, double buffered'),
+                roofline=roofline)
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -137,7 +137,8 @@ class InferencePlan(object):
         wt = wt.permute(2, 3, 1, 0).reshape(27, conv.out_channels)           # k = (kh*3+kw)*3 + ci
         self._ops.append(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
                               relu=int(relu), out=self._tensor(out_name, self.N, ho, wo, conv.out_channels),
-                              w_f32=self._add_f32(wt), scale=self._add_f32(scale), shift=self._add_f32(shift)))
+                              w_f32=self._add_f32(wt), scale=self._add_f32(scale), shift=self._add_f32(shift),
+                              modules=(conv, norm)))
         return ho, wo
 
     def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None):
@@ -164,7 +165,7 @@ class InferencePlan(object):
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
                   gn_groups=gn_groups, cc=cc, inp=in_name, out=self._tensor(out_name, self.N, ho, wo, cout), res=res,
-                  w_bf16=w_off, scale=sc_off, shift=sh_off, query=q)
+                  w_bf16=w_off, scale=sc_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
         if gn_groups:
             op['stats'] = len([o for o in self._ops if o.get('stats') is not None and o['kind'] == nat.OP_CONV])
         self._ops.append(op)
@@ -235,7 +236,7 @@ class InferencePlan(object):
                                           Cout=tconv.out_channels, gn_groups=tnorm.num_groups, inp=raw,
                                           out=self._tensor(act, self.N, fh, fw, tconv.out_channels), stats=stats_id,
                                           gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
-                                          beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias)))
+                                          beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias), modules=(tnorm,)))
                     x = act
                 raise ValueError('head tower without conv layers is not supported')
 
@@ -251,7 +252,8 @@ class InferencePlan(object):
                                       point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
                                       scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
                                       gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
-                                      beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias)))
+                                      beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias),
+                                      modules=(tnorm, [c for c, _ in convs], [sc for _, sc in convs])))
 
             if cls_tower is reg_tower:
                 raw, sid, tn = run_tower(cls_tower, 'm')
@@ -380,3 +382,36 @@ def make_norm_probe(head):
     """First norm module of the head tower (None when the head has no norm)."""
     tower = head.level_paths(0)[0]
     return tower[0][1] if tower else None
+
+
+class PostPlan(object):
+    """Pre-allocated device post-process (lfd_postprocess) for a fixed batch size / level geometry."""
+
+    def __init__(self, cfg, device):
+        self.cfg, self.device = cfg, device
+        N, cap = cfg.N, cfg.cap
+        self.ws = torch.empty(max(nat.lib().lfd_postprocess_workspace_bytes(C.byref(cfg)), 256), dtype=torch.uint8, device=device)
+        self.dets = torch.empty((N, cap, 5), dtype=torch.float32, device=device)
+        self.labels = torch.empty((N, cap), dtype=torch.int32, device=device)
+        self.src = torch.empty((N, cap), dtype=torch.int32, device=device)
+        self.count = torch.empty((N + 1,), dtype=torch.int32, device=device)   # [N] = overflow flag
+        self.meta = torch.zeros((3, N), dtype=torch.float32, device=device)   # widths, heights, resize scales
+        self._meta_host = None
+
+    def set_meta(self, widths, heights, scales):
+        host = (tuple(map(float, widths)), tuple(map(float, heights)), tuple(map(float, scales)))
+        if host != self._meta_host:
+            self.meta.copy_(torch.tensor(host, dtype=torch.float32))
+            self._meta_host = host
+
+    def run(self, cls, reg, score_thr=None, iou_thr=None):
+        """cls/reg: contiguous float32 CUDA tensors.  Results stay on the device (dets, labels, src, count[+overflow])."""
+        if score_thr is not None:
+            self.cfg.score_thr = float(score_thr)
+        if iou_thr is not None:
+            self.cfg.iou_thr = float(iou_thr)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().lfd_postprocess(C.byref(self.cfg), nat.ptr(cls), nat.ptr(reg), nat.ptr(self.meta[0]), nat.ptr(self.meta[1]),
+                                                nat.ptr(self.meta[2]), nat.ptr(self.ws), nat.ptr(self.dets), nat.ptr(self.labels),
+                                                nat.ptr(self.src), nat.ptr(self.count), nat.ptr(self.count[self.cfg.N:]), nat.stream_ptr()))
+        return self.dets, self.labels, self.src, self.count

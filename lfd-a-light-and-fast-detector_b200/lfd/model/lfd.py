@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import _native as nat
-from .._engine import InferencePlan
+from .._engine import InferencePlan, PostPlan
 
 __all__ = ['LFD']
 
@@ -80,6 +80,7 @@ class LFD(nn.Module):
         self._head_indexes_to_feature_map_sizes = dict()
         # native state (not part of the state_dict)
         self._plans = {}
+        self._post_plans = {}
         self._plan_fingerprint = None
         self.conv_impl = nat.CONV_UMMA
         self.use_cuda_graph = True
@@ -276,30 +277,28 @@ class LFD(nn.Module):
         cfg.cap = int(self.max_detections_per_image)
         return cfg
 
+    def post_plan(self, n, sizes, device, class_agnostic=False):
+        key = (n, tuple(map(tuple, sizes)), int(self.max_detections_per_image), str(device), bool(class_agnostic),
+               type(self._classification_loss_func).__name__, self._distance_to_bbox_mode, self._regression_loss_type)
+        if key not in self._post_plans:
+            self._post_plans[key] = PostPlan(self._post_cfg(n, sizes, self._classification_threshold, self._nms_cfg['iou_thr'],
+                                                            class_agnostic), device)
+        return self._post_plans[key]
+
     def detect(self, predict_outputs, heights, widths, scales, score_thr, iou_thr, class_agnostic=False):
-        """Device post-process.  -> (dets [N,cap,5] x1,y1,x2,y2,score ; labels [N,cap] ; src [N,cap] ; count [N]) on device."""
+        """Device post-process.  -> (dets [N,cap,5] x1,y1,x2,y2,score ; labels [N,cap] ; src [N,cap] ; count [N] ; overflow [1])
+        on the device (buffers owned by the cached post-process plan)."""
         cls, reg = predict_outputs
         if not cls.is_cuda:
             raise RuntimeError('lfd_b200 has no CPU path')
-        device = cls.device
         N = cls.shape[0]
-        cfg = self._post_cfg(N, self._sizes(), score_thr, iou_thr, class_agnostic)
-        if cfg.P != cls.shape[1]:
-            raise ValueError('prediction has %d points but the recorded feature maps give %d' % (cls.shape[1], cfg.P))
-        cls_c, reg_c = cls.detach().float().contiguous(), reg.detach().float().contiguous()
-        meta = torch.tensor([list(map(float, widths)), list(map(float, heights)), list(map(float, scales))],
-                            dtype=torch.float32).to(device)
-        ws = torch.empty(nat.lib().lfd_postprocess_workspace_bytes(C.byref(cfg)), dtype=torch.uint8, device=device)
-        dets = torch.empty((N, cfg.cap, 5), dtype=torch.float32, device=device)
-        labels = torch.empty((N, cfg.cap), dtype=torch.int32, device=device)
-        src = torch.empty((N, cfg.cap), dtype=torch.int32, device=device)
-        count = torch.empty((N,), dtype=torch.int32, device=device)
-        overflow = torch.empty((1,), dtype=torch.int32, device=device)
-        with torch.cuda.device(device):
-            nat.check(nat.lib().lfd_postprocess(C.byref(cfg), nat.ptr(cls_c), nat.ptr(reg_c), nat.ptr(meta[0]), nat.ptr(meta[1]),
-                                                nat.ptr(meta[2]), nat.ptr(ws), nat.ptr(dets), nat.ptr(labels), nat.ptr(src),
-                                                nat.ptr(count), nat.ptr(overflow), nat.stream_ptr()))
-        return dets, labels, src, count, overflow
+        sizes = self._sizes()
+        pp = self.post_plan(N, sizes, cls.device, class_agnostic)
+        if pp.cfg.P != cls.shape[1]:
+            raise ValueError('prediction has %d points but the recorded feature maps give %d' % (cls.shape[1], pp.cfg.P))
+        pp.set_meta(widths, heights, scales)
+        dets, labels, src, count = pp.run(cls.detach().float().contiguous(), reg.detach().float().contiguous(), score_thr, iou_thr)
+        return dets, labels, src, count[:N], count[N:]
 
     @staticmethod
     def _rows(dets, labels, count, overflow, cap):

@@ -1,0 +1,73 @@
+# -*- coding: utf-8 -*-
+"""StreamingDetector -- end-to-end batched inference from HOST frames to HOST detections.
+
+Double-buffered: the host->device copy of batch i+1 (copy stream) overlaps the forward + post-process of batch i
+(compute stream); the small device->host read of the results rides on the compute stream.  This is the serving-side
+counterpart of the reference's `predict_for_single_image` (lfd/model/lfd.py:544-655), which moves one image at a time
+and synchronises after every stage.
+"""
+import torch
+
+from . import _native as nat
+
+
+class StreamingDetector(object):
+
+    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None):
+        self.model = model
+        self.device = device if device is not None else next(model.parameters()).device
+        self.N, self.H, self.W = batch, height, width
+        self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
+        self.max_out = min(int(max_out), int(model.max_detections_per_image))
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.copy_stream = torch.cuda.Stream(device=dev)
+            self.compute_stream = torch.cuda.Stream(device=dev)
+        self.plan = model.inference_plan(batch, height, width, dev)
+        for i, hw in enumerate(self.plan.level_sizes):
+            model._head_indexes_to_feature_map_sizes[i] = hw
+        self.post = model.post_plan(batch, self.plan.level_sizes, dev)
+        self.post.set_meta([width] * batch, [height] * batch, [1.0] * batch)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append(dict(
+                x=torch.empty((batch, height, width, 3), dtype=torch.uint8, device=dev),
+                out_dets=torch.empty((batch, self.max_out, 5), dtype=torch.float32).pin_memory(),
+                out_labels=torch.empty((batch, self.max_out), dtype=torch.int32).pin_memory(),
+                out_count=torch.empty((batch + 1,), dtype=torch.int32).pin_memory(),
+                h2d=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
+        self.step = 0
+        self.h2d_bytes = batch * height * width * 3
+        self.d2h_bytes = batch * self.max_out * (5 * 4 + 4) + (batch + 1) * 4
+
+    def submit(self, frames_u8):
+        """frames_u8: pinned (or pageable) host uint8 [N,H,W,3].  Enqueues copy + compute; returns the slot index."""
+        s = self.slots[self.step % 2]
+        if s['busy']:
+            s['done'].synchronize()
+        with torch.cuda.stream(self.copy_stream):
+            s['x'].copy_(frames_u8, non_blocking=True)
+            s['h2d'].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s['h2d'])
+            cls, reg = self.plan.forward(s['x'], use_graph=self.model.use_cuda_graph)
+            dets, labels, _, count = self.post.run(cls, reg, self.score_thr, self.iou_thr)
+            s['out_dets'].copy_(dets[:, :self.max_out], non_blocking=True)
+            s['out_labels'].copy_(labels[:, :self.max_out], non_blocking=True)
+            s['out_count'].copy_(count, non_blocking=True)
+            s['done'].record(self.compute_stream)
+        s['busy'] = True
+        self.step += 1
+        return (self.step - 1) % 2
+
+    def collect(self, slot):
+        """Blocks until the slot's results are on the host.  -> (dets [N,max_out,5], labels [N,max_out], counts [N])."""
+        s = self.slots[slot]
+        s['done'].synchronize()
+        s['busy'] = False
+        if int(s['out_count'][self.N]) != 0:
+            raise nat.LfdError('post-process capacity overflow; raise model.max_detections_per_image')
+        return s['out_dets'], s['out_labels'], s['out_count'][:self.N]
+
+    def infer(self, frames_u8):
+        return self.collect(self.submit(frames_u8))

@@ -59,7 +59,7 @@ def test_conv_matches_fp32_reference(case, impl):
 
 def test_conv_large_grid_persistent_loop():
     """More tiles than SMs: exercises the persistent tile loop, both accumulator stages and ring wrap-around."""
-    case = (2, 90, 160, 64, 64, 3, 1, True, True, 0)
+    case = (3, 90, 160, 64, 64, 3, 1, True, True, 0)
     x, w, scale, shift, res = _make(case, seed=3)
     out, _, q = run_conv(x, w, scale, shift, 1, True, res=res)
     assert q['num_tiles'] > 2 * nat.lib().lfd_device_sm_count()

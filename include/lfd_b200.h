@@ -34,6 +34,7 @@ extern "C" {
 
 #define LFD_B200_ABI_VERSION 1
 #define LFD_MAX_LEVELS 8
+#define LFD_MAX_BRANCHES 8
 
 typedef enum lfd_status {
     LFD_OK = 0,
@@ -73,6 +74,8 @@ typedef struct lfd_op {
     int32_t N, H, W, Cin, Ho, Wo, Cout;
     int32_t ksize, stride, relu, gn_groups;
     int32_t n_cls, n_reg, point_off, cc;
+    int32_t branch, reserved; /* branch 0 = main stream; ops of branch b > 0 run on side stream b, forked after the
+                                 main-stream op that precedes the branch's first op and joined at the end */
     int64_t in_off, out_off, res_off, stats_off; /* bytes; -1 = unused */
     const void* weight;
     const float* scale;

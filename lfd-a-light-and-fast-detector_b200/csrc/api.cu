@@ -56,6 +56,10 @@ struct lfd_plan {
         int fmt;
     };
     std::vector<GraphEntry> graphs;
+    // side streams for independent branches (the per-level neck + head chains)
+    cudaStream_t side[LFD_MAX_BRANCHES];
+    cudaEvent_t fork_ev[LFD_MAX_BRANCHES], join_ev[LFD_MAX_BRANCHES];
+    int n_branches;
 };
 static constexpr size_t kMaxGraphs = 32;
 
@@ -189,11 +193,23 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
     lfd_plan* pl = new lfd_plan();
     pl->N = N; pl->P = P; pl->cls_channels = cls_channels; pl->conv_impl = conv_impl;
     pl->stats_off = stats_off; pl->stats_bytes = stats_bytes; pl->workspace_bytes = workspace_bytes;
+    pl->n_branches = 1;
     for (int i = 0; i < n_ops; ++i) {
         PlannedOp po;
         int rc = plan_op(ops[i], conv_impl, &po);
         if (rc) { delete pl; return rc; }
+        if (ops[i].branch < 0 || ops[i].branch >= LFD_MAX_BRANCHES) { delete pl; return fail(LFD_ERR_INVALID, "op %d: branch %d out of range", i, ops[i].branch); }
+        if (ops[i].branch + 1 > pl->n_branches) pl->n_branches = ops[i].branch + 1;
         pl->ops.push_back(po);
+    }
+    for (int b = 1; b < pl->n_branches; ++b) {
+        if (cudaStreamCreateWithFlags(&pl->side[b], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pl->fork_ev[b], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&pl->join_ev[b], cudaEventDisableTiming) != cudaSuccess) {
+            pl->n_branches = b;  // destroy what exists
+            lfd_plan_destroy(pl);
+            return fail(LFD_ERR_CUDA, "lfd_plan_create: cannot create side streams");
+        }
     }
     *out = pl;
     return LFD_OK;
@@ -202,6 +218,11 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
 extern "C" int lfd_plan_destroy(lfd_plan* plan) {
     if (!plan) return LFD_OK;
     for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    for (int b = 1; b < plan->n_branches; ++b) {
+        cudaStreamDestroy(plan->side[b]);
+        cudaEventDestroy(plan->fork_ev[b]);
+        cudaEventDestroy(plan->join_ev[b]);
+    }
     delete plan;
     return LFD_OK;
 }
@@ -210,11 +231,27 @@ extern "C" int lfd_plan_num_launches(const lfd_plan* plan) { return plan ? (int)
 
 static int enqueue_all(lfd_plan* pl, const void* input, int fmt, uint8_t* ws, float* cls, float* reg, cudaStream_t st) {
     if (pl->stats_bytes > 0) CUDA_TRY(cudaMemsetAsync(ws + pl->stats_off, 0, (size_t)pl->stats_bytes, st));
-    for (size_t i = 0; i < pl->ops.size(); ++i) {
-        int rc = launch_op(pl->ops[i], input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, st);
-        if (rc) return rc;
+    bool started[LFD_MAX_BRANCHES] = {false};
+    int rc = LFD_OK;
+    for (size_t i = 0; i < pl->ops.size() && !rc; ++i) {
+        const int b = pl->ops[i].op.branch;
+        cudaStream_t s = st;
+        if (b > 0) {
+            s = pl->side[b];
+            if (!started[b]) {  // fork: everything enqueued on the main stream so far precedes this branch
+                CUDA_TRY(cudaEventRecord(pl->fork_ev[b], st));
+                CUDA_TRY(cudaStreamWaitEvent(s, pl->fork_ev[b], 0));
+                started[b] = true;
+            }
+        }
+        rc = launch_op(pl->ops[i], input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, s);
     }
-    return LFD_OK;
+    for (int b = 1; b < pl->n_branches; ++b)   // join (also on error paths, so that a stream capture can be closed)
+        if (started[b]) {
+            cudaEventRecord(pl->join_ev[b], pl->side[b]);
+            cudaStreamWaitEvent(st, pl->join_ev[b], 0);
+        }
+    return rc;
 }
 
 extern "C" int lfd_plan_forward(lfd_plan* pl, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,

@@ -33,6 +33,7 @@ struct UmmaConvParams {
     int tiles_x, tiles_per_img, num_tiles;
     int n_px;                   // halo pixels loaded per stage
     int Cc, stages, b_resident;
+    int log2_cpc, log2_cpr, log2_rp128, tmem_cols, ctas_per_sm;
     uint32_t lbo_a, sbo_a;
     uint32_t a_stage_bytes, b_slice_bytes, stage_bytes, w_total_bytes;
     uint32_t smem_w_off, smem_ring_off;

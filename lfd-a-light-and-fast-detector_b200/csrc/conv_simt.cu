@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     const size_t total = (size_t)p.HW * cpr;
     const uint4* in = reinterpret_cast<const uint4*>(p.in + (size_t)n * p.HW * p.C);
     uint4* out = reinterpret_cast<uint4*>(p.out + (size_t)n * p.HW * p.C);
+#pragma unroll 4
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % cpr);
         const uint4 q = in[i];
@@ -162,7 +163,7 @@ cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st
     if (p.C != p.groups * 8 || p.groups > 32) return cudaErrorInvalidValue;
     const size_t total = (size_t)p.HW * (p.C >> 3);
     int bx = (int)((total + 255) / 256);
-    const int cap = (4 * num_sms + p.N - 1) / p.N;
+    const int cap = (8 * num_sms + p.N - 1) / p.N;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     gn_apply_kernel<<<dim3(bx, p.N), 256, 0, st>>>(p);
@@ -172,75 +173,100 @@ cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st
 // ===================================================================================================
 // head final: GN apply + ReLU (bf16 round) -> narrow 1x1 convs -> fp32 (N, P, C') / (N, P, 4)
 // ===================================================================================================
-static constexpr int kHfThreads = 128;
+static constexpr int kHfThreads = 256;
+static constexpr int kHfPpt = 4;                       // pixels per thread
+static constexpr int kHfPixPerBlock = (kHfThreads / 8) * kHfPpt;   // 128
 static constexpr int kHfMaxC = 128;
 
+// 8 threads share one pixel (16 channels each): coalesced 256-byte rows, the 16-channel weight slice of every output
+// is a broadcast-friendly 64-byte shared-memory read, partial dot products are combined with 3 warp shuffles.
 __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalParams p) {
     extern __shared__ __align__(16) float hf_smem[];
     float* wsm = hf_smem;                                 // [n_out][C]
     float* s_mean = wsm + (size_t)p.n_out * p.C;          // [groups]
     float* s_rstd = s_mean + 32;
-    float* s_gamma = s_rstd + 32;                         // [C]
-    float* s_beta = s_gamma + kHfMaxC;
     const int n = blockIdx.y;
     for (int i = threadIdx.x; i < p.n_out * p.C; i += kHfThreads) wsm[i] = p.w[i];
-    for (int i = threadIdx.x; i < p.C; i += kHfThreads) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
     if (threadIdx.x < p.groups)
         gn_mean_rstd(p.stats, n, threadIdx.x, p.groups, (double)p.HW * 8.0, p.eps, &s_mean[threadIdx.x], &s_rstd[threadIdx.x]);
     __syncthreads();
-    const int pix = blockIdx.x * kHfThreads + threadIdx.x;
-    if (pix >= p.HW) return;
-    // normalised activation row, packed bf16x2 (C <= 128 -> 64 registers)
-    uint32_t a[kHfMaxC / 2];
-    const uint4* src = reinterpret_cast<const uint4*>(p.in + ((size_t)n * p.HW + pix) * p.C);
+    const int sl = threadIdx.x & 7;                       // channel slice: channels [16 sl, 16 sl + 16)
+    float ga[16], be[16];
 #pragma unroll
-    for (int c8 = 0; c8 < kHfMaxC / 8; ++c8) {
-        if (c8 * 8 < p.C) {
-            const uint4 q = src[c8];
-            float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-            const float m = s_mean[c8], r = s_rstd[c8];
+    for (int j = 0; j < 16; ++j) { ga[j] = p.gamma[sl * 16 + j]; be[j] = p.beta[sl * 16 + j]; }
+    const float m0 = s_mean[2 * sl], r0 = s_rstd[2 * sl], m1 = s_mean[2 * sl + 1], r1 = s_rstd[2 * sl + 1];
+    const int pix0 = blockIdx.x * kHfPixPerBlock + (threadIdx.x >> 3);
+    float a[kHfPpt][16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = (f[j] - m) * r;
-                y = fmaf(y, s_gamma[c8 * 8 + j], s_beta[c8 * 8 + j]);
-                f[j] = fmaxf(y, 0.f);
-            }
-            a[c8 * 4 + 0] = pack_bf16x2(f[0], f[1]); a[c8 * 4 + 1] = pack_bf16x2(f[2], f[3]);
-            a[c8 * 4 + 2] = pack_bf16x2(f[4], f[5]); a[c8 * 4 + 3] = pack_bf16x2(f[6], f[7]);
+    for (int k = 0; k < kHfPpt; ++k) {
+        const int pix = pix0 + k * (kHfThreads / 8);
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        if (pix < p.HW) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.in + ((size_t)n * p.HW + pix) * p.C + sl * 16);
+            q0 = src[0]; q1 = src[1];
+        }
+        float f[16] = {bf16_lo(q0.x), bf16_hi(q0.x), bf16_lo(q0.y), bf16_hi(q0.y), bf16_lo(q0.z), bf16_hi(q0.z), bf16_lo(q0.w), bf16_hi(q0.w),
+                       bf16_lo(q1.x), bf16_hi(q1.x), bf16_lo(q1.y), bf16_hi(q1.y), bf16_lo(q1.z), bf16_hi(q1.z), bf16_lo(q1.w), bf16_hi(q1.w)};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float y = (f[j] - (j < 8 ? m0 : m1)) * (j < 8 ? r0 : r1);
+            y = fmaf(y, ga[j], be[j]);
+            a[k][j] = bf16_round(fmaxf(y, 0.f));          // rounding point Rg
         }
     }
-    float* cls_row = p.cls ? p.cls + ((size_t)n * p.P + p.point_off + pix) * p.cls_stride : nullptr;
-    float* reg_row = p.reg ? p.reg + ((size_t)n * p.P + p.point_off + pix) * 4 : nullptr;
-    for (int o0 = 0; o0 < p.n_out; o0 += 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int o0 = 0; o0 < p.n_out; o0 += 8) {
+        float acc[8][kHfPpt];
 #pragma unroll
-        for (int c2 = 0; c2 < kHfMaxC / 2; ++c2) {
-            if (c2 * 2 < p.C) {
-                const float x0 = bf16_lo(a[c2]), x1 = bf16_hi(a[c2]);
+        for (int o = 0; o < 8; ++o)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (o0 + k < p.n_out) {
-                        const float* wr = wsm + (size_t)(o0 + k) * p.C + c2 * 2;
-                        acc[k] = fmaf(x0, wr[0], acc[k]);
-                        acc[k] = fmaf(x1, wr[1], acc[k]);
+            for (int k = 0; k < kHfPpt; ++k) acc[o][k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            if (o0 + o < p.n_out) {
+                const float4* wr = reinterpret_cast<const float4*>(wsm + (size_t)(o0 + o) * p.C + sl * 16);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float4 w4 = wr[v];
+#pragma unroll
+                    for (int k = 0; k < kHfPpt; ++k) {
+                        acc[o][k] = fmaf(a[k][v * 4 + 0], w4.x, acc[o][k]); acc[o][k] = fmaf(a[k][v * 4 + 1], w4.y, acc[o][k]);
+                        acc[o][k] = fmaf(a[k][v * 4 + 2], w4.z, acc[o][k]); acc[o][k] = fmaf(a[k][v * 4 + 3], w4.w, acc[o][k]);
                     }
                 }
             }
         }
+        // combine the 8 channel slices; afterwards lane `sl` owns output o0 + sl
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int o = o0 + k;
-            if (o >= p.n_out) break;
-            const float v = fmaf(acc[k], p.scale[o], p.shift[o]);
-            if (o < p.n_cls) cls_row[o] = v;
-            else reg_row[o - p.n_cls] = v;
+        for (int o = 0; o < 8; ++o)
+#pragma unroll
+            for (int k = 0; k < kHfPpt; ++k) {
+                float v = acc[o][k];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                acc[o][k] = v;
+            }
+        const int o = o0 + sl;
+        if (o < p.n_out) {
+            const float sc = p.scale[o], sh = p.shift[o];
+#pragma unroll
+            for (int k = 0; k < kHfPpt; ++k) {
+                const int pix = pix0 + k * (kHfThreads / 8);
+                if (pix >= p.HW) continue;
+                float v = 0.f;
+#pragma unroll
+                for (int oo = 0; oo < 8; ++oo) v = (oo == sl) ? acc[oo][k] : v;   // select without dynamic register indexing
+                v = fmaf(v, sc, sh);
+                if (o < p.n_cls) p.cls[((size_t)n * p.P + p.point_off + pix) * p.cls_stride + o] = v;
+                else p.reg[((size_t)n * p.P + p.point_off + pix) * 4 + (o - p.n_cls)] = v;
+            }
         }
     }
 }
 
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
-    if (p.C > kHfMaxC || p.C != p.groups * 8 || p.groups > 32) return cudaErrorInvalidValue;
-    const size_t smem = ((size_t)p.n_out * p.C + 64 + 2 * kHfMaxC) * sizeof(float);
+    if (p.C != kHfMaxC || p.groups != 16) return cudaErrorInvalidValue;   // 128 channels, 16 groups of 8 (every shipped head)
+    const size_t smem = ((size_t)p.n_out * p.C + 64) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(head_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -248,7 +274,7 @@ cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
         attr = true;
     }
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
-    head_final_kernel<<<dim3((p.HW + kHfThreads - 1) / kHfThreads, p.N), kHfThreads, smem, st>>>(p);
+    head_final_kernel<<<dim3((p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock, p.N), kHfThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -33,7 +33,6 @@ static constexpr int kMmaWarp = 4;
 static constexpr int kProdThreads = 128;
 static constexpr int kThreads = kEpiThreads + 32 + kProdThreads;  // 288
 static constexpr int kLag = 2;                                     // cp.async groups kept in flight per producer thread
-static constexpr int kTmemCols = 256;
 
 struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's input origin) and where it goes
     int16_t dy, dx;
@@ -42,7 +41,7 @@ struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvParams p) {
+__global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
     uint64_t* empty = full + kMaxStages;
@@ -76,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
         mbar_init(wbar, 1);
         fence_mbar_init();
     }
-    if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
     for (int c = tid; c < p.Cout; c += kThreads) {
         s_scale[c] = p.scale[c];
         s_shift[c] = p.shift[c];
@@ -115,10 +114,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     if (warp < 4) {
         // ============================================================== EPILOGUE
         const int m = tid;  // D row == TMEM lane
-        const int cpr = p.Cout >> 3;          // 16 B chunks per staged row
+        const int cpr = p.Cout >> 3;          // 16 B chunks per staged row (power of two)
+        const int l2cpr = p.log2_cpr;
         const int row_bytes = p.Cout * 2;
-        const int rp128 = row_bytes >= 128 ? 1 : 128 / row_bytes;  // rows per 128 B (swizzle granularity)
+        const int l2rp = p.log2_rp128;         // log2(rows per 128 B): swizzle granularity for rows shorter than 128 B
         const int swz_mask = (cpr < 8 ? cpr : 8) - 1;
+        const int HoWo = p.Ho * p.Wo;
         const uint32_t stg = smem_u32(staging);
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
@@ -130,17 +131,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             const size_t img_out = (size_t)n * p.Ho * p.Wo;
             // pixel index (within the image) of staged row r, or -1 when outside the feature map
             auto row_pixel = [&](int r) -> int {
-                if (MODE == MODE_FLAT) { int q = p0 + r; return q < p.Ho * p.Wo ? q : -1; }
+                if (MODE == MODE_FLAT) { int q = p0 + r; return q < HoWo ? q : -1; }
                 int y = oy0 + (r >> 3), x = ox0 + (r & 7);
                 return (y < p.Ho && x < p.Wo) ? y * p.Wo + x : -1;
             };
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
             if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
                 for (int e = tid; e < 128 * cpr; e += kEpiThreads) {
-                    int r = e / cpr, c = e - r * cpr;
-                    int q = row_pixel(r);
+                    const int r = e >> l2cpr, c = e & (cpr - 1);
+                    const int q = row_pixel(r);
                     const __nv_bfloat16* src = p.res + ((img_out + (q < 0 ? 0 : q)) * p.Cout + c * 8);
-                    cp_async16(stg + r * row_bytes + ((c ^ ((r / rp128) & swz_mask)) << 4), src, q >= 0);
+                    cp_async16(stg + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4), src, q >= 0);
                 }
                 cp_async_commit();
             }
@@ -152,13 +153,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
             }
             const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * p.Cout;
             uint8_t* my_row = staging + m * row_bytes;
-            const int my_swz = (m / rp128) & swz_mask;
-            for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-                float v[16];
+            const int my_swz = (m >> l2rp) & swz_mask;
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                float v[32];
                 tmem_ld16(trow + c0, v);
+                if (c0 + 16 < p.Cout) tmem_ld16(trow + c0 + 16, v + 16);
                 tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < 4; ++h) {
+                    if (c0 + h * 8 >= p.Cout) break;
                     const int chunk = (c0 >> 3) + h;
                     uint4* slot = reinterpret_cast<uint4*>(my_row + ((chunk ^ my_swz) << 4));
                     float o[8];
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                 float s1 = 0.f, s2 = 0.f;
                 for (int r = sl; r < 128; r += 8) {
                     if (row_pixel(r) < 0) continue;
-                    uint4 q = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((g ^ ((r / rp128) & swz_mask)) << 4));
+                    uint4 q = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((g ^ ((r >> l2rp) & swz_mask)) << 4));
                     float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                   bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
@@ -205,10 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                 }
             }
             for (int e = tid; e < 128 * cpr; e += kEpiThreads) {  // coalesced store
-                int r = e / cpr, c = e - r * cpr;
-                int q = row_pixel(r);
+                const int r = e >> l2cpr, c = e & (cpr - 1);
+                const int q = row_pixel(r);
                 if (q < 0) continue;
-                uint4 val = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((c ^ ((r / rp128) & swz_mask)) << 4));
+                const uint4 val = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4));
                 *reinterpret_cast<uint4*>(p.out + ((img_out + q) * p.Cout + c * 8)) = val;
             }
             named_bar_sync(1, kEpiThreads);  // staging free again
@@ -226,10 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                     bulk_g2s(smem_u32(wres) + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wbar);
                 }
             }
-            mbar_wait(wbar, 0);
+            if (lane == 0) mbar_wait(wbar, 0);
         }
         uint32_t it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = blockIdx.x; lane == 0 && tile < p.num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after_sync();
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                 mbar_wait(&full[s], ph);
                 tc_fence_after_sync();
                 fence_proxy_async_smem();
-                if (lane == 0) {
+                {
                     const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
                     const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes
                                                          : a_base + p.a_stage_bytes;
@@ -260,13 +263,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                     umma_commit(&empty[s]);
                     if (cc == n_cc - 1) umma_commit(&tfull[a]);
                 }
-                __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ============================================================== PRODUCERS
         const int ptid = tid - (kEpiThreads + 32);
-        const int n_el = p.n_px * cpc;
+        // every thread owns ONE 16-byte channel chunk (cpc divides 128) and walks the halo pixels with a fixed stride
+        const int ch = ptid & (cpc - 1);
+        const int px0 = ptid >> p.log2_cpc;
+        const int pstep = kProdThreads >> p.log2_cpc;
+        const uint32_t ch_dst = ch * p.lbo_a;
         // A full-barrier arrival for stage-iteration j is made at the end of iteration j+lag; the empty wait of
         // iteration j+SA must come later than that, hence lag <= SA-1.
         const uint32_t lag = SA >= 3 ? (uint32_t)kLag : 1u;
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                 iy0 = (MODE == MODE_3X3S1) ? oy0 : 2 * oy0;
                 ix0 = (MODE == MODE_3X3S1) ? ox0 : 2 * ox0;
             }
-            const __nv_bfloat16* img = p.in + (size_t)n * HW * p.Cin;
+            const __nv_bfloat16* img = p.in + (size_t)n * HW * p.Cin + ch * 8;
             for (int cc = 0; cc < n_cc; ++cc, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
@@ -291,21 +298,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
                     bulk_g2s(a_base + p.a_stage_bytes, reinterpret_cast<const uint8_t*>(p.w) + (size_t)cc * p.b_slice_bytes,
                              p.b_slice_bytes, &full[s]);
                 }
-                for (int e = ptid; e < n_el; e += kProdThreads) {
-                    const int pxi = e / cpc, ch = e - pxi * cpc;
-                    const PxEntry pe = table[pxi];
-                    bool ok;
-                    size_t pix;
-                    if (MODE == MODE_FLAT) {
-                        int q = ix0 + pe.dx;
-                        ok = q < HW;
-                        pix = ok ? q : 0;
-                    } else {
-                        int y = iy0 + pe.dy, x = ix0 + pe.dx;
-                        ok = (y >= 0) && (y < p.H) && (x >= 0) && (x < p.W);
-                        pix = ok ? (size_t)y * p.W + x : 0;
+                const __nv_bfloat16* src_cc = img + cc * p.Cc;
+                const uint32_t dst_cc = a_base + ch_dst;
+                if (MODE == MODE_FLAT) {
+#pragma unroll 4
+                    for (int pxi = px0; pxi < 128; pxi += pstep) {
+                        const int q = ix0 + pxi;
+                        const bool ok = q < HW;
+                        cp_async16(dst_cc + pxi * 16, src_cc + (ok ? q : 0) * p.Cin, ok);
                     }
-                    cp_async16(a_base + ch * p.lbo_a + pe.slot * 16, img + pix * p.Cin + cc * p.Cc + ch * 8, ok);
+                } else {
+#pragma unroll 4
+                    for (int pxi = px0; pxi < p.n_px; pxi += pstep) {
+                        const PxEntry pe = table[pxi];
+                        const int y = iy0 + pe.dy, x = ix0 + pe.dx;
+                        const bool ok = ((unsigned)y < (unsigned)p.H) && ((unsigned)x < (unsigned)p.W);
+                        cp_async16(dst_cc + pe.slot * 16, src_cc + (ok ? (y * p.W + x) : 0) * p.Cin, ok);
+                    }
                 }
                 cp_async_commit();
                 if (it >= lag) {
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const UmmaConvPa
     __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after_sync();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        tmem_dealloc(tmem_base, p.tmem_cols);
     }
 }
 
@@ -362,26 +371,37 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     const size_t fixed = kSmemStagingOff + staging;
     const size_t budget = 224 * 1024;
     const size_t w_total = (size_t)taps * g.Cin * g.Cout * 2;
-    // choose channel chunk Cc, residency and stage count
-    int best_cc = 0, best_res = 0, best_st = 0;
+    // Choose the channel chunk Cc, weight residency and ring depth.  Preference order:
+    //   1. resident weights (loaded once per CTA) with >= 3 A stages, the largest Cc first;
+    //   2. otherwise streamed weights: the largest Cc that still gives >= 4 stages (deep ring hides the per-stage
+    //      weight fetch), then >= 3, then >= 2.
+    // Memory-bound 1x1 layers additionally cap the ring so that two CTAs fit on one SM (latency hiding).
     const int cands[3] = {64, 32, 16};
-    for (int resident = 1; resident >= 0 && !best_cc; --resident) {
-        for (int ci = 0; ci < 3; ++ci) {
-            int cc = cands[ci];
-            if (g.Cin % cc) continue;
-            size_t a_stage = (size_t)px_slots * cc * 2;
-            size_t b_slice = (size_t)taps * cc * g.Cout * 2;
-            size_t stage = a_stage + (resident ? 0 : b_slice);
-            size_t avail = budget - fixed - (resident ? w_total : 0);
-            if (resident && w_total + fixed + 2 * a_stage > budget) continue;
-            int st = (int)(avail / stage);
-            int n_stage_units = (g.Cin / cc);
-            if (st > kMaxStages) st = kMaxStages;
-            if (st > 4 && a_stage >= 16384) st = 4;
-            if (st < 2) continue;
-            (void)n_stage_units;
-            best_cc = cc; best_res = resident; best_st = st;
-            break;
+    int best_cc = 0, best_res = 0, best_st = 0;
+    auto stages_for = [&](int cc, int resident) -> int {
+        if (g.Cin % cc) return 0;
+        const size_t a_stage = (size_t)px_slots * cc * 2;
+        const size_t b_slice = (size_t)taps * cc * g.Cout * 2;
+        const size_t stage = a_stage + (resident ? 0 : b_slice);
+        if (fixed + (resident ? w_total : 0) + 2 * stage > budget) return 0;
+        int st = (int)((budget - fixed - (resident ? w_total : 0)) / stage);
+        if (st > kMaxStages) st = kMaxStages;
+        if (st > 4 && stage >= 8192) st = 4;
+        return st;
+    };
+    for (int want = 3; want >= 2 && !best_cc; --want)
+        for (int ci = 0; ci < 3 && !best_cc; ++ci) {
+            int st = stages_for(cands[ci], 1);
+            if (st >= want) { best_cc = cands[ci]; best_res = 1; best_st = st; }
+        }
+    if (!best_cc || best_st < 3) {
+        for (int want = 4; want >= 2; --want) {
+            bool found = false;
+            for (int ci = 0; ci < 3 && !found; ++ci) {
+                int st = stages_for(cands[ci], 0);
+                if (st >= want && (!best_cc || st > best_st)) { best_cc = cands[ci]; best_res = 0; best_st = st; found = true; }
+            }
+            if (found) break;
         }
     }
     if (!best_cc) return -2;
@@ -392,8 +412,26 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     p.w_total_bytes = (uint32_t)w_total;
     p.smem_w_off = (uint32_t)fixed;
     p.smem_ring_off = (uint32_t)(fixed + (best_res ? w_total : 0));
+    // two CTAs per SM when a 3-deep ring fits in half of the shared memory (1x1 layers)
+    p.ctas_per_sm = 1;
+    {
+        const size_t half = (227 * 1024) / 2 - 1024;
+        const size_t base = p.smem_ring_off;
+        if (base + 2 * (size_t)p.stage_bytes <= half) {
+            int st = (int)((half - base) / p.stage_bytes);
+            if (st > p.stages) st = p.stages;
+            if (st >= 2) { p.stages = st; p.ctas_per_sm = 2; }
+        }
+    }
+    auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+    p.log2_cpc = ilog2(p.Cc / 8);
+    p.log2_cpr = ilog2(g.Cout / 8);
+    if ((1 << p.log2_cpr) != g.Cout / 8) return -3;   // Cout must be 16/32/64/128
+    p.log2_rp128 = g.Cout * 2 >= 128 ? 0 : ilog2(128 / (g.Cout * 2));
+    p.tmem_cols = 2 * g.Cout < 32 ? 32 : 2 * g.Cout;  // two accumulator stages; power of two because Cout is
     *smem_bytes = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
-    *grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    const int max_ctas = num_sms * p.ctas_per_sm;
+    *grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
     *out = p;
     return 0;
 }

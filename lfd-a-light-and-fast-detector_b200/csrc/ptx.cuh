@@ -81,16 +81,15 @@ LFD_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uin
 }
 
 // ---------------------------------------------------------------- tcgen05: TMEM alloc
-template <int COLS>
-LFD_DEVINL void tmem_alloc(uint32_t* slot_in_smem) {  // whole warp, .sync.aligned
+// cols: power of two in [32, 512]
+LFD_DEVINL void tmem_alloc(uint32_t* slot_in_smem, uint32_t cols) {  // whole warp, .sync.aligned
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
-                 "n"(COLS)
+                 "r"(cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-template <int COLS>
-LFD_DEVINL void tmem_dealloc(uint32_t taddr) {  // whole warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+LFD_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05: descriptors

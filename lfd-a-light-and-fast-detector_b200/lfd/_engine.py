@@ -84,6 +84,8 @@ class InferencePlan(object):
         self._f32_n, self._bf16_n = 0, 0
         self._ops = []                       # dicts; tensors referenced by name
         self._tensors = {}                   # name -> bytes
+        self._branch = 0                     # branch id given to the ops being emitted (0 = main stream)
+        self.concurrent_levels = not os.environ.get('LFD_B200_NO_BRANCHES')
         self._build(model)
         self._finalize()
 
@@ -135,7 +137,7 @@ class InferencePlan(object):
         scale, shift = self._fold(conv, norm)
         wt = conv.weight.detach().float().cpu().to(torch.bfloat16).float()   # [Cout, 3, 3, 3] rounded (Rw)
         wt = wt.permute(2, 3, 1, 0).reshape(27, conv.out_channels)           # k = (kh*3+kw)*3 + ci
-        self._ops.append(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
+        self._push(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
                               relu=int(relu), out=self._tensor(out_name, self.N, ho, wo, conv.out_channels),
                               w_f32=self._add_f32(wt), scale=self._add_f32(scale), shift=self._add_f32(shift),
                               modules=(conv, norm)))
@@ -168,7 +170,7 @@ class InferencePlan(object):
                   w_bf16=w_off, scale=sc_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
         if gn_groups:
             op['stats'] = len([o for o in self._ops if o.get('stats') is not None and o['kind'] == nat.OP_CONV])
-        self._ops.append(op)
+        self._push(op)
         return ho, wo
 
     # ------------------------------------------------------------------ graph walk
@@ -183,8 +185,26 @@ class InferencePlan(object):
             else:
                 h, w = self._emit_conv(conv, norm, relu, cur, name, h, w)
             cur = name
-        feats = []
         taps = list(bb._out_indices)
+        if len(taps) != head._num_heads:
+            raise ValueError('backbone taps (%d) and head levels (%d) differ' % (len(taps), head._num_heads))
+        if not isinstance(make_norm_probe(head), nn.GroupNorm):
+            raise NotImplementedError('the B200 head kernels implement the GroupNorm towers of the shipped configs')
+        # point offsets need every level size up front: strides are fixed by the stage index
+        sizes, hh, ww = {}, h, w
+        for si, stage in enumerate(bb.stages()):
+            hh, ww = _conv_out(hh, 3, 2), _conv_out(ww, 3, 2)
+            for bi in range(len(stage)):
+                if (si, bi) in taps:
+                    sizes[(si, bi)] = (hh, ww)
+        self.level_sizes = [sizes[t] for t in taps]
+        self.P = sum(fh * fw for (fh, fw) in self.level_sizes)
+        self.cls_channels = head.num_cls_channels
+        offs, acc = [], 0
+        for (fh, fw) in self.level_sizes:
+            offs.append(acc)
+            acc += fh * fw
+        cache = {}
         for si, stage in enumerate(bb.stages()):
             for bi, block in enumerate(stage):
                 base = 's%db%d' % (si, bi)
@@ -202,68 +222,69 @@ class InferencePlan(object):
                     x = name
                 cur, h, w = x, hh, ww
                 if (si, bi) in taps:
-                    feats.append((cur, h, w))
-        if len(feats) != head._num_heads:
-            raise ValueError('backbone taps (%d) and head levels (%d) differ' % (len(feats), head._num_heads))
-        self.level_sizes = [(fh, fw) for (_, fh, fw) in feats]
-        self.P = sum(fh * fw for (fh, fw) in self.level_sizes)
-        self.cls_channels = head.num_cls_channels
-        if not isinstance(make_norm_probe(head), nn.GroupNorm):
-            raise NotImplementedError('the B200 head kernels implement the GroupNorm towers of the shipped configs')
-        cache = {}
-        point_off = 0
-        for l, (fname, fh, fw) in enumerate(feats):
-            conv, norm = neck.level(l)
-            nk = 'neck%d' % l
-            self._emit_conv(conv, norm, True, fname, nk, fh, fw)
-            cls_tower, reg_tower, fin_cls, fin_reg = head.level_paths(l)
-            scale_l = float(head._scales[l]._scale.detach()) if head.uses_scale else 1.0
+                    l = taps.index((si, bi))
+                    assert (h, w) == self.level_sizes[l]
+                    # the level's neck + head chain only depends on this tap: run it on its own stream / graph branch,
+                    # concurrently with the rest of the backbone and with the other levels
+                    self._branch = 1 + l if (self.concurrent_levels and 1 + l < 8) else 0
+                    self._emit_level(neck, head, l, cur, h, w, offs[l], cache)
+                    self._branch = 0
 
-            def run_tower(tower, tag):
-                x = nk
-                for ti, (tconv, tnorm) in enumerate(tower):
-                    if tconv.kernel_size != (1, 1):
-                        raise NotImplementedError('head towers with conv_kernel_size=3 are outside the implemented hot path')
-                    if not isinstance(tnorm, nn.GroupNorm) or tnorm.num_channels != tnorm.num_groups * 8:
-                        raise NotImplementedError('head towers need GroupNorm with 8 channels per group')
-                    raw = 'h%d%s_raw%d' % (l, tag, ti)
-                    self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
-                    stats_id = self._ops[-1]['stats']
-                    if ti == len(tower) - 1:
-                        return raw, stats_id, tnorm
-                    act = 'h%d%s_act%d' % (l, tag, ti)
-                    self._ops.append(dict(kind=nat.OP_GN_APPLY, H=fh, W=fw, Cin=tconv.out_channels, Ho=fh, Wo=fw,
-                                          Cout=tconv.out_channels, gn_groups=tnorm.num_groups, inp=raw,
-                                          out=self._tensor(act, self.N, fh, fw, tconv.out_channels), stats=stats_id,
-                                          gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
-                                          beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias), modules=(tnorm,)))
-                    x = act
-                raise ValueError('head tower without conv layers is not supported')
+    def _emit_level(self, neck, head, l, fname, fh, fw, point_off, cache):
+        conv, norm = neck.level(l)
+        nk = 'neck%d' % l
+        self._emit_conv(conv, norm, True, fname, nk, fh, fw)
+        cls_tower, reg_tower, fin_cls, fin_reg = head.level_paths(l)
+        scale_l = float(head._scales[l]._scale.detach()) if head.uses_scale else 1.0
 
-            def final(raw, stats_id, tnorm, convs, n_cls, n_reg):
-                ws, scs, shs = [], [], []
-                for (fc, sc) in convs:
-                    ws.append(fc.weight.detach().float().cpu().reshape(fc.out_channels, -1).to(torch.bfloat16).float())
-                    b = fc.bias.detach().float().cpu() if fc.bias is not None else torch.zeros(fc.out_channels)
-                    scs.append(torch.full((fc.out_channels,), sc))
-                    shs.append(b * sc)
-                self._ops.append(dict(kind=nat.OP_HEAD_FINAL, H=fh, W=fw, Cin=ws[0].shape[1], Ho=fh, Wo=fw, Cout=n_cls + n_reg,
-                                      gn_groups=tnorm.num_groups, inp=raw, stats=stats_id, n_cls=n_cls, n_reg=n_reg,
-                                      point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
-                                      scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
-                                      gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
-                                      beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias),
-                                      modules=(tnorm, [c for c, _ in convs], [sc for _, sc in convs])))
+        def run_tower(tower, tag):
+            x = nk
+            for ti, (tconv, tnorm) in enumerate(tower):
+                if tconv.kernel_size != (1, 1):
+                    raise NotImplementedError('head towers with conv_kernel_size=3 are outside the implemented hot path')
+                if not isinstance(tnorm, nn.GroupNorm) or tnorm.num_channels != tnorm.num_groups * 8:
+                    raise NotImplementedError('head towers need GroupNorm with 8 channels per group')
+                raw = 'h%d%s_raw%d' % (l, tag, ti)
+                self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
+                stats_id = self._ops[-1]['stats']
+                if ti == len(tower) - 1:
+                    return raw, stats_id, tnorm
+                act = 'h%d%s_act%d' % (l, tag, ti)
+                self._push(dict(kind=nat.OP_GN_APPLY, H=fh, W=fw, Cin=tconv.out_channels, Ho=fh, Wo=fw,
+                                Cout=tconv.out_channels, gn_groups=tnorm.num_groups, inp=raw,
+                                out=self._tensor(act, self.N, fh, fw, tconv.out_channels), stats=stats_id,
+                                gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
+                                beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias), modules=(tnorm,)))
+                x = act
+            raise ValueError('head tower without conv layers is not supported')
 
-            if cls_tower is reg_tower:
-                raw, sid, tn = run_tower(cls_tower, 'm')
-                final(raw, sid, tn, [(fin_cls, 1.0), (fin_reg, scale_l)], fin_cls.out_channels, 4)
-            else:
-                raw, sid, tn = run_tower(cls_tower, 'c')
-                final(raw, sid, tn, [(fin_cls, 1.0)], fin_cls.out_channels, 0)
-                raw, sid, tn = run_tower(reg_tower, 'r')
-                final(raw, sid, tn, [(fin_reg, scale_l)], 0, 4)
-            point_off += fh * fw
+        def final(raw, stats_id, tnorm, convs, n_cls, n_reg):
+            ws, scs, shs = [], [], []
+            for (fc, sc) in convs:
+                ws.append(fc.weight.detach().float().cpu().reshape(fc.out_channels, -1).to(torch.bfloat16).float())
+                b = fc.bias.detach().float().cpu() if fc.bias is not None else torch.zeros(fc.out_channels)
+                scs.append(torch.full((fc.out_channels,), sc))
+                shs.append(b * sc)
+            self._push(dict(kind=nat.OP_HEAD_FINAL, H=fh, W=fw, Cin=ws[0].shape[1], Ho=fh, Wo=fw, Cout=n_cls + n_reg,
+                            gn_groups=tnorm.num_groups, inp=raw, stats=stats_id, n_cls=n_cls, n_reg=n_reg,
+                            point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
+                            scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
+                            gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
+                            beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias),
+                            modules=(tnorm, [c for c, _ in convs], [sc for _, sc in convs])))
+
+        if cls_tower is reg_tower:
+            raw, sid, tn = run_tower(cls_tower, 'm')
+            final(raw, sid, tn, [(fin_cls, 1.0), (fin_reg, scale_l)], fin_cls.out_channels, 4)
+        else:
+            raw, sid, tn = run_tower(cls_tower, 'c')
+            final(raw, sid, tn, [(fin_cls, 1.0)], fin_cls.out_channels, 0)
+            raw, sid, tn = run_tower(reg_tower, 'r')
+            final(raw, sid, tn, [(fin_reg, scale_l)], 0, 4)
+
+    def _push(self, op):
+        op['branch'] = self._branch
+        self._ops.append(op)
 
     def _cached_f32(self, cache, key, t):
         if key not in cache:
@@ -279,24 +300,34 @@ class InferencePlan(object):
         n_stats = len([o for o in self._ops if o['kind'] == nat.OP_CONV and o.get('gn_groups')])
         stats_each = self.N * 16 * 2 * 8
         self.stats_bytes = (n_stats * stats_each + 255) & ~255
-        arena = _Arena(base=self.stats_bytes)
-        last_use = {}
+        producer = {op['out']: op['branch'] for op in self._ops if op.get('out') is not None}
+        last_use, shared = {}, set()
         for i, op in enumerate(self._ops):
             for k in ('inp', 'res'):
                 if op.get(k) is not None:
                     last_use[op[k]] = i
-        offsets = {}
+                    if producer[op[k]] != op['branch']:
+                        shared.add(op[k])      # read by another branch (a backbone tap): lives for the whole forward
+        n_br = 1 + max(op['branch'] for op in self._ops)
+        arenas = [_Arena(base=0) for _ in range(n_br)]
+        local = {}                              # name -> (branch, offset inside the branch's arena)
+        no_reuse = bool(os.environ.get('LFD_B200_NO_REUSE'))
         for i, op in enumerate(self._ops):
             if op.get('out') is not None:
-                offsets[op['out']] = arena.alloc(self._tensors[op['out']])
+                local[op['out']] = (op['branch'], arenas[op['branch']].alloc(self._tensors[op['out']]))
             for name, lu in list(last_use.items()):
-                if lu == i and not os.environ.get('LFD_B200_NO_REUSE'):
-                    arena.release(offsets[name], self._tensors[name])
+                if lu == i:
                     del last_use[name]
-            if op.get('out') is not None and op['out'] not in last_use:
-                # produced but never consumed by a later op (cannot happen for a well-formed graph) -- keep it
-                pass
-        self.workspace_bytes = max(arena.top, 256)
+                    if not no_reuse and name not in shared:
+                        arenas[local[name][0]].release(local[name][1], self._tensors[name])
+        bases, top = [], self.stats_bytes
+        for a in arenas:
+            bases.append(top)
+            top += (a.top + 255) & ~255
+        offsets = {name: bases[b] + off for name, (b, off) in local.items()}
+        self.workspace_bytes = max(top, 256)
+        self.tensor_branch = {name: b for name, (b, _) in local.items()}
+        self.shared_tensors = shared
         self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=dev)
         self.activation_bytes = sum(self._tensors.values())
         fb, bb = self.params_f32.data_ptr(), self.params_bf16.data_ptr()
@@ -308,6 +339,7 @@ class InferencePlan(object):
             o.ksize, o.stride, o.relu = op.get('ksize', 1), op.get('stride', 1), op.get('relu', 0)
             o.gn_groups = op.get('gn_groups', 0)
             o.n_cls, o.n_reg, o.point_off, o.cc = op.get('n_cls', 0), op.get('n_reg', 0), op.get('point_off', 0), op.get('cc', 0)
+            o.branch = op.get('branch', 0)
             o.in_off = offsets[op['inp']] if op.get('inp') is not None else -1
             o.out_off = offsets[op['out']] if op.get('out') is not None else -1
             o.res_off = offsets[op['res']] if op.get('res') is not None else -1

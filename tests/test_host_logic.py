@@ -103,4 +103,15 @@ def test_planner_builds_expected_graph(name, n_conv):
             if born[a] <= last_use.get(b, born[b]) and born[b] <= last_use.get(a, born[a]):   # lifetimes intersect
                 oa, ob = plan.offsets[a], plan.offsets[b]
                 assert oa + plan._tensors[a] <= ob or ob + plan._tensors[b] <= oa, (a, b)
-    assert plan.workspace_bytes < plan.activation_bytes + plan.stats_bytes + 4096
+    assert plan.workspace_bytes < plan.activation_bytes + plan.stats_bytes + 65536
+    # branches (per-level neck + head chains) run concurrently with the backbone: their buffers must be disjoint from
+    # every other branch's, and a tap read across branches is never recycled
+    branches = sorted(set(plan.tensor_branch.values()))
+    assert branches == list(range(len(plan.level_sizes) + 1))
+    for a in names:
+        for b in names:
+            if a < b and (plan.tensor_branch[a] != plan.tensor_branch[b] or a in plan.shared_tensors or b in plan.shared_tensors):
+                oa, ob = plan.offsets[a], plan.offsets[b]
+                if plan.tensor_branch[a] != plan.tensor_branch[b] or born[b] >= born[a] and a in plan.shared_tensors or born[a] >= born[b] and b in plan.shared_tensors:
+                    assert oa + plan._tensors[a] <= ob or ob + plan._tensors[b] <= oa, (a, b)
+    assert len(plan.shared_tensors) == len(plan.level_sizes)

@@ -11,6 +11,7 @@
 using namespace lfd;
 
 static thread_local char g_err[512] = "";
+static long long* g_trace = nullptr;   // debugging: see lfd_debug_set_trace
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -63,6 +64,10 @@ struct lfd_plan {
 };
 static constexpr size_t kMaxGraphs = 32;
 
+extern "C" int lfd_debug_set_trace(void* device_buffer) {
+    g_trace = reinterpret_cast<long long*>(device_buffer);
+    return LFD_OK;
+}
 extern "C" int lfd_abi_version(void) { return LFD_B200_ABI_VERSION; }
 extern "C" const char* lfd_last_error(void) { return g_err; }
 extern "C" int lfd_device_sm_count(void) {
@@ -157,6 +162,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 UmmaConvParams p = po.cp;
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
                 p.scale = o.scale; p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
+                p.trace = g_trace;
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
             break;

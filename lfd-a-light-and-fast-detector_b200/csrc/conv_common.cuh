@@ -28,6 +28,7 @@ struct UmmaConvParams {
     const float* scale;         // [Cout]
     const float* shift;         // [Cout]
     double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
+    long long* trace;           // debugging: clock64() timeline of CTA 0 ([role 0..2][tile < 32][4]), normally null
     int N, H, W, Cin, Ho, Wo, Cout;
     int relu, gn_groups, mode;
     int tiles_x, tiles_per_img, num_tiles;

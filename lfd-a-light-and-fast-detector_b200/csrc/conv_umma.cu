@@ -34,6 +34,9 @@ static constexpr int kProdThreads = 128;
 static constexpr int kThreads = kEpiThreads + 32 + kProdThreads;  // 288
 static constexpr int kLag = 2;                                     // cp.async groups kept in flight per producer thread
 
+#define LFD_TRACE(role, idx, slot) \
+    do { if (p.trace && blockIdx.x == 0 && (idx) < 32) p.trace[((role) * 32 + (idx)) * 4 + (slot)] = clock64(); } while (0)
+
 struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's input origin) and where it goes
     int16_t dy, dx;
     uint16_t slot;
@@ -145,8 +148,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                 }
                 cp_async_commit();
             }
+            if (tid == 0) LFD_TRACE(2, tcount, 0);
             mbar_wait(&tfull[a], aph);
             tc_fence_after_sync();
+            if (tid == 0) LFD_TRACE(2, tcount, 1);
             if (p.res) {
                 cp_async_wait<0>();
                 named_bar_sync(1, kEpiThreads);
@@ -184,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
             }
             tc_fence_before_sync();
             mbar_arrive(&tempty[a]);  // accumulator stage may be overwritten by the next-but-one tile
+            if (tid == 0) LFD_TRACE(2, tcount, 2);
             named_bar_sync(1, kEpiThreads);
             if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk
                 const int g = tid >> 3, sl = tid & 7;  // host guarantees Cout/groups == 8 and groups == 16
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                 *reinterpret_cast<uint4*>(p.out + ((img_out + q) * p.Cout + c * 8)) = val;
             }
             named_bar_sync(1, kEpiThreads);  // staging free again
+            if (tid == 0) LFD_TRACE(2, tcount, 3);
         }
     } else if (warp == kMmaWarp) {
         // ============================================================== MMA ISSUER
@@ -234,14 +241,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; lane == 0 && tile < p.num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+            LFD_TRACE(1, tcount, 0);
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after_sync();
+            LFD_TRACE(1, tcount, 1);
             const uint32_t d_tmem = tmem_base + a * p.Cout;
             for (int cc = 0; cc < n_cc; ++cc, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after_sync();
                 fence_proxy_async_smem();
+                if (cc == 0) LFD_TRACE(1, tcount, 2);
                 {
                     const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
                     const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                         }
                     }
                     umma_commit(&empty[s]);
-                    if (cc == n_cc - 1) umma_commit(&tfull[a]);
+                    if (cc == n_cc - 1) { umma_commit(&tfull[a]); LFD_TRACE(1, tcount, 3); }
                 }
             }
         }
@@ -291,7 +301,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
             const __nv_bfloat16* img = p.in + (size_t)n * HW * p.Cin + ch * 8;
             for (int cc = 0; cc < n_cc; ++cc, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
+                if (ptid == 0) LFD_TRACE(0, it, 0);
                 mbar_wait(&empty[s], ph ^ 1);
+                if (ptid == 0) LFD_TRACE(0, it, 1);
                 const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
                 if (!p.b_resident && ptid == 0) {
                     mbar_arrive_expect_tx(&full[s], p.b_slice_bytes);
@@ -317,10 +329,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                     }
                 }
                 cp_async_commit();
+                if (ptid == 0) LFD_TRACE(0, it, 2);
                 if (it >= lag) {
                     if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
                     fence_proxy_async_smem();
                     mbar_arrive(&full[(it - lag) % SA]);
+                    if (ptid == 0) LFD_TRACE(0, it - lag, 3);
                 }
             }
         }

@@ -1,0 +1,42 @@
+# -*- coding: utf-8 -*-
+"""Debug aid: clock64() timeline of CTA 0 of one tcgen05 conv launch (producer / MMA issuer / epilogue per tile)."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [HERE, os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), 'lfd-a-light-and-fast-detector_b200')]
+import torch  # noqa: E402
+
+from gpu_ops import run_conv  # noqa: E402
+from lfd import _native as nat  # noqa: E402
+from test_gpu_conv import _make  # noqa: E402
+
+CASES = {'3x3s1': (8, 90, 160, 64, 64, 3, 1, True, False, 0), 'flat': (8, 180, 320, 64, 64, 1, 1, True, False, 0),
+         '3x3s2': (8, 180, 320, 64, 64, 3, 2, True, False, 0), 'stream': (8, 12, 20, 128, 128, 3, 1, True, False, 0)}
+
+
+def main():
+    for name in (sys.argv[1:] or list(CASES)):
+        case = CASES[name]
+        x, w, scale, shift, res = _make(case)
+        buf = torch.zeros((3, 32, 4), dtype=torch.int64, device='cuda')
+        run_conv(x, w, scale, shift, case[6], case[7], res=res)          # warm-up (weights / L2)
+        nat.lib().lfd_debug_set_trace(nat.ptr(buf))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out, _, q = run_conv(x, w, scale, shift, case[6], case[7], res=res)
+        nat.lib().lfd_debug_set_trace(None)
+        t = buf.cpu()
+        t0 = int(t[t > 0].min())
+        rel = (t - t0).clamp(min=-1)
+        print('== %s %s plan=%s' % (name, case, q))
+        for role, rn, cols in ((0, 'producer', 'wait_empty got_empty issued arrived_full'), (1, 'mma', 'wait_tempty got_tempty first_full committed'),
+                               (2, 'epilogue', 'wait_tfull got_tfull tmem_read_done stored')):
+            print('  %s  [%s]' % (rn, cols))
+            for i in range(12):
+                if int(t[role, i].max()) == 0:
+                    break
+                print('    %2d  %s' % (i, '  '.join('%7d' % int(v) for v in rel[role, i])))
+
+
+if __name__ == '__main__':
+    main()

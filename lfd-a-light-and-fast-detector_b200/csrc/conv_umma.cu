@@ -7,18 +7,21 @@
 //
 // Formulation (NHWC bf16 activations, fp32 accumulate in TMEM):
 //   D[128 output pixels, Cout] = sum over taps (kh,kw) and channel chunks of  A_tap[128, 16] * W_tap[16, Cout]
-//   * one CTA per SM, persistent over output tiles, warp-specialised:
-//       warps 0-3  epilogue   : TMEM -> regs -> scale/shift (+residual) (+ReLU) -> bf16 -> smem -> coalesced store
-//                               (+ optional GroupNorm partial statistics of the stored tensor)
-//       warp  4    MMA issuer : one elected lane issues tcgen05.mma, commits to mbarriers
-//       warps 5-8  producers  : cp.async (16 B, zero-fill = conv padding) of the input halo tile into the A ring
+//   * persistent CTAs (1 per SM for 3x3, 2 per SM for the memory-bound 1x1 layers), warp-specialised:
+//       warps 0..E-1  epilogue   : TMEM -> regs -> scale/shift (+residual) (+ReLU) -> bf16 -> smem -> coalesced store
+//                                  (+ optional GroupNorm partial statistics of the stored tensor);
+//                                  E = 4 (one warp per TMEM lane quarter) or 8 (two warps per quarter, each half the columns)
+//       warp  E       MMA issuer : one lane issues tcgen05.mma with pre-built descriptors, commits to mbarriers
+//       warps E+1..   producers  : cp.async (16 B, zero-fill = conv padding) of the input halo tile into the A ring;
+//                                  completion is signalled by cp.async.mbarrier.arrive (no thread waits on its own copies)
 //   * the input halo tile is loaded ONCE per (tile, channel-chunk) into "pixel planes"
 //       plane[k-chunk][pixel][8 channels = 16 B]
 //     which is exactly the UMMA K-major / no-swizzle canonical layout (8-row core matrices of 16 B rows,
 //     SBO between 8-row groups, LBO between 16-byte K chunks).  A 3x3 tap is then just a *shifted view*
 //     (start address += tap offset, SBO = halo row pitch), so the 9 taps re-read shared memory, never L2.
 //     Stride-2 convolutions de-interleave the halo into 4 row/column parity planes so that every tap is
-//     again a unit-stride view.
+//     again a unit-stride view.  The plane pitch (LBO) is an ODD multiple of 16 B so that the 8 channel
+//     chunks of one pixel land in 8 different bank groups (conflict-free cp.async writes).
 //   * weights: pre-packed on the host in [channel-chunk][tap][k-chunk][Cout][8] order and brought in by
 //     the TMA engine as 1-D bulk copies (cp.async.bulk -> UBLKCP), either once (resident) or per stage
 //     (streamed, for 3x3x128x128 which does not fit next to the A ring).
@@ -28,11 +31,7 @@
 
 namespace lfd {
 
-static constexpr int kEpiThreads = 128;
-static constexpr int kMmaWarp = 4;
 static constexpr int kProdThreads = 128;
-static constexpr int kThreads = kEpiThreads + 32 + kProdThreads;  // 288
-static constexpr int kLag = 2;                                     // cp.async groups kept in flight per producer thread
 
 #define LFD_TRACE(role, idx, slot) \
     do { if (p.trace && blockIdx.x == 0 && (idx) < 32) p.trace[((role) * 32 + (idx)) * 4 + (slot)] = clock64(); } while (0)
@@ -44,7 +43,22 @@ struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvParams p) {
+__device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of tap's shifted view inside a plane
+    if (MODE == MODE_3X3S1) return (tap / 3) * 10 + (tap % 3);
+    if (MODE == MODE_3X3S2) {
+        const int kh = tap / 3, kw = tap % 3;
+        return (kh == 1 ? 0 : 288) + (kw == 1 ? 0 : (kh == 1 ? 144 : 153)) + (kh == 2 ? 9 : 0) + (kw == 2 ? 1 : 0);
+    }
+    return 0;
+}
+
+template <int MODE, int EPI_WARPS>
+__global__ void __launch_bounds__(EPI_WARPS * 32 + 32 + kProdThreads, (EPI_WARPS == 4 ? 2 : 1))
+conv_umma_kernel(const UmmaConvParams p) {
+    constexpr int kEpiThreads = EPI_WARPS * 32;
+    constexpr int kMmaWarp = EPI_WARPS;
+    constexpr int kThreads = kEpiThreads + 32 + kProdThreads;
+    constexpr int TAPS = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : 1;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
     uint64_t* empty = full + kMaxStages;
@@ -84,26 +98,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
         s_shift[c] = p.shift[c];
     }
     // halo pixel table (tile independent)
-    for (int i = tid; i < p.n_px; i += kThreads) {
-        PxEntry e;
-        e.pad = 0;
-        if (MODE == MODE_FLAT) {
-            e.dy = 0; e.dx = (int16_t)i; e.slot = (uint16_t)i;
-        } else if (MODE == MODE_3X3S1) {
-            int r = i / 10, c = i % 10;
-            e.dy = (int16_t)(r - 1); e.dx = (int16_t)(c - 1); e.slot = (uint16_t)i;
-        } else if (MODE == MODE_1X1S2) {
-            int r = i >> 3, c = i & 7;
-            e.dy = (int16_t)(2 * r); e.dx = (int16_t)(2 * c); e.slot = (uint16_t)i;
-        } else {  // MODE_3X3S2: EE(16x8) | EO(16x9) | OE(17x8) | OO(17x9); all planes use pitch 9
-            int j = i, r, c, base, rodd, codd;
-            if (j < 128) { r = j >> 3; c = j & 7; base = 0; rodd = 0; codd = 0; }
-            else if ((j -= 128) < 144) { r = j / 9; c = j % 9; base = 144; rodd = 0; codd = 1; }
-            else if ((j -= 144) < 136) { r = j >> 3; c = j & 7; base = 288; rodd = 1; codd = 0; }
-            else { j -= 136; r = j / 9; c = j % 9; base = 441; rodd = 1; codd = 1; }
-            e.dy = (int16_t)(2 * r - rodd); e.dx = (int16_t)(2 * c - codd); e.slot = (uint16_t)(base + r * 9 + c);
+    if (MODE != MODE_FLAT) {
+        for (int i = tid; i < p.n_px; i += kThreads) {
+            PxEntry e;
+            e.pad = 0;
+            if (MODE == MODE_3X3S1) {
+                int r = i / 10, c = i % 10;
+                e.dy = (int16_t)(r - 1); e.dx = (int16_t)(c - 1); e.slot = (uint16_t)i;
+            } else if (MODE == MODE_1X1S2) {
+                int r = i >> 3, c = i & 7;
+                e.dy = (int16_t)(2 * r); e.dx = (int16_t)(2 * c); e.slot = (uint16_t)i;
+            } else {  // MODE_3X3S2: EE(16x8) | EO(16x9) | OE(17x8) | OO(17x9); all planes use pitch 9
+                int j = i, r, c, base, rodd, codd;
+                if (j < 128) { r = j >> 3; c = j & 7; base = 0; rodd = 0; codd = 0; }
+                else if ((j -= 128) < 144) { r = j / 9; c = j % 9; base = 144; rodd = 0; codd = 1; }
+                else if ((j -= 144) < 136) { r = j >> 3; c = j & 7; base = 288; rodd = 1; codd = 0; }
+                else { j -= 136; r = j / 9; c = j % 9; base = 441; rodd = 1; codd = 1; }
+                e.dy = (int16_t)(2 * r - rodd); e.dx = (int16_t)(2 * c - codd); e.slot = (uint16_t)(base + r * 9 + c);
+            }
+            table[i] = e;
         }
-        table[i] = e;
     }
     tc_fence_before_sync();
     __syncthreads();
@@ -112,15 +126,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
 
     const int HW = p.H * p.W;
     const int n_cc = p.Cin / p.Cc;
-    const int taps = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : 1;
 
-    if (warp < 4) {
+    if (warp < EPI_WARPS) {
         // ============================================================== EPILOGUE
-        const int m = tid;  // D row == TMEM lane
-        const int cpr = p.Cout >> 3;          // 16 B chunks per staged row (power of two)
+        const int m = (warp & 3) * 32 + lane;        // D row == TMEM lane (a warp may only touch lane quarter warp % 4)
+        const int chalf = warp >> 2;                  // EPI_WARPS == 8: second warp of the quarter takes the upper columns
+        const int ccols = p.Cout / (EPI_WARPS / 4);   // columns handled by this thread
+        const int ccol0 = chalf * ccols;
+        const int cpr = p.Cout >> 3;                  // 16 B chunks per staged row (power of two)
         const int l2cpr = p.log2_cpr;
         const int row_bytes = p.Cout * 2;
-        const int l2rp = p.log2_rp128;         // log2(rows per 128 B): swizzle granularity for rows shorter than 128 B
+        const int l2rp = p.log2_rp128;                // log2(rows per 128 B): swizzle granularity for rows shorter than 128 B
         const int swz_mask = (cpr < 8 ? cpr : 8) - 1;
         const int HoWo = p.Ho * p.Wo;
         const uint32_t stg = smem_u32(staging);
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
             int oy0 = 0, ox0 = 0, p0 = 0;
             if (MODE == MODE_FLAT) p0 = t * 128;
             else { oy0 = (t / p.tiles_x) * 16; ox0 = (t % p.tiles_x) * 8; }
-            const size_t img_out = (size_t)n * p.Ho * p.Wo;
+            const size_t img_out = (size_t)n * HoWo;
             // pixel index (within the image) of staged row r, or -1 when outside the feature map
             auto row_pixel = [&](int r) -> int {
                 if (MODE == MODE_FLAT) { int q = p0 + r; return q < HoWo ? q : -1; }
@@ -140,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
             };
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
             if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
+#pragma unroll 4
                 for (int e = tid; e < 128 * cpr; e += kEpiThreads) {
                     const int r = e >> l2cpr, c = e & (cpr - 1);
                     const int q = row_pixel(r);
@@ -156,22 +173,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                 cp_async_wait<0>();
                 named_bar_sync(1, kEpiThreads);
             }
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * p.Cout;
+            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a * p.Cout + ccol0;
             uint8_t* my_row = staging + m * row_bytes;
             const int my_swz = (m >> l2rp) & swz_mask;
-            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            for (int c0 = 0; c0 < ccols; c0 += 32) {
                 float v[32];
                 tmem_ld16(trow + c0, v);
-                if (c0 + 16 < p.Cout) tmem_ld16(trow + c0 + 16, v + 16);
+                if (c0 + 16 < ccols) tmem_ld16(trow + c0 + 16, v + 16);
                 tmem_ld_wait();
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    if (c0 + h * 8 >= p.Cout) break;
-                    const int chunk = (c0 >> 3) + h;
-                    uint4* slot = reinterpret_cast<uint4*>(my_row + ((chunk ^ my_swz) << 4));
+                    if (c0 + h * 8 >= ccols) break;
+                    const int col = ccol0 + c0 + h * 8;
+                    uint4* slot = reinterpret_cast<uint4*>(my_row + (((col >> 3) ^ my_swz) << 4));
                     float o[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[h * 8 + j], s_scale[c0 + h * 8 + j], s_shift[c0 + h * 8 + j]);
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[h * 8 + j], s_scale[col + j], s_shift[col + j]);
                     if (p.res) {
                         uint4 rv = *slot;
                         o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
@@ -191,10 +208,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
             mbar_arrive(&tempty[a]);  // accumulator stage may be overwritten by the next-but-one tile
             if (tid == 0) LFD_TRACE(2, tcount, 2);
             named_bar_sync(1, kEpiThreads);
-            if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk
-                const int g = tid >> 3, sl = tid & 7;  // host guarantees Cout/groups == 8 and groups == 16
+            if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk (16 groups)
+                constexpr int TPG = kEpiThreads / 16;  // threads per group
+                const int g = tid / TPG, sl = tid % TPG;
                 float s1 = 0.f, s2 = 0.f;
-                for (int r = sl; r < 128; r += 8) {
+                for (int r = sl; r < 128; r += TPG) {
                     if (row_pixel(r) < 0) continue;
                     uint4 q = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((g ^ ((r >> l2rp) & swz_mask)) << 4));
                     float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
@@ -203,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                     for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
                 }
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
+                for (int o = 1; o < TPG; o <<= 1) {
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
@@ -213,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                     atomicAdd(dst + 1, (double)s2);
                 }
             }
+#pragma unroll 4
             for (int e = tid; e < 128 * cpr; e += kEpiThreads) {  // coalesced store
                 const int r = e >> l2cpr, c = e & (cpr - 1);
                 const int q = row_pixel(r);
@@ -225,57 +244,62 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
         }
     } else if (warp == kMmaWarp) {
         // ============================================================== MMA ISSUER
+        // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
+        // lane issues the tcgen05 instructions.
         const uint32_t idesc = umma_idesc_bf16(128, p.Cout);
-        const uint32_t lbo_a = p.lbo_a, sbo_a = p.sbo_a;
-        const uint32_t lbo_b = p.Cout * 16, sbo_b = 128;
+        const uint32_t lbo_b = p.Cout * 16;
+        // descriptors differ only in the 14-bit start-address field (bytes >> 4): pre-compute everything else
+        const uint64_t adesc0 = umma_smem_desc(0, p.lbo_a, p.sbo_a);
+        const uint64_t bdesc0 = umma_smem_desc(0, lbo_b, 128);
+        const uint32_t a_k16 = (2 * p.lbo_a) >> 4;      // address-field step per 16 input channels (A)
+        const uint32_t b_k16 = (2 * lbo_b) >> 4;        //   (B)
+        const uint32_t b_tap = (cpc * lbo_b) >> 4;      // address-field step per tap (B)
+        const int nk16 = p.Cc >> 4;
         if (p.b_resident) {
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 mbar_arrive_expect_tx(wbar, p.w_total_bytes);
                 for (uint32_t off = 0; off < p.w_total_bytes; off += 32768) {
-                    uint32_t n = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
-                    bulk_g2s(smem_u32(wres) + off, reinterpret_cast<const uint8_t*>(p.w) + off, n, wbar);
+                    uint32_t nb = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
+                    bulk_g2s(smem_u32(wres) + off, reinterpret_cast<const uint8_t*>(p.w) + off, nb, wbar);
                 }
             }
-            if (lane == 0) mbar_wait(wbar, 0);
+            __syncwarp();
+            mbar_wait(wbar, 0);
         }
         uint32_t it = 0, tcount = 0;
-        for (int tile = blockIdx.x; lane == 0 && tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
-            LFD_TRACE(1, tcount, 0);
+            if (lane == 0) LFD_TRACE(1, tcount, 0);
             mbar_wait(&tempty[a], aph ^ 1);
             tc_fence_after_sync();
-            LFD_TRACE(1, tcount, 1);
+            if (lane == 0) LFD_TRACE(1, tcount, 1);
             const uint32_t d_tmem = tmem_base + a * p.Cout;
             for (int cc = 0; cc < n_cc; ++cc, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after_sync();
-                fence_proxy_async_smem();
-                if (cc == 0) LFD_TRACE(1, tcount, 2);
-                {
-                    const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
-                    const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes
-                                                         : a_base + p.a_stage_bytes;
-                    for (int tap = 0; tap < taps; ++tap) {
-                        uint32_t view = 0;
-                        if (MODE == MODE_3X3S1) view = (tap / 3) * 10 + (tap % 3);
-                        if (MODE == MODE_3X3S2) {
-                            const int kh = tap / 3, kw = tap % 3;
-                            const int base = (kh == 1 ? 0 : 288) + (kw == 1 ? 0 : (kh == 1 ? 144 : 153));
-                            view = base + (kh == 2 ? 9 : 0) + (kw == 2 ? 1 : 0);
-                        }
-                        for (int k16 = 0; k16 < p.Cc / 16; ++k16) {
-                            uint64_t ad = umma_smem_desc(a_base + view * 16 + 2 * k16 * lbo_a, lbo_a, sbo_a);
-                            uint64_t bd = umma_smem_desc(b_base + (tap * cpc + 2 * k16) * lbo_b, lbo_b, sbo_b);
-                            umma_bf16(d_tmem, ad, bd, idesc, (cc | tap | k16) != 0);
+                fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+                if (cc == 0 && lane == 0) LFD_TRACE(1, tcount, 2);
+                const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
+                const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes : a_base + p.a_stage_bytes;
+                const uint64_t ad = adesc0 + (a_base >> 4), bd = bdesc0 + (b_base >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16) {
+                            if (k16 < nk16)
+                                umma_bf16(d_tmem, ad + (uint32_t)(tap_view<MODE>(tap) + k16 * a_k16), bd + (uint32_t)(tap * b_tap + k16 * b_k16),
+                                          idesc, (cc | tap | k16) != 0);
                         }
                     }
                     umma_commit(&empty[s]);
-                    if (cc == n_cc - 1) { umma_commit(&tfull[a]); LFD_TRACE(1, tcount, 3); }
+                    if (cc == n_cc - 1) umma_commit(&tfull[a]);
                 }
+                __syncwarp();
+                if (cc == n_cc - 1 && lane == 0) LFD_TRACE(1, tcount, 3);
             }
         }
-        __syncwarp();
     } else {
         // ============================================================== PRODUCERS
         const int ptid = tid - (kEpiThreads + 32);
@@ -284,9 +308,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
         const int px0 = ptid >> p.log2_cpc;
         const int pstep = kProdThreads >> p.log2_cpc;
         const uint32_t ch_dst = ch * p.lbo_a;
-        // A full-barrier arrival for stage-iteration j is made at the end of iteration j+lag; the empty wait of
-        // iteration j+SA must come later than that, hence lag <= SA-1.
-        const uint32_t lag = SA >= 3 ? (uint32_t)kLag : 1u;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n = tile / p.tiles_per_img;
@@ -328,19 +349,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
                         cp_async16(dst_cc + pe.slot * 16, src_cc + (ok ? (y * p.W + x) : 0) * p.Cin, ok);
                     }
                 }
-                cp_async_commit();
+                cp_async_mbar_arrive(&full[s]);   // arrives when this thread's copies have landed
                 if (ptid == 0) LFD_TRACE(0, it, 2);
-                if (it >= lag) {
-                    if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-                    fence_proxy_async_smem();
-                    mbar_arrive(&full[(it - lag) % SA]);
-                    if (ptid == 0) LFD_TRACE(0, it - lag, 3);
-                }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        for (uint32_t k = (it > lag ? it - lag : 0); k < it; ++k) mbar_arrive(&full[k % SA]);
+        cp_async_wait_all();
     }
 
     // ------------------------------------------------------------------ teardown
@@ -355,6 +368,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const UmmaConvPa
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+static int epi_warps_of(int mode) { return (mode == MODE_3X3S1 || mode == MODE_3X3S2) ? 8 : 4; }
+
 int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid) {
     UmmaConvParams p;
     memset(&p, 0, sizeof(p));
@@ -365,6 +380,7 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     else if (g.ksize == 1 && g.stride == 2) mode = MODE_1X1S2;
     else return -1;
     if (g.Cin % 16 || g.Cout % 16 || g.Cout > 128 || g.Cout < 16) return -1;
+    if (epi_warps_of(mode) == 8 && g.Cout < 32) return -1;   // two epilogue warps per lane quarter need >= 16 columns each
     p.mode = mode;
     p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Ho = g.Ho; p.Wo = g.Wo; p.Cout = g.Cout;
     const int taps = g.ksize * g.ksize;
@@ -379,7 +395,9 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
         else if (mode == MODE_3X3S2) { p.n_px = 561; px_slots = 594; p.sbo_a = 144; }
         else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }
     }
-    p.lbo_a = px_slots * 16;
+    // plane pitch = odd multiple of 16 B: the 8 chunks of a pixel fall into 8 distinct 16-byte bank groups
+    const int plane_slots = px_slots | 1;
+    p.lbo_a = plane_slots * 16;
     p.num_tiles = p.tiles_per_img * g.N;
     const size_t staging = (size_t)128 * g.Cout * 2;
     const size_t fixed = kSmemStagingOff + staging;
@@ -392,11 +410,11 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     // Memory-bound 1x1 layers additionally cap the ring so that two CTAs fit on one SM (latency hiding).
     const int cands[3] = {64, 32, 16};
     int best_cc = 0, best_res = 0, best_st = 0;
+    auto a_bytes = [&](int cc) -> size_t { return (((size_t)plane_slots * (cc / 8) * 16) + 127) & ~(size_t)127; };
     auto stages_for = [&](int cc, int resident) -> int {
         if (g.Cin % cc) return 0;
-        const size_t a_stage = (size_t)px_slots * cc * 2;
         const size_t b_slice = (size_t)taps * cc * g.Cout * 2;
-        const size_t stage = a_stage + (resident ? 0 : b_slice);
+        const size_t stage = a_bytes(cc) + (resident ? 0 : b_slice);
         if (fixed + (resident ? w_total : 0) + 2 * stage > budget) return 0;
         int st = (int)((budget - fixed - (resident ? w_total : 0)) / stage);
         if (st > kMaxStages) st = kMaxStages;
@@ -420,15 +438,15 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     }
     if (!best_cc) return -2;
     p.Cc = best_cc; p.b_resident = best_res; p.stages = best_st;
-    p.a_stage_bytes = (uint32_t)((size_t)px_slots * best_cc * 2);
+    p.a_stage_bytes = (uint32_t)a_bytes(best_cc);
     p.b_slice_bytes = (uint32_t)((size_t)taps * best_cc * g.Cout * 2);
     p.stage_bytes = p.a_stage_bytes + (best_res ? 0 : p.b_slice_bytes);
     p.w_total_bytes = (uint32_t)w_total;
     p.smem_w_off = (uint32_t)fixed;
     p.smem_ring_off = (uint32_t)(fixed + (best_res ? w_total : 0));
-    // two CTAs per SM when a 3-deep ring fits in half of the shared memory (1x1 layers)
+    // two CTAs per SM when a >= 2-deep ring fits in half of the shared memory (1x1 layers; 4 epilogue warps each)
     p.ctas_per_sm = 1;
-    {
+    if (epi_warps_of(mode) == 4) {
         const size_t half = (227 * 1024) / 2 - 1024;
         const size_t base = p.smem_ring_off;
         if (base + 2 * (size_t)p.stage_bytes <= half) {
@@ -450,24 +468,24 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     return 0;
 }
 
-template <int MODE>
+template <int MODE, int EPI_WARPS>
 static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
         if (e != cudaSuccess) return e;
-        configured = 224 * 1024;
+        configured = true;
     }
-    conv_umma_kernel<MODE><<<grid, kThreads, smem, st>>>(p);
+    conv_umma_kernel<MODE, EPI_WARPS><<<grid, EPI_WARPS * 32 + 32 + kProdThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
     switch (p.mode) {
-        case MODE_FLAT: return launch_mode<MODE_FLAT>(p, smem, grid, st);
-        case MODE_3X3S1: return launch_mode<MODE_3X3S1>(p, smem, grid, st);
-        case MODE_3X3S2: return launch_mode<MODE_3X3S2>(p, smem, grid, st);
-        case MODE_1X1S2: return launch_mode<MODE_1X1S2>(p, smem, grid, st);
+        case MODE_FLAT: return launch_mode<MODE_FLAT, 4>(p, smem, grid, st);
+        case MODE_3X3S1: return launch_mode<MODE_3X3S1, 8>(p, smem, grid, st);
+        case MODE_3X3S2: return launch_mode<MODE_3X3S2, 8>(p, smem, grid, st);
+        case MODE_1X1S2: return launch_mode<MODE_1X1S2, 4>(p, smem, grid, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -69,6 +69,12 @@ LFD_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
 LFD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+LFD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// The mbarrier receives one arrival (counted against its expected-arrival count, hence .noinc) once ALL cp.async
+// operations issued so far by this thread have completed -- the thread itself does not wait.
+LFD_DEVINL void cp_async_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 LFD_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -78,6 +84,17 @@ LFD_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uin
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// true on exactly one (the lowest active) lane of a converged warp
+LFD_DEVINL bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---------------------------------------------------------------- tcgen05: TMEM alloc

@@ -59,7 +59,8 @@ enum { LFD_CONV_UMMA = 0, LFD_CONV_SIMT = 1 }; /* SIMT = cross-check kernel, val
 
 /* One fused layer.  Activations are bf16 NHWC at byte offsets into the caller's workspace.
  *   STEM0      3x3/s2 conv on the 3-channel image + scale/shift (+ReLU); in_off ignored (reads the external input);
- *              weight = float[27][Cout] (k = tap*3 + ci, bf16-representable values).
+ *              weight = bf16 packed [4][Cout][8]: k = 8*kc + j with k = (kh*3 + kw)*3 + ci, entries with k >= 27 are 0
+ *              (the K = 27 im2col operand, padded to 32, is assembled from the raw image inside the kernel).
  *   CONV       ksize in {1,3}, stride in {1,2}, pad = ksize/2; y = conv(x)*scale + shift (+res) (ReLU) -> bf16;
  *              weight = bf16 packed [Cin/cc][ksize^2][cc/8][Cout][8] with cc from lfd_conv_query;
  *              gn_groups > 0: also accumulates sum / sum-of-squares of the stored output per (image, group)

@@ -79,12 +79,14 @@ extern "C" int lfd_device_sm_count(void) {
 static ConvGeom geom_of(const lfd_op& o) {
     ConvGeom g;
     g.N = o.N; g.H = o.H; g.W = o.W; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.ksize = o.ksize; g.stride = o.stride;
+    g.stem = o.kind == LFD_OP_STEM0 ? 1 : 0;
+    if (g.stem) g.Cin = 32;   // 27 (kh, kw, ci) taps padded to 32
     return g;
 }
 
 extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int* cc, int* stages,
                               int* weights_resident, int* num_tiles, int64_t* smem_bytes) {
-    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride};
+    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride, 0};
     UmmaConvParams p;
     size_t smem = 0;
     int grid = 0;
@@ -128,10 +130,10 @@ static int plan_op(const lfd_op& o, int conv_impl, PlannedOp* out) {
     out->op = o;
     out->smem = 0;
     out->grid = 0;
-    if (o.kind == LFD_OP_CONV) {
+    if (o.kind == LFD_OP_CONV || o.kind == LFD_OP_STEM0) {
         rc = umma_conv_configure(geom_of(o), sm_count() > 0 ? sm_count() : 148, &out->cp, &out->smem, &out->grid);
         if (rc) return fail(LFD_ERR_UNSUPPORTED, "conv %dx%d s%d Cin=%d Cout=%d unsupported (rc=%d)", o.ksize, o.ksize, o.stride, o.Cin, o.Cout, rc);
-        if (out->cp.Cc != o.cc) return fail(LFD_ERR_INVALID, "weights packed with cc=%d but the kernel needs cc=%d", o.cc, out->cp.Cc);
+        if (o.kind == LFD_OP_CONV && out->cp.Cc != o.cc) return fail(LFD_ERR_INVALID, "weights packed with cc=%d but the kernel needs cc=%d", o.cc, out->cp.Cc);
     }
     (void)conv_impl;
     return LFD_OK;
@@ -142,12 +144,21 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
     const lfd_op& o = po.op;
     switch (o.kind) {
         case LFD_OP_STEM0: {
-            Stem0Params p;
-            p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
-            p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
-            p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu;
             if (!input) return fail(LFD_ERR_INVALID, "stem0 needs the external input pointer");
-            CUDA_TRY(stem0_launch(p, st));
+            if (conv_impl == LFD_CONV_SIMT) {
+                Stem0Params p;
+                p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
+                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift;
+                p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu;
+                CUDA_TRY(stem0_launch(p, st));
+            } else {
+                UmmaConvParams p = po.cp;
+                p.in_raw = input; p.input_format = input_format; p.in = nullptr;
+                p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off); p.res = nullptr;
+                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift; p.stats = nullptr;
+                p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace;
+                CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
+            }
             break;
         }
         case LFD_OP_CONV: {

@@ -7,7 +7,7 @@
 
 namespace lfd {
 
-enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3 };
+enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3, MODE_STEM = 4 };
 
 static constexpr int kMaxStages = 8;
 // dynamic shared memory map of conv_umma_kernel (bytes)
@@ -18,11 +18,13 @@ static constexpr int kSmemStagingOff = 6144; // epilogue staging tile 128 x Cout
 
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
+    int stem;   // 1: 3x3/s2 conv on the raw 3-channel image (K = 27 padded to 32), operand built by the producers
 };
 
 struct UmmaConvParams {
     const __nv_bfloat16* in;
     __nv_bfloat16* out;
+    const void* in_raw;         // MODE_STEM: the image, fp32 NCHW (input_format 0) or uint8 NHWC (1)
     const __nv_bfloat16* res;   // optional residual (same shape as out)
     const __nv_bfloat16* w;     // packed [cc][tap][kc][Cout][8]
     const float* scale;         // [Cout]
@@ -37,7 +39,8 @@ struct UmmaConvParams {
     int log2_cpc, log2_cpr, log2_rp128, tmem_cols, ctas_per_sm;
     uint32_t lbo_a, sbo_a;
     uint32_t a_stage_bytes, b_slice_bytes, stage_bytes, w_total_bytes;
-    uint32_t smem_w_off, smem_ring_off;
+    uint32_t smem_w_off, smem_ring_off, smem_stem_off;
+    int input_format;
 };
 
 // returns 0 when the geometry is supported by the tcgen05 kernel

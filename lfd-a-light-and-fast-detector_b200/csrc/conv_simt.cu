@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
     const int oy0 = blockIdx.y * kS0TileH, ox0 = blockIdx.x * kS0TileW;
     const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
     const int Cout = NG * 8;
-    for (int i = tid; i < 27 * Cout; i += kS0Threads) wsm[i] = p.w[i];
+    for (int i = tid; i < 27 * Cout; i += kS0Threads) {
+        const int k = i / Cout, nn = i % Cout;
+        wsm[i] = __bfloat162float(p.w[((k >> 3) * Cout + nn) * 8 + (k & 7)]);
+    }
     // input patch -> smem, rounded to bf16 (rounding point R0 of DESIGN.md)
     for (int i = tid; i < 3 * kS0PatchH * kS0PatchW; i += kS0Threads) {
         int ci, r, c;

@@ -42,6 +42,18 @@ struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's
     uint16_t pad;
 };
 
+// MODE_STEM: the raw-image patch of one 16x8 output tile: 33 rows x 17 pixels x 3 channels, kept in shared memory as
+// bf16 [ci][row][col] (already normalised / rounded), double buffered.
+static constexpr int kStemRows = 33, kStemCols = 17, kStemElems = 3 * kStemRows * kStemCols;   // 1683
+static constexpr int kStemPerThread = (kStemElems + kProdThreads - 1) / kProdThreads;          // 14
+static constexpr int kStemPatchBytes = ((kStemElems * 2 + 127) / 128) * 128;                   // 3456
+struct StemEntry {   // patch element e: where it comes from (row, offset inside the row) and where it goes
+    int16_t row;     // input row relative to the tile's first input row
+    int16_t off;     // u8 NHWC: byte offset inside the row (pixel*3 + ci); fp32 NCHW: pixel offset
+    uint16_t dst;    // element index in the patch [ci][row][col]
+    uint16_t ci;
+};
+
 template <int MODE>
 __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of tap's shifted view inside a plane
     if (MODE == MODE_3X3S1) return (tap / 3) * 10 + (tap % 3);
@@ -97,8 +109,21 @@ conv_umma_kernel(const UmmaConvParams p) {
         s_scale[c] = p.scale[c];
         s_shift[c] = p.shift[c];
     }
+    StemEntry* stem_table = reinterpret_cast<StemEntry*>(smem + p.smem_stem_off);
+    __nv_bfloat16* stem_patch = reinterpret_cast<__nv_bfloat16*>(smem + p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128);
+    if (MODE == MODE_STEM) {
+        for (int e = tid; e < kStemElems; e += kThreads) {
+            StemEntry t;
+            int ci, r, c;
+            if (p.input_format == 1) { r = e / (kStemCols * 3); const int b = e % (kStemCols * 3); c = b / 3; ci = b % 3; t.off = (int16_t)b; }
+            else { ci = e / (kStemRows * kStemCols); const int q = e % (kStemRows * kStemCols); r = q / kStemCols; c = q % kStemCols; t.off = (int16_t)c; }
+            t.row = (int16_t)r; t.ci = (uint16_t)ci;
+            t.dst = (uint16_t)((ci * kStemRows + r) * kStemCols + c);
+            stem_table[e] = t;
+        }
+    }
     // halo pixel table (tile independent)
-    if (MODE != MODE_FLAT) {
+    if (MODE != MODE_FLAT && MODE != MODE_STEM) {
         for (int i = tid; i < p.n_px; i += kThreads) {
             PxEntry e;
             e.pad = 0;
@@ -303,6 +328,70 @@ conv_umma_kernel(const UmmaConvParams p) {
     } else {
         // ============================================================== PRODUCERS
         const int ptid = tid - (kEpiThreads + 32);
+        if (MODE == MODE_STEM) {
+            // im2col of the raw image: K = 27 (kh, kw, ci) padded to 32.  The patch of tile t+1 is fetched into registers
+            // while the operand of tile t is assembled from the shared-memory patch of tile t.
+            const int my = ptid >> 3, mx = ptid & 7;            // this thread's output pixel inside the 16x8 tile
+            float pre[kStemPerThread];
+            auto fetch = [&](int tile) {
+                const int n = tile / p.tiles_per_img, t = tile - n * p.tiles_per_img;
+                const int iy0 = 2 * (t / p.tiles_x) * 16 - 1, ix0 = 2 * (t % p.tiles_x) * 8 - 1;
+#pragma unroll
+                for (int j = 0; j < kStemPerThread; ++j) {
+                    const int e = ptid + j * kProdThreads;
+                    float v = 0.f;
+                    if (e < kStemElems) {
+                        const StemEntry se = stem_table[e];
+                        const int y = iy0 + se.row;
+                        if ((unsigned)y < (unsigned)p.H) {
+                            if (p.input_format == 1) {
+                                const int b = ix0 * 3 + se.off;
+                                if (b >= 0 && b < p.W * 3)
+                                    v = ((float)__ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + y) * p.W * 3 + b) - 127.5f) * (1.0f / 127.5f);
+                            } else {
+                                const int x = ix0 + se.off;
+                                if ((unsigned)x < (unsigned)p.W)
+                                    v = __ldg(reinterpret_cast<const float*>(p.in_raw) + (((size_t)n * 3 + se.ci) * p.H + y) * p.W + x);
+                            }
+                        }
+                    }
+                    pre[j] = v;
+                }
+            };
+            uint32_t it = 0;
+            int buf = 0;
+            if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, buf ^= 1) {
+                __nv_bfloat16* patch = stem_patch + buf * (kStemPatchBytes / 2);
+#pragma unroll
+                for (int j = 0; j < kStemPerThread; ++j) {
+                    const int e = ptid + j * kProdThreads;
+                    if (e < kStemElems) patch[stem_table[e].dst] = __float2bfloat16_rn(pre[j]);   // rounding point R0
+                }
+                named_bar_sync(2, kProdThreads);
+                if (tile + (int)gridDim.x < p.num_tiles) fetch(tile + gridDim.x);
+                const uint32_t s = it % SA, ph = (it / SA) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
+                const unsigned short* pp = reinterpret_cast<const unsigned short*>(patch) + (2 * my) * kStemCols + 2 * mx;
+                uint32_t w[16];
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    uint32_t lo = 0, hi = 0;
+                    const int k0 = 2 * k2, k1 = 2 * k2 + 1;
+                    if (k0 < 27) lo = pp[((k0 % 3) * kStemRows + (k0 / 9)) * kStemCols + ((k0 / 3) % 3)];
+                    if (k1 < 27) hi = pp[((k1 % 3) * kStemRows + (k1 / 9)) * kStemCols + ((k1 / 3) % 3)];
+                    w[k2] = lo | (hi << 16);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t dst = a_base + c * p.lbo_a + ptid * 16;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+                }
+                fence_proxy_async_smem();       // generic-proxy st.shared -> tcgen05.mma reads
+                mbar_arrive(&full[s]);
+            }
+        } else {
         // every thread owns ONE 16-byte channel chunk (cpc divides 128) and walks the halo pixels with a fixed stride
         const int ch = ptid & (cpc - 1);
         const int px0 = ptid >> p.log2_cpc;
@@ -354,6 +443,7 @@ conv_umma_kernel(const UmmaConvParams p) {
             }
         }
         cp_async_wait_all();
+        }
     }
 
     // ------------------------------------------------------------------ teardown
@@ -374,7 +464,10 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     UmmaConvParams p;
     memset(&p, 0, sizeof(p));
     int mode;
-    if (g.ksize == 1 && g.stride == 1) mode = MODE_FLAT;
+    if (g.stem) {
+        if (g.ksize != 3 || g.stride != 2 || g.Cin != 32) return -1;   // Cin = 27 taps*channels padded to 32
+        mode = MODE_STEM;
+    } else if (g.ksize == 1 && g.stride == 1) mode = MODE_FLAT;
     else if (g.ksize == 3 && g.stride == 1) mode = MODE_3X3S1;
     else if (g.ksize == 3 && g.stride == 2) mode = MODE_3X3S2;
     else if (g.ksize == 1 && g.stride == 2) mode = MODE_1X1S2;
@@ -383,7 +476,7 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     if (epi_warps_of(mode) == 8 && g.Cout < 32) return -1;   // two epilogue warps per lane quarter need >= 16 columns each
     p.mode = mode;
     p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Ho = g.Ho; p.Wo = g.Wo; p.Cout = g.Cout;
-    const int taps = g.ksize * g.ksize;
+    const int taps = g.stem ? 1 : g.ksize * g.ksize;
     int px_slots;  // plane size in pixels (slots), n_px = pixels actually loaded
     if (mode == MODE_FLAT) {
         p.tiles_x = 0; p.tiles_per_img = (g.Ho * g.Wo + 127) / 128;
@@ -393,7 +486,7 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
         p.tiles_per_img = p.tiles_x * ((g.Ho + 15) / 16);
         if (mode == MODE_3X3S1) { p.n_px = 180; px_slots = 180; p.sbo_a = 160; }
         else if (mode == MODE_3X3S2) { p.n_px = 561; px_slots = 594; p.sbo_a = 144; }
-        else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }
+        else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }   // MODE_1X1S2 and MODE_STEM: one 16x8 plane
     }
     // plane pitch = odd multiple of 16 B: the 8 chunks of a pixel fall into 8 distinct 16-byte bank groups
     const int plane_slots = px_slots | 1;
@@ -462,6 +555,11 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     p.log2_rp128 = g.Cout * 2 >= 128 ? 0 : ilog2(128 / (g.Cout * 2));
     p.tmem_cols = 2 * g.Cout < 32 ? 32 : 2 * g.Cout;  // two accumulator stages; power of two because Cout is
     *smem_bytes = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
+    if (mode == MODE_STEM) {   // element table + two patch buffers behind the ring
+        p.smem_stem_off = (uint32_t)((*smem_bytes + 127) & ~(size_t)127);
+        *smem_bytes = p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128 + 2 * kStemPatchBytes;
+        p.ctas_per_sm = (2 * (*smem_bytes + 1024) <= 227 * 1024) ? 2 : 1;
+    }
     const int max_ctas = num_sms * p.ctas_per_sm;
     *grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
     *out = p;
@@ -486,6 +584,7 @@ cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cud
         case MODE_3X3S1: return launch_mode<MODE_3X3S1, 8>(p, smem, grid, st);
         case MODE_3X3S2: return launch_mode<MODE_3X3S2, 8>(p, smem, grid, st);
         case MODE_1X1S2: return launch_mode<MODE_1X1S2, 4>(p, smem, grid, st);
+        case MODE_STEM: return launch_mode<MODE_STEM, 4>(p, smem, grid, st);
     }
     return cudaErrorInvalidValue;
 }

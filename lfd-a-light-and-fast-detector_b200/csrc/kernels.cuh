@@ -11,7 +11,7 @@ static constexpr int kMaxLevels = 8;
 struct Stem0Params {
     const void* in;            // fp32 NCHW (input_format 0) or u8 NHWC (1)
     __nv_bfloat16* out;        // bf16 NHWC
-    const float* w;            // [9*3][Cout] fp32 holding bf16-rounded values, k = tap*3 + ci
+    const __nv_bfloat16* w;    // packed [4][Cout][8]: element (kc, n, j) = weight of output n for k = 8 kc + j, k = (kh*3 + kw)*3 + ci (k >= 27: 0)
     const float* scale;
     const float* shift;
     int input_format, N, H, W, Ho, Wo, Cout, relu;

@@ -37,6 +37,14 @@ def pack_conv_weight(weight, cc):
     return wt.permute(1, 0, 2, 4, 3).contiguous().to(torch.bfloat16)
 
 
+def pack_stem_weight(weight):
+    """[Cout, 3, 3, 3] float -> bf16 [4][Cout][8]: k = (kh*3 + kw)*3 + ci padded from 27 to 32 (stem operand order)."""
+    cout = weight.shape[0]
+    w27 = weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(27, cout)
+    w32 = torch.cat([w27, torch.zeros(5, cout)], 0).reshape(4, 8, cout)
+    return w32.permute(0, 2, 1).contiguous().to(torch.bfloat16)
+
+
 class _Arena(object):
     """First-fit allocator with coalescing free list over one workspace (byte offsets, 256 B aligned)."""
 
@@ -135,11 +143,10 @@ class InferencePlan(object):
             raise NotImplementedError('the B200 stem kernel handles the 3x3/s2 conv on a 3-channel image only')
         ho, wo = _conv_out(h, 3, 2), _conv_out(w, 3, 2)
         scale, shift = self._fold(conv, norm)
-        wt = conv.weight.detach().float().cpu().to(torch.bfloat16).float()   # [Cout, 3, 3, 3] rounded (Rw)
-        wt = wt.permute(2, 3, 1, 0).reshape(27, conv.out_channels)           # k = (kh*3+kw)*3 + ci
+        wt = pack_stem_weight(conv.weight)
         self._push(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
                               relu=int(relu), out=self._tensor(out_name, self.N, ho, wo, conv.out_channels),
-                              w_f32=self._add_f32(wt), scale=self._add_f32(scale), shift=self._add_f32(shift),
+                              w_bf16=self._add_bf16(wt), scale=self._add_f32(scale), shift=self._add_f32(shift),
                               modules=(conv, norm)))
         return ho, wo
 

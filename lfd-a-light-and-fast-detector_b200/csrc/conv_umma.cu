@@ -212,8 +212,14 @@ conv_umma_kernel(const UmmaConvParams p) {
                     const int col = ccol0 + c0 + h * 8;
                     uint4* slot = reinterpret_cast<uint4*>(my_row + (((col >> 3) ^ my_swz) << 4));
                     float o[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[h * 8 + j], s_scale[col + j], s_shift[col + j]);
+                    {
+                        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + col), sc1 = *reinterpret_cast<const float4*>(s_scale + col + 4);
+                        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + col), sh1 = *reinterpret_cast<const float4*>(s_shift + col + 4);
+                        o[0] = fmaf(v[h * 8 + 0], sc0.x, sh0.x); o[1] = fmaf(v[h * 8 + 1], sc0.y, sh0.y);
+                        o[2] = fmaf(v[h * 8 + 2], sc0.z, sh0.z); o[3] = fmaf(v[h * 8 + 3], sc0.w, sh0.w);
+                        o[4] = fmaf(v[h * 8 + 4], sc1.x, sh1.x); o[5] = fmaf(v[h * 8 + 5], sc1.y, sh1.y);
+                        o[6] = fmaf(v[h * 8 + 6], sc1.z, sh1.z); o[7] = fmaf(v[h * 8 + 7], sc1.w, sh1.w);
+                    }
                     if (p.res) {
                         uint4 rv = *slot;
                         o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
@@ -309,14 +315,11 @@ conv_umma_kernel(const UmmaConvParams p) {
                 const uint32_t b_base = p.b_resident ? smem_u32(wres) + cc * p.b_slice_bytes : a_base + p.a_stage_bytes;
                 const uint64_t ad = adesc0 + (a_base >> 4), bd = bdesc0 + (b_base >> 4);
                 if (elect_one_sync()) {
+                    for (int k16 = 0; k16 < nk16; ++k16) {
+                        const uint64_t adk = ad + (uint32_t)(k16 * a_k16), bdk = bd + (uint32_t)(k16 * b_k16);
 #pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-#pragma unroll
-                        for (int k16 = 0; k16 < 4; ++k16) {
-                            if (k16 < nk16)
-                                umma_bf16(d_tmem, ad + (uint32_t)(tap_view<MODE>(tap) + k16 * a_k16), bd + (uint32_t)(tap * b_tap + k16 * b_k16),
-                                          idesc, (cc | tap | k16) != 0);
-                        }
+                        for (int tap = 0; tap < TAPS; ++tap)
+                            umma_bf16(d_tmem, adk + (uint32_t)tap_view<MODE>(tap), bdk + (uint32_t)(tap * b_tap), idesc, (cc | k16 | tap) != 0);
                     }
                     umma_commit(&empty[s]);
                     if (cc == n_cc - 1) umma_commit(&tfull[a]);
@@ -332,30 +335,31 @@ conv_umma_kernel(const UmmaConvParams p) {
             // im2col of the raw image: K = 27 (kh, kw, ci) padded to 32.  The patch of tile t+1 is fetched into registers
             // while the operand of tile t is assembled from the shared-memory patch of tile t.
             const int my = ptid >> 3, mx = ptid & 7;            // this thread's output pixel inside the 16x8 tile
-            float pre[kStemPerThread];
+            // raw values of the NEXT tile's patch elements (loads are unconditional on clamped addresses so that all of
+            // them are in flight together; out-of-image elements are masked when the patch is written)
+            uint32_t raw[kStemPerThread];
+            uint32_t okmask = 0;
             auto fetch = [&](int tile) {
                 const int n = tile / p.tiles_per_img, t = tile - n * p.tiles_per_img;
                 const int iy0 = 2 * (t / p.tiles_x) * 16 - 1, ix0 = 2 * (t % p.tiles_x) * 8 - 1;
+                okmask = 0;
 #pragma unroll
                 for (int j = 0; j < kStemPerThread; ++j) {
-                    const int e = ptid + j * kProdThreads;
-                    float v = 0.f;
-                    if (e < kStemElems) {
-                        const StemEntry se = stem_table[e];
-                        const int y = iy0 + se.row;
-                        if ((unsigned)y < (unsigned)p.H) {
-                            if (p.input_format == 1) {
-                                const int b = ix0 * 3 + se.off;
-                                if (b >= 0 && b < p.W * 3)
-                                    v = ((float)__ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + y) * p.W * 3 + b) - 127.5f) * (1.0f / 127.5f);
-                            } else {
-                                const int x = ix0 + se.off;
-                                if ((unsigned)x < (unsigned)p.W)
-                                    v = __ldg(reinterpret_cast<const float*>(p.in_raw) + (((size_t)n * 3 + se.ci) * p.H + y) * p.W + x);
-                            }
-                        }
+                    const int e = min(ptid + j * kProdThreads, kStemElems - 1);
+                    const StemEntry se = stem_table[e];
+                    const int y = iy0 + se.row;
+                    const int yc = min(max(y, 0), p.H - 1);
+                    if (p.input_format == 1) {
+                        const int b = ix0 * 3 + se.off;
+                        const int bc = min(max(b, 0), p.W * 3 - 1);
+                        if (y == yc && b == bc) okmask |= 1u << j;
+                        raw[j] = __ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + yc) * p.W * 3 + bc);
+                    } else {
+                        const int x = ix0 + se.off;
+                        const int xc = min(max(x, 0), p.W - 1);
+                        if (y == yc && x == xc) okmask |= 1u << j;
+                        raw[j] = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.in_raw) + (((size_t)n * 3 + se.ci) * p.H + yc) * p.W + xc));
                     }
-                    pre[j] = v;
                 }
             };
             uint32_t it = 0;
@@ -366,7 +370,11 @@ conv_umma_kernel(const UmmaConvParams p) {
 #pragma unroll
                 for (int j = 0; j < kStemPerThread; ++j) {
                     const int e = ptid + j * kProdThreads;
-                    if (e < kStemElems) patch[stem_table[e].dst] = __float2bfloat16_rn(pre[j]);   // rounding point R0
+                    if (e < kStemElems) {
+                        float v = p.input_format == 1 ? ((float)raw[j] - 127.5f) * (1.0f / 127.5f) : __uint_as_float(raw[j]);
+                        if (!((okmask >> j) & 1u)) v = 0.f;
+                        patch[stem_table[e].dst] = __float2bfloat16_rn(v);   // rounding point R0
+                    }
                 }
                 named_bar_sync(2, kProdThreads);
                 if (tile + (int)gridDim.x < p.num_tiles) fetch(tile + gridDim.x);

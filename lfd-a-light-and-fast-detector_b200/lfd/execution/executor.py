@@ -1,0 +1,153 @@
+# -*- coding: utf-8 -*-
+"""Executor -- the train / val loop of the reference (lfd/execution/executor.py:13-259) with the same `config_dict`
+contract and hook bus, re-hosted on one process per GPU: the model is placed on this rank's device (no DataParallel
+wrap), each rank runs its shard of every batch through the native forward, the loss is the native `get_loss`, and
+gradients are combined by `parallel.allreduce_gradients` (one flat NCCL bucket) before clipping and the optimizer step.
+"""
+import logging
+import os
+from collections import OrderedDict
+
+import torch
+
+from .hooks import CheckpointHook, LoggerHook, LrSchedulerHook, OptimizerHook, SpeedHook, get_priority
+from .parallel import shard_batch, world
+from .utils import AverageMeter, get_root_logger, load_checkpoint, save_checkpoint
+
+_RESUME_BLACKLIST = ('timestamp', 'work_dir', 'log_path', 'training_epochs', 'gpu_list', 'display_interval', 'save_interval',
+                     'val_interval', 'weight_path', 'resume_path', 'batch_size', 'num_train_workers', 'num_val_workers',
+                     'train_dataset_path', 'optimizer_grad_clip_cfg')
+
+
+class Executor(object):
+
+    def __init__(self, config_dict):
+        self.config_dict = cfg = config_dict
+        if not os.path.exists(cfg['work_dir']):
+            os.makedirs(cfg['work_dir'], exist_ok=True)
+        cfg['logger'] = get_root_logger(cfg.get('log_path'), log_level=logging.INFO)
+        cfg.update(epoch=0, train_iter=0, inner_train_iter=0, inner_val_iter=0,
+                   train_average_meter=AverageMeter(), val_average_meter=AverageMeter())
+        if cfg.get('resume_path') is not None:
+            self.resume_weight()
+        elif cfg.get('weight_path') is not None:
+            self.load()
+        rank, _ = world()
+        gpu_list = cfg.get('gpu_list') or [0]
+        self.device = torch.device('cuda', gpu_list[rank % len(gpu_list)]) if torch.cuda.is_available() else torch.device('cpu')
+        cfg['model'] = cfg['model'].to(self.device)
+        if cfg.get('resume_path') is not None:
+            self.resume_optimizer()
+            self.resume_lr_scheduler()
+        self._hooks = []
+        self._register_all_hooks()
+
+    # ------------------------------------------------------------------ hooks
+    def _register_hook(self, hook, priority='NORMAL'):
+        hook.priority = get_priority(priority)
+        for i in range(len(self._hooks) - 1, -1, -1):
+            if hook.priority >= self._hooks[i].priority:
+                self._hooks.insert(i + 1, hook)
+                return
+        self._hooks.insert(0, hook)
+
+    def _register_all_hooks(self):
+        cfg = self.config_dict
+        self._register_hook(LrSchedulerHook(**cfg['warmup_setting']) if 'warmup_setting' in cfg else LrSchedulerHook(), 'NORMAL')
+        self._register_hook(OptimizerHook(cfg.get('optimizer_grad_clip_cfg'), cfg['training_epochs']), 'HIGH')
+        self._register_hook(SpeedHook(), 'LOW')
+        self._register_hook(LoggerHook(), 'VERY_LOW')
+        self._register_hook(CheckpointHook(), 'LOWEST')
+
+    def _call_hooks(self, fn_name):
+        for hook in self._hooks:
+            getattr(hook, fn_name)(self)
+
+    # ------------------------------------------------------------------ checkpoints
+    def _generate_meta(self):
+        types = [str, int, float, list, dict, bool, type(None), OrderedDict]
+        return {k: v for k, v in self.config_dict.items() if type(v) in types}
+
+    def save(self):
+        cfg = self.config_dict
+        save_checkpoint(cfg['model'], os.path.join(cfg['work_dir'], 'epoch_' + str(cfg['epoch']) + '.pth'),
+                        optimizer=cfg['optimizer'], lr_scheduler=cfg['lr_scheduler'], meta=self._generate_meta())
+
+    def load(self):
+        cfg = self.config_dict
+        cfg['logger'].info('Load weights from checkpoint:{}'.format(cfg['weight_path']))
+        load_checkpoint(cfg['model'], load_path=cfg['weight_path'], strict=True, logger=cfg['logger'])
+
+    def resume_weight(self):
+        cfg = self.config_dict
+        cfg['logger'].info('Resume training from checkpoint:{}'.format(cfg['resume_path']))
+        checkpoint = load_checkpoint(cfg['model'], load_path=cfg['resume_path'], strict=True, logger=cfg['logger'])
+        cfg['checkpoint'] = checkpoint
+        for k in _RESUME_BLACKLIST:
+            checkpoint['meta'].pop(k, None)
+        cfg.update(checkpoint['meta'])
+
+    def resume_optimizer(self):
+        if 'optimizer_state_dict' in self.config_dict['checkpoint']:
+            self.config_dict['optimizer'].load_state_dict(self.config_dict['checkpoint']['optimizer_state_dict'])
+
+    def resume_lr_scheduler(self):
+        if 'lr_scheduler_state_dict' in self.config_dict['checkpoint']:
+            self.config_dict['lr_scheduler'].load_state_dict(self.config_dict['checkpoint']['lr_scheduler_state_dict'])
+
+    def get_current_lr(self):
+        return self.config_dict['optimizer'].param_groups[0]['lr']
+
+    # ------------------------------------------------------------------ loops
+    def _to_device(self, image_batch):
+        t = torch.from_numpy(image_batch) if not torch.is_tensor(image_batch) else image_batch
+        return t.to(self.device, non_blocking=True)
+
+    def train(self):
+        cfg = self.config_dict
+        cfg['mode'] = 'train'
+        cfg['model'].train()
+        self._call_hooks('before_train_epoch')
+        for i, data_batch in enumerate(cfg['train_data_loader']):
+            cfg.update(inner_train_iter=i)
+            self._call_hooks('before_train_iter')
+            image_batch, annotation_batch, meta_batch = shard_batch(data_batch)
+            cfg.update(batch_size=len(annotation_batch))
+            predict_outputs = cfg['model'](self._to_device(image_batch))
+            loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
+            cfg.update(loss=loss_dict['loss'])
+            for name, value in loss_dict['loss_values'].items():
+                cfg['train_average_meter'].update(name, value, cfg['batch_size'])
+            cfg['train_iter'] += 1
+            self._call_hooks('after_train_iter')
+        cfg['epoch'] += 1
+        self._call_hooks('after_train_epoch')
+
+    def val(self):
+        cfg = self.config_dict
+        cfg['mode'] = 'val'
+        cfg['model'].eval()
+        self._call_hooks('before_val_epoch')
+        for i, data_batch in enumerate(cfg['val_data_loader']):
+            cfg.update(inner_val_iter=i)
+            self._call_hooks('before_val_iter')
+            image_batch, annotation_batch, meta_batch = shard_batch(data_batch)
+            cfg.update(batch_size=len(annotation_batch))
+            with torch.no_grad():
+                predict_outputs = cfg['model'](self._to_device(image_batch))
+                loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
+                predict_results = cfg['model'].get_results(predict_outputs, meta_batch)
+            for name, value in loss_dict['loss_values'].items():
+                cfg['val_average_meter'].update(name, value, cfg['batch_size'])
+            cfg.update(eval_results=(predict_results, meta_batch))
+            self._call_hooks('after_val_iter')
+        self._call_hooks('after_val_epoch')
+
+    def run(self):
+        cfg = self.config_dict
+        self._call_hooks('before_run')
+        while cfg['epoch'] < cfg['training_epochs']:
+            self.train()
+            if cfg.get('evaluator') is not None and cfg.get('val_interval', 0) > 0 and cfg['epoch'] % cfg['val_interval'] == 0:
+                self.val()
+        self._call_hooks('after_run')

@@ -1,0 +1,103 @@
+# -*- coding: utf-8 -*-
+"""CPU tests of the host-side training / sharding plumbing (lfd.execution): hook ordering, checkpoint format, lr warm-up,
+and the world_size-2 gloo path of the flat-bucket gradient all-reduce and of batch sharding."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import synth_model
+from lfd.execution import parallel
+from lfd.execution.hooks import Hook, LrSchedulerHook, get_priority
+from lfd.execution.utils import AverageMeter, load_checkpoint, save_checkpoint
+
+
+def test_shard_range_covers_everything_once():
+    for total in (0, 1, 7, 8, 64, 65):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_checkpoint_roundtrip_matches_reference_format():
+    model, sd = synth_model('WIDERFACE_XS')
+    opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[5, 7], gamma=0.1)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'w', 'epoch_3.pth')
+        save_checkpoint(model, path, optimizer=opt, lr_scheduler=sched, meta=dict(epoch=3, train_iter=30))
+        ck = torch.load(path, weights_only=False)
+        assert set(ck) == {'meta', 'state_dict', 'optimizer_state_dict', 'lr_scheduler_state_dict'}
+        assert list(ck['state_dict']) == list(sd) and 'time' in ck['meta']
+        other, _ = synth_model('WIDERFACE_XS', seed=1)
+        got = load_checkpoint(other, path, strict=True)
+        assert got['meta']['epoch'] == 3
+        for k, v in other.state_dict().items():
+            assert torch.equal(v, sd[k])
+        # DataParallel-style 'module.' prefixes of reference checkpoints are stripped
+        torch.save(dict(meta={}, state_dict={'module.' + k: v for k, v in sd.items()}), path)
+        load_checkpoint(other, path, strict=True)
+
+
+def test_lr_warmup_then_scheduler():
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=0.1)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[2], gamma=0.1)
+
+    class Ex(object):
+        config_dict = dict(optimizer=opt, lr_scheduler=sched, train_iter=0, epoch=0)
+    ex = Ex()
+    hook = LrSchedulerHook(by_epoch=False, warmup_mode='linear', warmup_loops=4, warmup_ratio=0.1)
+    hook.before_run(ex)
+    lrs = []
+    for it in range(6):
+        hook.before_train_iter(ex)
+        lrs.append(opt.param_groups[0]['lr'])
+        ex.config_dict['train_iter'] += 1
+    assert lrs[0] == pytest.approx(0.1 * (1 - 0.75 * 0.9)) and lrs[3] == pytest.approx(0.1) and lrs[5] == pytest.approx(0.1)
+    assert lrs == sorted(lrs)
+    assert get_priority('HIGH') < get_priority('LOW') and callable(Hook().before_run)
+    m = AverageMeter()
+    m.update('loss', 2.0, 3)
+    m.update('loss', 4.0, 1)
+    assert m.average('loss') == pytest.approx(2.5)
+
+
+def _worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    params = list(net.parameters())
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    if rank == 1:
+        params[-1].grad = None   # ragged: a gradient missing on one rank still reduces with the same bucket layout
+    n = parallel.allreduce_gradients(net.parameters())
+    grads = [p.grad.clone() for p in net.parameters()]
+    batch = (np.arange(10).reshape(5, 2), list(range(5)), [dict(i=i) for i in range(5)])
+    shard = parallel.shard_batch(batch)
+    total = parallel.allreduce_scalar(len(shard[1]))
+    torch.save(dict(n=n, grads=grads, shard=shard[1], total=total), out % rank)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_flat_bucket_allreduce_and_sharding():
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'r%d.pt')
+        port = 29500 + os.getpid() % 2000
+        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+        r0, r1 = torch.load(out % 0, weights_only=False), torch.load(out % 1, weights_only=False)
+    assert r0['n'] == r1['n'] == 4 * 3 + 3 + 3 * 2 + 2
+    for i, (a, b) in enumerate(zip(r0['grads'], r1['grads'])):
+        assert torch.equal(a, b)
+        expect = (1 + 2) * (i + 1) / 2.0 if i < 3 else 1 * (i + 1) / 2.0     # last grad existed on rank 0 only
+        assert torch.allclose(a, torch.full_like(a, expect))
+    assert r0['shard'] == [0, 1, 2] and r1['shard'] == [3, 4] and r0['total'] == r1['total'] == 5

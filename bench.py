@@ -91,11 +91,14 @@ def op_algorithmic(row, N, input_bytes_per_px):
     """(bytes, flops) one launch must move / compute: input once, output once, residual once, weights once."""
     k, cin, cout = row['ksize'], row['Cin'], row['Cout']
     px_in, px_out = N * row['H'] * row['W'], N * row['Ho'] * row['Wo']
+    tc = row.get('tail_cout', 0)            # fused 1x1 tail: the cout-channel intermediate never reaches HBM
+    cf = tc if tc else cout
+    tail_b, tail_f = (cout * tc * 2, 2.0 * px_out * cout * tc) if tc else (0, 0.0)
     if row['kind'] == 'stem0':
-        return px_in * input_bytes_per_px + px_out * cout * 2 + 27 * cout * 2, 2.0 * px_out * cout * 27
+        return px_in * input_bytes_per_px + px_out * cf * 2 + 27 * cout * 2 + tail_b, 2.0 * px_out * cout * 27 + tail_f
     if row['kind'] == 'conv':
-        b = px_in * cin * 2 + px_out * cout * 2 * (2 if row['res'] else 1) + k * k * cin * cout * 2
-        return b, 2.0 * px_out * cout * cin * k * k
+        b = px_in * cin * 2 + px_out * cf * 2 * (2 if row['res'] else 1) + k * k * cin * cout * 2 + tail_b
+        return b, 2.0 * px_out * cout * cin * k * k + tail_f
     if row['kind'] == 'gn_apply':
         return px_in * cin * 2 * 2, 0.0
     return px_in * cin * 2 + px_out * cout * 4, 2.0 * px_out * cout * cin   # head_final
@@ -308,8 +311,8 @@ def main():
     if args.profile_ops:
         for r in table:
             row = r['row']
-            sys.stderr.write('%-10s k%d s%d %3d->%3d %4dx%-4d res=%d  %8.3f ms  bound %7.3f ms  %5.1f%%  %7.1f GB/s %7.1f TF/s\n' % (
-                row['kind'], row['ksize'], row['stride'], row['Cin'], row['Cout'], row['Ho'], row['Wo'], int(row['res']), r['ms'], r['t_bound_ms'],
+            sys.stderr.write('%-10s k%d s%d %3d->%3d%s %4dx%-4d res=%d  %8.3f ms  bound %7.3f ms  %5.1f%%  %7.1f GB/s %7.1f TF/s\n' % (
+                row['kind'], row['ksize'], row['stride'], row['Cin'], row['Cout'], ('->%3d' % row['tail_cout']) if row.get('tail_cout') else '     ', row['Ho'], row['Wo'], int(row['res']), r['ms'], r['t_bound_ms'],
                 100 * r['t_bound_ms'] / max(r['ms'], 1e-9), r['bytes'] / (r['ms'] * 1e-3) / 1e9, r['flops'] / (r['ms'] * 1e-3) / 1e12))
         sys.stderr.write('sum of ops %.3f ms; graph step (incl. post-process) %.3f ms\n' % (sum_ms, ms_step))
 

@@ -83,12 +83,19 @@ typedef struct lfd_op {
     const float* shift;
     const float* gamma;
     const float* beta;
+    /* STEM0 / CONV only: a 1x1/s1 conv (Cout -> tail_cout) + scale/shift (+ReLU) fused behind this layer inside the same
+     * kernel; tail_weight = bf16 packed [Cout/8][tail_cout][8].  The stored tensor then has tail_cout channels and
+     * res_off / gn_groups / stats_off refer to it; the Cout-channel intermediate never reaches HBM.  0 = no tail. */
+    int32_t tail_cout, tail_relu;
+    const void* tail_weight;
+    const float* tail_scale;
+    const float* tail_shift;
 } lfd_op;
 
 /* Tile / pipeline configuration the tcgen05 kernel will use for a conv (host only, no launch).
  * cc = input-channel chunk the weights must be packed with. */
-int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int* cc, int* stages,
-                   int* weights_resident, int* num_tiles, int64_t* smem_bytes);
+int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int* cc,
+                   int* stages, int* weights_resident, int* num_tiles, int64_t* smem_bytes);
 
 /* The plan copies the op list.  stats_off/stats_bytes: region of the workspace zeroed at the start of each forward. */
 int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int cls_channels, int64_t stats_off, int64_t stats_bytes,

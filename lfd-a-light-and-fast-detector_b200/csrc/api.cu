@@ -80,13 +80,14 @@ static ConvGeom geom_of(const lfd_op& o) {
     ConvGeom g;
     g.N = o.N; g.H = o.H; g.W = o.W; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.ksize = o.ksize; g.stride = o.stride;
     g.stem = o.kind == LFD_OP_STEM0 ? 1 : 0;
+    g.tail_cout = o.tail_cout;
     if (g.stem) g.Cin = 32;   // 27 (kh, kw, ci) taps padded to 32
     return g;
 }
 
-extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int* cc, int* stages,
-                              int* weights_resident, int* num_tiles, int64_t* smem_bytes) {
-    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride, 0};
+extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int* cc,
+                              int* stages, int* weights_resident, int* num_tiles, int64_t* smem_bytes) {
+    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, 0};
     UmmaConvParams p;
     size_t smem = 0;
     int grid = 0;
@@ -111,7 +112,7 @@ static int check_op(const lfd_op& o) {
             break;
         case LFD_OP_CONV:
             if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "conv output size mismatch (%dx%d vs %dx%d)", o.Ho, o.Wo, eh, ew);
-            if (o.gn_groups && (o.Cout != o.gn_groups * 8 || o.gn_groups != 16)) return fail(LFD_ERR_UNSUPPORTED, "fused GroupNorm statistics need 16 groups of 8 channels (Cout=%d groups=%d)", o.Cout, o.gn_groups);
+            if (o.gn_groups && ((o.tail_cout ? o.tail_cout : o.Cout) != o.gn_groups * 8 || o.gn_groups != 16)) return fail(LFD_ERR_UNSUPPORTED, "fused GroupNorm statistics need 16 groups of 8 channels (Cout=%d groups=%d)", o.Cout, o.gn_groups);
             if (o.cc <= 0 || o.Cin % o.cc) return fail(LFD_ERR_INVALID, "conv cc=%d does not divide Cin=%d", o.cc, o.Cin);
             break;
         case LFD_OP_GN_APPLY:
@@ -146,6 +147,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
         case LFD_OP_STEM0: {
             if (!input) return fail(LFD_ERR_INVALID, "stem0 needs the external input pointer");
             if (conv_impl == LFD_CONV_SIMT) {
+                if (o.tail_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails");
                 Stem0Params p;
                 p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift;
@@ -157,6 +159,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off); p.res = nullptr;
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift; p.stats = nullptr;
                 p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace;
+                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
             break;
@@ -167,12 +170,14 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
             const __nv_bfloat16* res = o.res_off >= 0 ? reinterpret_cast<const __nv_bfloat16*>(ws + o.res_off) : nullptr;
             double* stats = o.gn_groups ? reinterpret_cast<double*>(ws + o.stats_off) : nullptr;
             if (conv_impl == LFD_CONV_SIMT) {
+                if (o.tail_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails");
                 CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight), o.scale,
                                           o.shift, stats, o.gn_groups, o.relu, st));
             } else {
                 UmmaConvParams p = po.cp;
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
                 p.scale = o.scale; p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
+                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 p.trace = g_trace;
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }

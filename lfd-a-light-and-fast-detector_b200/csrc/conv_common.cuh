@@ -12,12 +12,13 @@ enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3, MODE_STEM 
 static constexpr int kMaxStages = 8;
 // dynamic shared memory map of conv_umma_kernel (bytes)
 static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
-static constexpr int kSmemScaleOff = 256;    // scale[128], shift[128] fp32
-static constexpr int kSmemTableOff = 1280;   // halo pixel table (<= 561 entries x 8 B)
-static constexpr int kSmemStagingOff = 6144; // epilogue staging tile 128 x Cout bf16
+static constexpr int kSmemScaleOff = 256;    // scale[128], shift[128], tail scale[128], tail shift[128] fp32
+static constexpr int kSmemTableOff = 2304;   // halo pixel table (<= 561 entries x 8 B)
+static constexpr int kSmemStagingOff = 7168; // epilogue staging tile 128 x Cf bf16
 
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
+    int tail_cout;   // > 0: a 1x1/s1 conv (Cout -> tail_cout) is fused behind this conv (second GEMM in the same kernel)
     int stem;   // 1: 3x3/s2 conv on the raw 3-channel image (K = 27 padded to 32), operand built by the producers
 };
 
@@ -29,6 +30,13 @@ struct UmmaConvParams {
     const __nv_bfloat16* w;     // packed [cc][tap][kc][Cout][8]
     const float* scale;         // [Cout]
     const float* shift;         // [Cout]
+    // fused trailing 1x1 conv ("tail"): out = act2(scale2 * (W2 . act(scale * conv(x) + shift)) + shift2); `out`, `res`,
+    // `stats` then refer to the tail's output (Cf channels) and the intermediate never leaves the SM
+    const __nv_bfloat16* w2;    // packed [Cout/8][Cout2][8]
+    const float* scale2;
+    const float* shift2;
+    int Cout2, relu2, Cf;       // Cf = channels of the stored tensor (Cout2 with a tail, else Cout)
+    uint32_t smem_w2_off, smem_a2_off, a2_bytes, n_a2;
     double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
     long long* trace;           // debugging: clock64() timeline of CTA 0 ([role 0..2][tile < 32][4]), normally null
     int N, H, W, Cin, Ho, Wo, Cout;

@@ -77,9 +77,15 @@ conv_umma_kernel(const UmmaConvParams p) {
     uint64_t* tfull = empty + kMaxStages;
     uint64_t* tempty = tfull + 2;
     uint64_t* wbar = tempty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    uint64_t* a2_full = wbar + 1;     // tail: intermediate operand written by the epilogue warps
+    uint64_t* a2_empty = a2_full + 2; //       ... consumed by the tail MMAs
+    uint64_t* tfull2 = a2_empty + 2;  //       tail accumulator ready
+    uint64_t* tempty2 = tfull2 + 2;   //       tail accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty2 + 2);
     float* s_scale = reinterpret_cast<float*>(smem + kSmemScaleOff);
     float* s_shift = s_scale + 128;
+    float* s_scale2 = s_shift + 128;
+    float* s_shift2 = s_scale2 + 128;
     PxEntry* table = reinterpret_cast<PxEntry*>(smem + kSmemTableOff);
     uint8_t* staging = smem + kSmemStagingOff;
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
@@ -102,6 +108,12 @@ conv_umma_kernel(const UmmaConvParams p) {
             mbar_init(&tempty[i], kEpiThreads);
         }
         mbar_init(wbar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a2_full[i], kEpiThreads);
+            mbar_init(&a2_empty[i], 1);
+            mbar_init(&tfull2[i], 1);
+            mbar_init(&tempty2[i], kEpiThreads);
+        }
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -109,6 +121,11 @@ conv_umma_kernel(const UmmaConvParams p) {
         s_scale[c] = p.scale[c];
         s_shift[c] = p.shift[c];
     }
+    if (p.Cout2)
+        for (int c = tid; c < p.Cout2; c += kThreads) {
+            s_scale2[c] = p.scale2[c];
+            s_shift2[c] = p.shift2[c];
+        }
     StemEntry* stem_table = reinterpret_cast<StemEntry*>(smem + p.smem_stem_off);
     __nv_bfloat16* stem_patch = reinterpret_cast<__nv_bfloat16*>(smem + p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128);
     if (MODE == MODE_STEM) {
@@ -156,17 +173,70 @@ conv_umma_kernel(const UmmaConvParams p) {
         // ============================================================== EPILOGUE
         const int m = (warp & 3) * 32 + lane;        // D row == TMEM lane (a warp may only touch lane quarter warp % 4)
         const int chalf = warp >> 2;                  // EPI_WARPS == 8: second warp of the quarter takes the upper columns
-        const int ccols = p.Cout / (EPI_WARPS / 4);   // columns handled by this thread
-        const int ccol0 = chalf * ccols;
-        const int cpr = p.Cout >> 3;                  // 16 B chunks per staged row (power of two)
+        const int Cf = p.Cf;                          // channels of the stored tensor
+        const int cpr = Cf >> 3;                      // 16 B chunks per staged row (power of two)
         const int l2cpr = p.log2_cpr;
-        const int row_bytes = p.Cout * 2;
+        const int row_bytes = Cf * 2;
         const int l2rp = p.log2_rp128;                // log2(rows per 128 B): swizzle granularity for rows shorter than 128 B
         const int swz_mask = (cpr < 8 ? cpr : 8) - 1;
         const int HoWo = p.Ho * p.Wo;
         const uint32_t stg = smem_u32(staging);
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+        // scale/shift (+ReLU) of 8 accumulator columns -> packed bf16
+        auto affine8 = [&](const float* v, const float* sc, const float* sh, int col, int relu, const uint4* resv) -> uint4 {
+            const float4 sc0 = *reinterpret_cast<const float4*>(sc + col), sc1 = *reinterpret_cast<const float4*>(sc + col + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(sh + col), sh1 = *reinterpret_cast<const float4*>(sh + col + 4);
+            float o[8];
+            o[0] = fmaf(v[0], sc0.x, sh0.x); o[1] = fmaf(v[1], sc0.y, sh0.y); o[2] = fmaf(v[2], sc0.z, sh0.z); o[3] = fmaf(v[3], sc0.w, sh0.w);
+            o[4] = fmaf(v[4], sc1.x, sh1.x); o[5] = fmaf(v[5], sc1.y, sh1.y); o[6] = fmaf(v[6], sc1.z, sh1.z); o[7] = fmaf(v[7], sc1.w, sh1.w);
+            if (resv) {
+                const uint4 rv = *resv;
+                o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
+                o[4] += bf16_lo(rv.z); o[5] += bf16_hi(rv.z); o[6] += bf16_lo(rv.w); o[7] += bf16_hi(rv.w);
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            uint4 ov;
+            ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+            return ov;
+        };
+
+        // ---- tail phase 1: main accumulator -> bf16 operand of the fused 1x1 conv (never leaves the SM)
+        auto mid_tile = [&](uint32_t tc) {
+            const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
+            const uint32_t b = p.n_a2 == 2 ? (tc & 1) : 0;
+            const uint32_t use = p.n_a2 == 2 ? (tc >> 1) : tc;       // how often this operand buffer has been filled before
+            const int ccols = p.Cout / (EPI_WARPS / 4), ccol0 = chalf * ccols;
+            mbar_wait(&tfull[a], aph);
+            mbar_wait(&a2_empty[b], (use & 1) ^ 1);                   // tail MMAs of the previous user of this buffer are done
+            tc_fence_after_sync();
+            const uint32_t trow = tmem_base + lane_base + a * p.Cout + ccol0;
+            uint8_t* dst = smem + p.smem_a2_off + b * p.a2_bytes + m * 16;
+            const uint32_t lbo2 = 129 * 16;
+            for (int c0 = 0; c0 < ccols; c0 += 32) {
+                float v[32];
+                tmem_ld16(trow + c0, v);
+                if (c0 + 16 < ccols) tmem_ld16(trow + c0 + 16, v + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (c0 + h * 8 >= ccols) break;
+                    const int col = ccol0 + c0 + h * 8;
+                    *reinterpret_cast<uint4*>(dst + (col >> 3) * lbo2) = affine8(v + h * 8, s_scale, s_shift, col, p.relu, nullptr);
+                }
+            }
+            tc_fence_before_sync();
+            fence_proxy_async_smem();           // st.shared (generic proxy) -> tcgen05.mma (async proxy)
+            mbar_arrive(&a2_full[b]);
+            mbar_arrive(&tempty[a]);
+        };
+
+        // ---- final phase: accumulator -> scale/shift (+residual) (+ReLU) -> bf16 staging -> (GN statistics) -> global
+        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, const float* sc,
+                               const float* sh, int relu) {
             const int n = tile / p.tiles_per_img;
             const int t = tile - n * p.tiles_per_img;
             int oy0 = 0, ox0 = 0, p0 = 0;
@@ -179,26 +249,27 @@ conv_umma_kernel(const UmmaConvParams p) {
                 int y = oy0 + (r >> 3), x = ox0 + (r & 7);
                 return (y < p.Ho && x < p.Wo) ? y * p.Wo + x : -1;
             };
-            const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
+            const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
+            const int ccols = Cf / (EPI_WARPS / 4), ccol0 = chalf * ccols;
             if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
 #pragma unroll 4
                 for (int e = tid; e < 128 * cpr; e += kEpiThreads) {
                     const int r = e >> l2cpr, c = e & (cpr - 1);
                     const int q = row_pixel(r);
-                    const __nv_bfloat16* src = p.res + ((img_out + (q < 0 ? 0 : q)) * p.Cout + c * 8);
+                    const __nv_bfloat16* src = p.res + ((img_out + (q < 0 ? 0 : q)) * Cf + c * 8);
                     cp_async16(stg + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4), src, q >= 0);
                 }
                 cp_async_commit();
             }
-            if (tid == 0) LFD_TRACE(2, tcount, 0);
-            mbar_wait(&tfull[a], aph);
+            if (tid == 0) LFD_TRACE(2, tc, 0);
+            mbar_wait(&bar_full[a], aph);
             tc_fence_after_sync();
-            if (tid == 0) LFD_TRACE(2, tcount, 1);
+            if (tid == 0) LFD_TRACE(2, tc, 1);
             if (p.res) {
                 cp_async_wait<0>();
                 named_bar_sync(1, kEpiThreads);
             }
-            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a * p.Cout + ccol0;
+            const uint32_t trow = tmem_base + lane_base + col_base + a * Cf + ccol0;
             uint8_t* my_row = staging + m * row_bytes;
             const int my_swz = (m >> l2rp) & swz_mask;
             for (int c0 = 0; c0 < ccols; c0 += 32) {
@@ -211,33 +282,12 @@ conv_umma_kernel(const UmmaConvParams p) {
                     if (c0 + h * 8 >= ccols) break;
                     const int col = ccol0 + c0 + h * 8;
                     uint4* slot = reinterpret_cast<uint4*>(my_row + (((col >> 3) ^ my_swz) << 4));
-                    float o[8];
-                    {
-                        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + col), sc1 = *reinterpret_cast<const float4*>(s_scale + col + 4);
-                        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + col), sh1 = *reinterpret_cast<const float4*>(s_shift + col + 4);
-                        o[0] = fmaf(v[h * 8 + 0], sc0.x, sh0.x); o[1] = fmaf(v[h * 8 + 1], sc0.y, sh0.y);
-                        o[2] = fmaf(v[h * 8 + 2], sc0.z, sh0.z); o[3] = fmaf(v[h * 8 + 3], sc0.w, sh0.w);
-                        o[4] = fmaf(v[h * 8 + 4], sc1.x, sh1.x); o[5] = fmaf(v[h * 8 + 5], sc1.y, sh1.y);
-                        o[6] = fmaf(v[h * 8 + 6], sc1.z, sh1.z); o[7] = fmaf(v[h * 8 + 7], sc1.w, sh1.w);
-                    }
-                    if (p.res) {
-                        uint4 rv = *slot;
-                        o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
-                        o[4] += bf16_lo(rv.z); o[5] += bf16_hi(rv.z); o[6] += bf16_lo(rv.w); o[7] += bf16_hi(rv.w);
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-                    }
-                    uint4 ov;
-                    ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
-                    ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
-                    *slot = ov;
+                    *slot = affine8(v + h * 8, sc, sh, col, relu, p.res ? slot : nullptr);
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&tempty[a]);  // accumulator stage may be overwritten by the next-but-one tile
-            if (tid == 0) LFD_TRACE(2, tcount, 2);
+            mbar_arrive(&bar_empty[a]);  // accumulator stage may be overwritten by the next-but-one tile
+            if (tid == 0) LFD_TRACE(2, tc, 2);
             named_bar_sync(1, kEpiThreads);
             if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk (16 groups)
                 constexpr int TPG = kEpiThreads / 16;  // threads per group
@@ -268,10 +318,25 @@ conv_umma_kernel(const UmmaConvParams p) {
                 const int q = row_pixel(r);
                 if (q < 0) continue;
                 const uint4 val = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4));
-                *reinterpret_cast<uint4*>(p.out + ((img_out + q) * p.Cout + c * 8)) = val;
+                *reinterpret_cast<uint4*>(p.out + ((img_out + q) * Cf + c * 8)) = val;
             }
             named_bar_sync(1, kEpiThreads);  // staging free again
-            if (tid == 0) LFD_TRACE(2, tcount, 3);
+            if (tid == 0) LFD_TRACE(2, tc, 3);
+        };
+
+        if (!p.Cout2) {
+            uint32_t tcount = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount)
+                finish_tile(tile, tcount, tfull, tempty, 0, s_scale, s_shift, p.relu);
+        } else {
+            // software pipelined: intermediate of tile t, then the finished tail of tile t-1
+            uint32_t tcount = 0;
+            for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
+                const bool has = tile < p.num_tiles;
+                if (has) mid_tile(tcount);
+                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout, s_scale2, s_shift2, p.relu2);
+                if (!has) break;
+            }
         }
     } else if (warp == kMmaWarp) {
         // ============================================================== MMA ISSUER
@@ -286,17 +351,41 @@ conv_umma_kernel(const UmmaConvParams p) {
         const uint32_t b_k16 = (2 * lbo_b) >> 4;        //   (B)
         const uint32_t b_tap = (cpc * lbo_b) >> 4;      // address-field step per tap (B)
         const int nk16 = p.Cc >> 4;
-        if (p.b_resident) {
+        const uint32_t w2_bytes = p.Cout2 ? (uint32_t)(p.Cout * p.Cout2 * 2) : 0u;
+        if (p.b_resident || p.Cout2) {
             if (elect_one_sync()) {
-                mbar_arrive_expect_tx(wbar, p.w_total_bytes);
-                for (uint32_t off = 0; off < p.w_total_bytes; off += 32768) {
-                    uint32_t nb = p.w_total_bytes - off < 32768 ? p.w_total_bytes - off : 32768;
+                const uint32_t w1_bytes = p.b_resident ? p.w_total_bytes : 0u;
+                mbar_arrive_expect_tx(wbar, w1_bytes + w2_bytes);
+                for (uint32_t off = 0; off < w1_bytes; off += 32768) {
+                    uint32_t nb = w1_bytes - off < 32768 ? w1_bytes - off : 32768;
                     bulk_g2s(smem_u32(wres) + off, reinterpret_cast<const uint8_t*>(p.w) + off, nb, wbar);
                 }
+                if (w2_bytes) bulk_g2s(smem_u32(smem + p.smem_w2_off), p.w2, w2_bytes, wbar);
             }
             __syncwarp();
             mbar_wait(wbar, 0);
         }
+        // fused 1x1 tail: D2[128 x Cout2] = A2[128 x Cout] . W2, A2 written by the epilogue warps (mid_tile)
+        const uint32_t idesc2 = umma_idesc_bf16(128, p.Cout2 ? p.Cout2 : 16);
+        const uint64_t a2desc0 = umma_smem_desc(0, 129 * 16, 128);
+        const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), p.Cout2 * 16, 128);
+        auto issue_tail = [&](uint32_t u) {
+            const uint32_t b = p.n_a2 == 2 ? (u & 1) : 0, use = p.n_a2 == 2 ? (u >> 1) : u;
+            const uint32_t a2s = u & 1, a2ph = (u >> 1) & 1;
+            mbar_wait(&a2_full[b], use & 1);
+            mbar_wait(&tempty2[a2s], a2ph ^ 1);
+            tc_fence_after_sync();
+            fence_proxy_async_smem();
+            if (elect_one_sync()) {
+                const uint64_t ad2 = a2desc0 + ((smem_u32(smem + p.smem_a2_off) + b * p.a2_bytes) >> 4);
+                const uint32_t d2 = tmem_base + 2 * p.Cout + a2s * p.Cout2;
+                for (int k16 = 0; k16 < (p.Cout >> 4); ++k16)
+                    umma_bf16(d2, ad2 + (uint32_t)(k16 * ((2 * 129 * 16) >> 4)), b2desc0 + (uint32_t)(k16 * ((2 * p.Cout2 * 16) >> 4)), idesc2, k16 != 0);
+                umma_commit(&tfull2[a2s]);
+                umma_commit(&a2_empty[b]);
+            }
+            __syncwarp();
+        };
         uint32_t it = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
             const uint32_t a = tcount & 1, aph = (tcount >> 1) & 1;
@@ -327,7 +416,9 @@ conv_umma_kernel(const UmmaConvParams p) {
                 __syncwarp();
                 if (cc == n_cc - 1 && lane == 0) LFD_TRACE(1, tcount, 3);
             }
+            if (p.Cout2 && tcount >= 1) issue_tail(tcount - 1);
         }
+        if (p.Cout2 && tcount >= 1) issue_tail(tcount - 1);
     } else {
         // ============================================================== PRODUCERS
         const int ptid = tid - (kEpiThreads + 32);
@@ -500,9 +591,19 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     const int plane_slots = px_slots | 1;
     p.lbo_a = plane_slots * 16;
     p.num_tiles = p.tiles_per_img * g.N;
-    const size_t staging = (size_t)128 * g.Cout * 2;
+    const int Cf = g.tail_cout > 0 ? g.tail_cout : g.Cout;
+    if (g.tail_cout) {
+        if (g.tail_cout % 16 || g.tail_cout > 128 || g.tail_cout < 16 || 2 * (g.Cout + g.tail_cout) > 512) return -4;
+        if (epi_warps_of(mode) == 8 && g.tail_cout < 32) return -4;
+    }
+    const size_t staging = (size_t)128 * Cf * 2;
     const size_t fixed = kSmemStagingOff + staging;
-    const size_t budget = 224 * 1024;
+    // everything that lives behind the ring: MODE_STEM patch machinery, fused-tail weights + two operand buffers
+    const size_t a2_bytes = g.tail_cout ? ((size_t)(g.Cout / 8) * 129 * 16 + 127) & ~(size_t)127 : 0;
+    const size_t w2_bytes = g.tail_cout ? ((size_t)g.Cout * g.tail_cout * 2 + 127) & ~(size_t)127 : 0;
+    const size_t stem_bytes = mode == MODE_STEM ? (size_t)((kStemElems * 8 + 127) / 128) * 128 + 2 * kStemPatchBytes : 0;
+    const size_t post = stem_bytes + w2_bytes + 2 * a2_bytes;
+    const size_t budget = 224 * 1024 - post;
     const size_t w_total = (size_t)taps * g.Cin * g.Cout * 2;
     // Choose the channel chunk Cc, weight residency and ring depth.  Preference order:
     //   1. resident weights (loaded once per CTA) with >= 3 A stages, the largest Cc first;
@@ -545,11 +646,11 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     p.w_total_bytes = (uint32_t)w_total;
     p.smem_w_off = (uint32_t)fixed;
     p.smem_ring_off = (uint32_t)(fixed + (best_res ? w_total : 0));
-    // two CTAs per SM when a >= 2-deep ring fits in half of the shared memory (1x1 layers; 4 epilogue warps each)
+    // two CTAs per SM when a >= 2-deep ring fits in half of the shared memory (1x1 / stem layers; 4 epilogue warps each)
     p.ctas_per_sm = 1;
     if (epi_warps_of(mode) == 4) {
         const size_t half = (227 * 1024) / 2 - 1024;
-        const size_t base = p.smem_ring_off;
+        const size_t base = p.smem_ring_off + post;
         if (base + 2 * (size_t)p.stage_bytes <= half) {
             int st = (int)((half - base) / p.stage_bytes);
             if (st > p.stages) st = p.stages;
@@ -558,16 +659,25 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     }
     auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
     p.log2_cpc = ilog2(p.Cc / 8);
-    p.log2_cpr = ilog2(g.Cout / 8);
-    if ((1 << p.log2_cpr) != g.Cout / 8) return -3;   // Cout must be 16/32/64/128
-    p.log2_rp128 = g.Cout * 2 >= 128 ? 0 : ilog2(128 / (g.Cout * 2));
-    p.tmem_cols = 2 * g.Cout < 32 ? 32 : 2 * g.Cout;  // two accumulator stages; power of two because Cout is
-    *smem_bytes = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
-    if (mode == MODE_STEM) {   // element table + two patch buffers behind the ring
-        p.smem_stem_off = (uint32_t)((*smem_bytes + 127) & ~(size_t)127);
-        *smem_bytes = p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128 + 2 * kStemPatchBytes;
-        p.ctas_per_sm = (2 * (*smem_bytes + 1024) <= 227 * 1024) ? 2 : 1;
+    p.Cf = Cf;
+    p.Cout2 = g.tail_cout;
+    p.log2_cpr = ilog2(Cf / 8);
+    if ((1 << p.log2_cpr) != Cf / 8) return -3;       // stored channel count must be 16/32/64/128
+    p.log2_rp128 = Cf * 2 >= 128 ? 0 : ilog2(128 / (Cf * 2));
+    {   // TMEM: two accumulator stages of the conv (+ two of the tail); power of two >= 32
+        int need = 2 * g.Cout + 2 * g.tail_cout, cols = 32;
+        while (cols < need) cols <<= 1;
+        p.tmem_cols = cols;
     }
+    size_t off = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
+    if (mode == MODE_STEM) { p.smem_stem_off = (uint32_t)off; off += stem_bytes; }
+    if (g.tail_cout) {
+        p.smem_w2_off = (uint32_t)off; off += w2_bytes;
+        p.smem_a2_off = (uint32_t)off; off += 2 * a2_bytes;
+        p.a2_bytes = (uint32_t)a2_bytes; p.n_a2 = 2;
+    }
+    *smem_bytes = off;
+    if (p.ctas_per_sm == 2 && 2 * p.tmem_cols > 512) p.ctas_per_sm = 1;
     const int max_ctas = num_sms * p.ctas_per_sm;
     *grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
     *out = p;

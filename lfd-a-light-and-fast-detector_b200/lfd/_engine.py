@@ -94,6 +94,8 @@ class InferencePlan(object):
         self._tensors = {}                   # name -> bytes
         self._branch = 0                     # branch id given to the ops being emitted (0 = main stream)
         self.concurrent_levels = not os.environ.get('LFD_B200_NO_BRANCHES')
+        # conv -> 1x1 conv pairs run as ONE kernel (tensor-core kernels only; the SIMT cross-check runs them unfused)
+        self.fuse_tails = conv_impl == nat.CONV_UMMA and not os.environ.get('LFD_B200_NO_TAIL')
         self._build(model)
         self._finalize()
 
@@ -138,26 +140,42 @@ class InferencePlan(object):
         return name
 
     # ------------------------------------------------------------------ op emitters
-    def _emit_stem0(self, conv, norm, relu, out_name, h, w):
+    def _tail_fields(self, tail, cmid):
+        """tail = (conv1x1, norm, relu) fused behind a layer with cmid output channels -> op fields."""
+        conv2, norm2, relu2 = tail
+        scale2, shift2 = self._fold(conv2, norm2)
+        return dict(tail_cout=conv2.out_channels, tail_relu=int(relu2), tail_w=self._add_bf16(pack_conv_weight(conv2.weight, cmid)),
+                    tail_scale=self._add_f32(scale2), tail_shift=self._add_f32(shift2), tail_modules=(conv2, norm2))
+
+    @staticmethod
+    def _can_tail(conv, nxt):
+        """nxt = (conv, norm, relu): a bias-free-or-not 1x1/s1 conv directly consuming `conv`'s output."""
+        c2 = nxt[0]
+        return (c2.kernel_size == (1, 1) and c2.stride == (1, 1) and c2.groups == 1 and c2.in_channels == conv.out_channels
+                and conv.out_channels in (32, 64) and c2.out_channels in (32, 64, 128))
+
+    def _emit_stem0(self, conv, norm, relu, out_name, h, w, tail=None):
         if conv.in_channels != 3 or conv.kernel_size != (3, 3) or conv.stride != (2, 2):
             raise NotImplementedError('the B200 stem kernel handles the 3x3/s2 conv on a 3-channel image only')
         ho, wo = _conv_out(h, 3, 2), _conv_out(w, 3, 2)
         scale, shift = self._fold(conv, norm)
         wt = pack_stem_weight(conv.weight)
-        self._push(dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2,
-                              relu=int(relu), out=self._tensor(out_name, self.N, ho, wo, conv.out_channels),
-                              w_bf16=self._add_bf16(wt), scale=self._add_f32(scale), shift=self._add_f32(shift),
-                              modules=(conv, norm)))
+        op = dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2, relu=int(relu),
+                  w_bf16=self._add_bf16(wt), scale=self._add_f32(scale), shift=self._add_f32(shift), modules=(conv, norm))
+        if tail is not None:
+            op.update(self._tail_fields(tail, conv.out_channels))
+        op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or conv.out_channels)
+        self._push(op)
         return ho, wo
 
-    def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None):
+    def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None, tail=None):
         k, s = conv.kernel_size[0], conv.stride[0]
         if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or s not in (1, 2) or conv.padding[0] != k // 2 \
                 or conv.groups != 1 or conv.dilation != (1, 1):
             raise NotImplementedError('unsupported conv geometry for the B200 kernels: %r' % (conv,))
         cin, cout = conv.in_channels, conv.out_channels
         ho, wo = _conv_out(h, k, s), _conv_out(w, k, s)
-        q = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s)
+        q = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s, tail[0].out_channels if tail is not None else 0)
         cc = q['cc']
         key = (id(conv), id(norm), cc)
         if cache is not None and key in cache:
@@ -173,8 +191,11 @@ class InferencePlan(object):
             if cache is not None:
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
-                  gn_groups=gn_groups, cc=cc, inp=in_name, out=self._tensor(out_name, self.N, ho, wo, cout), res=res,
+                  gn_groups=gn_groups, cc=cc, inp=in_name, res=res,
                   w_bf16=w_off, scale=sc_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
+        if tail is not None:
+            op.update(self._tail_fields(tail, cout))
+        op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or cout)
         if gn_groups:
             op['stats'] = len([o for o in self._ops if o.get('stats') is not None and o['kind'] == nat.OP_CONV])
         self._push(op)
@@ -185,13 +206,20 @@ class InferencePlan(object):
         bb, neck, head = model._backbone, model._neck, model._head
         h, w = self.H, self.W
         cur = None
-        for i, (conv, norm, relu) in enumerate(bb.stem_layers()):
-            name = 'stem%d' % i
+        layers = bb.stem_layers()
+        i = 0
+        while i < len(layers):
+            conv, norm, relu = layers[i]
+            tail = None
+            if self.fuse_tails and i + 1 < len(layers) and self._can_tail(conv, layers[i + 1]):
+                tail = layers[i + 1]
+            name = 'stem%d' % (i + (1 if tail is not None else 0))      # a fused pair is named after its last layer
             if i == 0:
-                h, w = self._emit_stem0(conv, norm, relu, name, h, w)
+                h, w = self._emit_stem0(conv, norm, relu, name, h, w, tail=tail)
             else:
-                h, w = self._emit_conv(conv, norm, relu, cur, name, h, w)
+                h, w = self._emit_conv(conv, norm, relu, cur, name, h, w, tail=tail)
             cur = name
+            i += 2 if tail is not None else 1
         taps = list(bb._out_indices)
         if len(taps) != head._num_heads:
             raise ValueError('backbone taps (%d) and head levels (%d) differ' % (len(taps), head._num_heads))
@@ -347,6 +375,10 @@ class InferencePlan(object):
             o.gn_groups = op.get('gn_groups', 0)
             o.n_cls, o.n_reg, o.point_off, o.cc = op.get('n_cls', 0), op.get('n_reg', 0), op.get('point_off', 0), op.get('cc', 0)
             o.branch = op.get('branch', 0)
+            o.tail_cout, o.tail_relu = op.get('tail_cout', 0), op.get('tail_relu', 0)
+            if op.get('tail_cout'):
+                o.tail_weight = bb + 2 * op['tail_w']
+                o.tail_scale, o.tail_shift = fb + 4 * op['tail_scale'], fb + 4 * op['tail_shift']
             o.in_off = offsets[op['inp']] if op.get('inp') is not None else -1
             o.out_off = offsets[op['out']] if op.get('out') is not None else -1
             o.res_off = offsets[op['res']] if op.get('res') is not None else -1
@@ -404,7 +436,7 @@ class InferencePlan(object):
         rows = []
         for op in self._ops:
             rows.append(dict(kind=names[op['kind']], H=op['H'], W=op['W'], Cin=op['Cin'], Ho=op['Ho'], Wo=op['Wo'], Cout=op['Cout'],
-                             ksize=op.get('ksize', 1), stride=op.get('stride', 1), res=op.get('res') is not None,
+                             ksize=op.get('ksize', 1), stride=op.get('stride', 1), res=op.get('res') is not None, tail_cout=op.get('tail_cout', 0),
                              out=op.get('out'), query=op.get('query')))
         return rows
 

@@ -34,7 +34,9 @@ class Op(C.Structure):
                 ('branch', C.c_int32), ('reserved', C.c_int32),
                 ('in_off', C.c_int64), ('out_off', C.c_int64), ('res_off', C.c_int64), ('stats_off', C.c_int64),
                 ('weight', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p),
-                ('gamma', C.c_void_p), ('beta', C.c_void_p)]
+                ('gamma', C.c_void_p), ('beta', C.c_void_p),
+                ('tail_cout', C.c_int32), ('tail_relu', C.c_int32),
+                ('tail_weight', C.c_void_p), ('tail_scale', C.c_void_p), ('tail_shift', C.c_void_p)]
 
 
 class PostCfg(C.Structure):
@@ -59,7 +61,7 @@ SYMBOLS = {
     'lfd_abi_version': (_i, []),
     'lfd_last_error': (C.c_char_p, []),
     'lfd_device_sm_count': (_i, []),
-    'lfd_conv_query': (_i, [_i] * 9 + [C.POINTER(_i)] * 4 + [C.POINTER(_i64)]),
+    'lfd_conv_query': (_i, [_i] * 10 + [C.POINTER(_i)] * 4 + [C.POINTER(_i64)]),
     'lfd_plan_create': (_i, [C.POINTER(Op), _i, _i, _i, _i, _i64, _i64, _i64, _i, C.POINTER(_vp)]),
     'lfd_plan_destroy': (_i, [_vp]),
     'lfd_plan_num_launches': (_i, [_vp]),
@@ -124,9 +126,9 @@ def ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride):
+def conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout=0):
     cc, st, res, nt = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     smem = C.c_int64()
-    check(lib().lfd_conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, C.byref(cc), C.byref(st), C.byref(res),
+    check(lib().lfd_conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, C.byref(cc), C.byref(st), C.byref(res),
                                C.byref(nt), C.byref(smem)))
     return dict(cc=cc.value, stages=st.value, weights_resident=res.value, num_tiles=nt.value, smem_bytes=smem.value)

@@ -17,18 +17,19 @@ def conv_out(size, k, s):
     return (size + 2 * (k // 2) - k) // s + 1
 
 
-def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, impl=nat.CONV_UMMA):
+def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, impl=nat.CONV_UMMA, tail=None):
     """x_nhwc: cuda bf16 [N,H,W,Cin]; weight fp32 [Cout,Cin,k,k] (already bf16-representable).
     -> (out bf16 [N,Ho,Wo,Cout], stats double [N,groups,2] or None)"""
     dev = x_nhwc.device
     N, H, W, Cin = x_nhwc.shape
     Cout, _, k, _ = weight.shape
     Ho, Wo = conv_out(H, k, stride), conv_out(W, k, stride)
-    q = nat.conv_query(N, H, W, Cin, Ho, Wo, Cout, k, stride)
+    Cf = tail[0].shape[0] if tail is not None else Cout
+    q = nat.conv_query(N, H, W, Cin, Ho, Wo, Cout, k, stride, Cf if tail is not None else 0)
     wp = pack_conv_weight(weight, q['cc']).to(dev)
     sc, sh = scale.float().to(dev).contiguous(), shift.float().to(dev).contiguous()
     in_b = x_nhwc.numel() * 2
-    out_b = N * Ho * Wo * Cout * 2
+    out_b = N * Ho * Wo * Cf * 2
     al = lambda v: (v + 255) & ~255
     off_in, off_out = 4096, 4096 + al(in_b)
     off_res = off_out + al(out_b)
@@ -44,10 +45,16 @@ def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, 
     op.in_off, op.out_off, op.res_off = off_in, off_out, (off_res if res is not None else -1)
     op.stats_off = 0 if gn_groups else -1
     op.weight, op.scale, op.shift = wp.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    if tail is not None:
+        w2, sc2, sh2, relu2 = tail
+        w2p = pack_conv_weight(w2, Cout).to(dev)
+        sc2d, sh2d = sc2.float().to(dev).contiguous(), sh2.float().to(dev).contiguous()
+        op.tail_cout, op.tail_relu = Cf, int(relu2)
+        op.tail_weight, op.tail_scale, op.tail_shift = w2p.data_ptr(), sc2d.data_ptr(), sh2d.data_ptr()
     with torch.cuda.device(dev):
         nat.check(nat.lib().lfd_run_op(C.byref(op), None, 0, nat.ptr(ws), None, None, 0, 0, impl, nat.stream_ptr()))
         torch.cuda.synchronize()
-    out = ws[off_out:off_out + out_b].view(torch.bfloat16).view(N, Ho, Wo, Cout).clone()
+    out = ws[off_out:off_out + out_b].view(torch.bfloat16).view(N, Ho, Wo, Cf).clone()
     stats = ws[0:N * gn_groups * 16].view(torch.float64).view(N, gn_groups, 2).clone() if gn_groups else None
     return out, stats, q
 

@@ -64,3 +64,38 @@ def test_conv_large_grid_persistent_loop():
     out, _, q = run_conv(x, w, scale, shift, 1, True, res=res)
     assert q['num_tiles'] > 2 * nat.lib().lfd_device_sm_count()
     assert_bf16_close(out, ref_conv(x, w, scale, shift, 1, True, res=res), 'large conv')
+
+
+TAIL_CASES = [   # (N, H, W, Cin, Cmid, k, stride, Cout2, residual on the tail output, gn on the tail output)
+    (2, 45, 80, 64, 64, 3, 2, 64, False, 0),     # stem2 + stem3 pattern
+    (1, 37, 29, 64, 64, 3, 1, 128, True, 0),
+    (2, 23, 31, 32, 32, 1, 1, 64, False, 0),
+    (1, 33, 41, 64, 64, 1, 1, 128, False, 16),
+]
+
+
+@pytest.mark.parametrize('case', TAIL_CASES, ids=lambda c: 'N%d_%dx%d_%d-%d_k%ds%d_tail%d_res%d_gn%d' % c)
+def test_conv_with_fused_1x1_tail(case):
+    """conv + scale/shift + ReLU -> (bf16) -> 1x1 conv + scale/shift (+res) + ReLU in ONE kernel == the two layers run
+    one after the other with the intermediate rounded to bf16."""
+    N, H, W, Cin, Cmid, k, s, C2, use_res, gn = case
+    x, w, scale, shift, _ = _make((N, H, W, Cin, Cmid, k, s, True, False, 0), seed=5)
+    g = torch.Generator().manual_seed(9)
+    w2 = bf16r(torch.randn((C2, Cmid, 1, 1), generator=g) * (2.0 / Cmid) ** 0.5)
+    sc2, sh2 = torch.rand((C2,), generator=g) + 0.5, torch.randn((C2,), generator=g) * 0.2
+    if gn:
+        sc2, sh2 = torch.ones(C2), torch.zeros(C2)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    res = bf16r(torch.randn((N, Ho, Wo, C2), generator=g)).to(torch.bfloat16).cuda() if use_res else None
+    out, stats, q = run_conv(x, w, scale, shift, s, True, res=res, gn_groups=gn, tail=(w2, sc2, sh2, not gn))
+    mid = bf16r(ref_conv(x, w, scale, shift, s, True))
+    ref = ref_conv(mid.to(torch.bfloat16), w2, sc2, sh2, 1, not gn, res=res)
+    # the intermediate itself may differ from the CPU one by 1 bf16 ulp on isolated elements (fp32 summation order), which
+    # moves isolated outputs by more than one output ulp: allow 2e-3 of the output range on top of the 1-ulp bound
+    o, r = out.float().cpu(), ref.float()
+    tol = r.abs() * 2.0 ** -7 + 2e-3 * float(r.abs().max())
+    assert bool(((o - r).abs() <= tol).all()), 'fused tail %s: max err %g (ref max %g) plan %s' % (case, float((o - r).abs().max()), float(r.abs().max()), q)
+    assert float(torch.sqrt(((o - r) ** 2).mean()) / torch.sqrt((r ** 2).mean())) < 3e-3
+    if gn:
+        og = out.float().cpu().reshape(N, -1, gn, C2 // gn).double()
+        assert torch.allclose(stats[..., 0].cpu(), og.sum(dim=(1, 3)), rtol=1e-6, atol=1e-3)

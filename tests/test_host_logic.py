@@ -75,13 +75,13 @@ def test_arena_reuses_and_coalesces():
     assert a.alloc(10) == o3 + 256
 
 
-@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 3 + 2 * 11 + 4 + 5 + 10), ('TT100K_L', 1 + 2 * 12 + 4 + 4 + 16)])
+@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 1 + 2 * 11 + 4 + 5 + 10), ('TT100K_L', 0 + 2 * 12 + 4 + 4 + 16)])   # stem 1x1 convs are fused tails
 def test_planner_builds_expected_graph(name, n_conv):
     model, _ = synth_model(name)
     plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
     rows = plan.describe()
     kinds = [r['kind'] for r in rows]
-    assert kinds[0] == 'stem0' and kinds.count('stem0') == 1
+    assert kinds[0] == 'stem0' and kinds.count('stem0') == 1 and rows[0]['tail_cout'] == 64
     assert kinds.count('conv') == n_conv
     levels = len(plan.level_sizes)
     merged = name.startswith('WIDERFACE')

@@ -110,7 +110,7 @@ int lfd_plan_forward(lfd_plan* plan, const void* input, int input_format, void* 
  * Synchronises the stream.  Used by bench.py for the live per-kernel roofline. */
 int lfd_plan_profile(lfd_plan* plan, const void* input, int input_format, void* workspace, float* cls_out, float* reg_out,
                      float* ms_per_op, lfd_stream stream);
-/* Debugging aid: device buffer long long[3][32][4] that CTA 0 of every following tcgen05 conv launch fills with a
+/* Debugging aid: device buffer long long[4][32][4] that CTA 0 of every following tcgen05 conv launch fills with a
  * clock64() timeline (role 0 producer / 1 MMA issuer / 2 epilogue, per tile); NULL switches it off. */
 int lfd_debug_set_trace(void* device_buffer);
 /* run a single op (tests / debugging) */

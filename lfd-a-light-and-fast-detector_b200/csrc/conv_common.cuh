@@ -42,6 +42,7 @@ struct UmmaConvParams {
     int N, H, W, Cin, Ho, Wo, Cout;
     int relu, gn_groups, mode;
     int tiles_x, tiles_per_img, num_tiles;
+    unsigned long long magic_tpi, magic_tx;   // ceil(2^40 / d) for division-free tile decomposition
     int n_px;                   // halo pixels loaded per stage
     int Cc, stages, b_resident;
     int log2_cpc, log2_cpr, log2_rp128, tmem_cols, ctas_per_sm;

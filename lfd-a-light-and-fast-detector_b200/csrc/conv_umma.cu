@@ -26,6 +26,8 @@
 //     the TMA engine as 1-D bulk copies (cp.async.bulk -> UBLKCP), either once (resident) or per stage
 //     (streamed, for 3x3x128x128 which does not fit next to the A ring).
 //   * two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "conv_common.cuh"
 #include "ptx.cuh"
 
@@ -35,6 +37,9 @@ static constexpr int kProdThreads = 128;
 
 #define LFD_TRACE(role, idx, slot) \
     do { if (p.trace && blockIdx.x == 0 && (idx) < 32) p.trace[((role) * 32 + (idx)) * 4 + (slot)] = clock64(); } while (0)
+
+// floor(x / d) for 0 <= x < 2^24 via one 32x32->64 multiply; m = ceil(2^40 / d), exact for d < 2^16
+LFD_DEVINL int fast_div(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
 
 struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's input origin) and where it goes
     int16_t dy, dx;
@@ -91,6 +96,9 @@ conv_umma_kernel(const UmmaConvParams p) {
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
     uint8_t* ring = smem + p.smem_ring_off;     // stages: [A chunk | B slice (streaming only)]
 
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
+    // weight fetch) while this one is still running; everything that touches upstream results waits at pdl_wait().
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -171,6 +179,7 @@ conv_umma_kernel(const UmmaConvParams p) {
 
     if (warp < EPI_WARPS) {
         // ============================================================== EPILOGUE
+        pdl_wait();                                   // residual reads, output stores and statistics depend on upstream kernels
         const int m = (warp & 3) * 32 + lane;        // D row == TMEM lane (a warp may only touch lane quarter warp % 4)
         const int chalf = warp >> 2;                  // EPI_WARPS == 8: second warp of the quarter takes the upper columns
         const int Cf = p.Cf;                          // channels of the stored tensor
@@ -182,7 +191,15 @@ conv_umma_kernel(const UmmaConvParams p) {
         const int HoWo = p.Ho * p.Wo;
         const uint32_t stg = smem_u32(staging);
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-
+        // Each thread moves the same (row, chunk) slots of the staging tile for every tile, and because the thread count is a
+        // multiple of 8 * (chunks per row) every per-slot quantity is affine in the slot index k: row_k = row_0 + k * rstep.
+        const int n_slots = (128 * cpr) / kEpiThreads;
+        const int sl_c = tid & (cpr - 1), sl_r0 = tid >> l2cpr, sl_rstep = kEpiThreads >> l2cpr;      // rstep is a multiple of 8
+        const uint32_t sl_stg0 = sl_r0 * row_bytes + ((sl_c ^ ((sl_r0 >> l2rp) & swz_mask)) << 4), sl_dstg = sl_rstep * row_bytes;
+        const int sl_goff0 = (MODE == MODE_FLAT ? sl_r0 * Cf : ((sl_r0 >> 3) * p.Wo + (sl_r0 & 7)) * Cf) + sl_c * 8;
+        const int sl_dgoff = MODE == MODE_FLAT ? sl_rstep * Cf : (sl_rstep >> 3) * p.Wo * Cf;
+        const int sl_y0 = MODE == MODE_FLAT ? sl_r0 : (sl_r0 >> 3), sl_dy = MODE == MODE_FLAT ? sl_rstep : (sl_rstep >> 3);
+        const int sl_x = sl_r0 & 7;
         // scale/shift (+ReLU) of 8 accumulator columns -> packed bf16
         auto affine8 = [&](const float* v, const float* sc, const float* sh, int col, int relu, const uint4* resv) -> uint4 {
             const float4 sc0 = *reinterpret_cast<const float4*>(sc + col), sc1 = *reinterpret_cast<const float4*>(sc + col + 4);
@@ -237,11 +254,11 @@ conv_umma_kernel(const UmmaConvParams p) {
         // ---- final phase: accumulator -> scale/shift (+residual) (+ReLU) -> bf16 staging -> (GN statistics) -> global
         auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, const float* sc,
                                const float* sh, int relu) {
-            const int n = tile / p.tiles_per_img;
+            const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
             int oy0 = 0, ox0 = 0, p0 = 0;
             if (MODE == MODE_FLAT) p0 = t * 128;
-            else { oy0 = (t / p.tiles_x) * 16; ox0 = (t % p.tiles_x) * 8; }
+            else { const int ty = fast_div(t, p.magic_tx); oy0 = ty * 16; ox0 = (t - ty * p.tiles_x) * 8; }
             const size_t img_out = (size_t)n * HoWo;
             // pixel index (within the image) of staged row r, or -1 when outside the feature map
             auto row_pixel = [&](int r) -> int {
@@ -251,13 +268,15 @@ conv_umma_kernel(const UmmaConvParams p) {
             };
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             const int ccols = Cf / (EPI_WARPS / 4), ccol0 = chalf * ccols;
+            // first element of the tile in the stored tensor, and the number of rows / columns of the tile inside the map
+            const size_t tile_org = (img_out + (MODE == MODE_FLAT ? p0 : oy0 * p.Wo + ox0)) * Cf;
+            const int lim_y = MODE == MODE_FLAT ? HoWo - p0 : p.Ho - oy0, lim_x = p.Wo - ox0;
+            const bool col_ok = MODE == MODE_FLAT ? true : sl_x < lim_x;
             if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
 #pragma unroll 4
-                for (int e = tid; e < 128 * cpr; e += kEpiThreads) {
-                    const int r = e >> l2cpr, c = e & (cpr - 1);
-                    const int q = row_pixel(r);
-                    const __nv_bfloat16* src = p.res + ((img_out + (q < 0 ? 0 : q)) * Cf + c * 8);
-                    cp_async16(stg + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4), src, q >= 0);
+                for (int k = 0; k < n_slots; ++k) {
+                    const bool ok = col_ok && (sl_y0 + k * sl_dy) < lim_y;
+                    cp_async16(stg + sl_stg0 + k * sl_dstg, p.res + (ok ? tile_org + sl_goff0 + k * sl_dgoff : 0), ok);
                 }
                 cp_async_commit();
             }
@@ -269,6 +288,7 @@ conv_umma_kernel(const UmmaConvParams p) {
                 cp_async_wait<0>();
                 named_bar_sync(1, kEpiThreads);
             }
+            if (tid == 0) LFD_TRACE(3, tc, 0);
             const uint32_t trow = tmem_base + lane_base + col_base + a * Cf + ccol0;
             uint8_t* my_row = staging + m * row_bytes;
             const int my_swz = (m >> l2rp) & swz_mask;
@@ -289,6 +309,7 @@ conv_umma_kernel(const UmmaConvParams p) {
             mbar_arrive(&bar_empty[a]);  // accumulator stage may be overwritten by the next-but-one tile
             if (tid == 0) LFD_TRACE(2, tc, 2);
             named_bar_sync(1, kEpiThreads);
+            if (tid == 0) LFD_TRACE(3, tc, 1);
             if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk (16 groups)
                 constexpr int TPG = kEpiThreads / 16;  // threads per group
                 const int g = tid / TPG, sl = tid % TPG;
@@ -313,13 +334,10 @@ conv_umma_kernel(const UmmaConvParams p) {
                 }
             }
 #pragma unroll 4
-            for (int e = tid; e < 128 * cpr; e += kEpiThreads) {  // coalesced store
-                const int r = e >> l2cpr, c = e & (cpr - 1);
-                const int q = row_pixel(r);
-                if (q < 0) continue;
-                const uint4 val = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4));
-                *reinterpret_cast<uint4*>(p.out + ((img_out + q) * Cf + c * 8)) = val;
-            }
+            for (int k = 0; k < n_slots; ++k)   // coalesced store
+                if (col_ok && (sl_y0 + k * sl_dy) < lim_y)
+                    *reinterpret_cast<uint4*>(p.out + tile_org + sl_goff0 + k * sl_dgoff) = *reinterpret_cast<const uint4*>(staging + sl_stg0 + k * sl_dstg);
+            if (tid == 0) LFD_TRACE(3, tc, 2);
             named_bar_sync(1, kEpiThreads);  // staging free again
             if (tid == 0) LFD_TRACE(2, tc, 3);
         };
@@ -431,8 +449,9 @@ conv_umma_kernel(const UmmaConvParams p) {
             uint32_t raw[kStemPerThread];
             uint32_t okmask = 0;
             auto fetch = [&](int tile) {
-                const int n = tile / p.tiles_per_img, t = tile - n * p.tiles_per_img;
-                const int iy0 = 2 * (t / p.tiles_x) * 16 - 1, ix0 = 2 * (t % p.tiles_x) * 8 - 1;
+                const int n = fast_div(tile, p.magic_tpi), t = tile - n * p.tiles_per_img;
+                const int ty = fast_div(t, p.magic_tx);
+                const int iy0 = 2 * ty * 16 - 1, ix0 = 2 * (t - ty * p.tiles_x) * 8 - 1;
                 okmask = 0;
 #pragma unroll
                 for (int j = 0; j < kStemPerThread; ++j) {
@@ -455,6 +474,7 @@ conv_umma_kernel(const UmmaConvParams p) {
             };
             uint32_t it = 0;
             int buf = 0;
+            pdl_wait();
             if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, buf ^= 1) {
                 __nv_bfloat16* patch = stem_patch + buf * (kStemPatchBytes / 2);
@@ -497,13 +517,15 @@ conv_umma_kernel(const UmmaConvParams p) {
         const int pstep = kProdThreads >> p.log2_cpc;
         const uint32_t ch_dst = ch * p.lbo_a;
         uint32_t it = 0;
+        pdl_wait();                                   // the input activations are produced by the previous kernel
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int n = tile / p.tiles_per_img;
+            const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
             int iy0 = 0, ix0 = 0;
             if (MODE == MODE_FLAT) ix0 = t * 128;
             else {
-                int oy0 = (t / p.tiles_x) * 16, ox0 = (t % p.tiles_x) * 8;
+                const int ty = fast_div(t, p.magic_tx);
+                int oy0 = ty * 16, ox0 = (t - ty * p.tiles_x) * 8;
                 iy0 = (MODE == MODE_3X3S1) ? oy0 : 2 * oy0;
                 ix0 = (MODE == MODE_3X3S1) ? ox0 : 2 * ox0;
             }
@@ -591,6 +613,9 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     const int plane_slots = px_slots | 1;
     p.lbo_a = plane_slots * 16;
     p.num_tiles = p.tiles_per_img * g.N;
+    if (p.num_tiles >= (1 << 24) || p.tiles_per_img >= (1 << 16)) return -5;
+    p.magic_tpi = ((1ull << 40) + p.tiles_per_img - 1) / p.tiles_per_img;
+    p.magic_tx = p.tiles_x ? ((1ull << 40) + p.tiles_x - 1) / p.tiles_x : 0;
     const int Cf = g.tail_cout > 0 ? g.tail_cout : g.Cout;
     if (g.tail_cout) {
         if (g.tail_cout % 16 || g.tail_cout > 128 || g.tail_cout < 16 || 2 * (g.Cout + g.tail_cout) > 512) return -4;
@@ -692,8 +717,19 @@ static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, c
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    conv_umma_kernel<MODE, EPI_WARPS><<<grid, EPI_WARPS * 32 + 32 + kProdThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    static const bool use_pdl = getenv("LFD_B200_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(EPI_WARPS * 32 + 32 + kProdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, EPI_WARPS>, p);
 }
 
 cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {

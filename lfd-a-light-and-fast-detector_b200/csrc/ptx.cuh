@@ -63,6 +63,10 @@ LFD_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+LFD_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+LFD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- cp.async (LDGSTS) 16 B with zero fill
 LFD_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
     uint32_t sz = valid ? 16u : 0u;

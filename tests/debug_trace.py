@@ -11,7 +11,7 @@ from gpu_ops import run_conv  # noqa: E402
 from lfd import _native as nat  # noqa: E402
 from test_gpu_conv import _make  # noqa: E402
 
-CASES = {'3x3s1': (8, 90, 160, 64, 64, 3, 1, True, False, 0), 'flat': (8, 180, 320, 64, 64, 1, 1, True, False, 0),
+CASES = {'3x3s1': (8, 90, 160, 64, 64, 3, 1, True, False, 0), '3x3s1res': (8, 90, 160, 64, 64, 3, 1, True, True, 0), 'flat': (8, 180, 320, 64, 64, 1, 1, True, False, 0),
          '3x3s2': (8, 180, 320, 64, 64, 3, 2, True, False, 0), 'stream': (8, 12, 20, 128, 128, 3, 1, True, False, 0)}
 
 
@@ -19,7 +19,7 @@ def main():
     for name in (sys.argv[1:] or list(CASES)):
         case = CASES[name]
         x, w, scale, shift, res = _make(case)
-        buf = torch.zeros((3, 32, 4), dtype=torch.int64, device='cuda')
+        buf = torch.zeros((4, 32, 4), dtype=torch.int64, device='cuda')
         run_conv(x, w, scale, shift, case[6], case[7], res=res)          # warm-up (weights / L2)
         nat.lib().lfd_debug_set_trace(nat.ptr(buf))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,7 +30,8 @@ def main():
         rel = (t - t0).clamp(min=-1)
         print('== %s %s plan=%s' % (name, case, q))
         for role, rn, cols in ((0, 'producer', 'wait_empty got_empty issued arrived_full'), (1, 'mma', 'wait_tempty got_tempty first_full committed'),
-                               (2, 'epilogue', 'wait_tfull got_tfull tmem_read_done stored')):
+                               (2, 'epilogue', 'wait_tfull got_tfull tmem_read_done stored'),
+                               (3, 'epilogue detail', 'res_ready after_bar1 store_loop_done -')):
             print('  %s  [%s]' % (rn, cols))
             for i in range(12):
                 if int(t[role, i].max()) == 0:

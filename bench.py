@@ -34,7 +34,7 @@ import torch  # noqa: E402
 WORKLOADS = {
     'WIDERFACE_S': dict(cfg='WIDERFACE_S', N=8, H=720, W=1280, name='WIDERFACE-S inference 1280x720 batch=8 per GPU'),
     'WIDERFACE_XS': dict(cfg='WIDERFACE_XS', N=1, H=480, W=640, name='WIDERFACE-XS inference 640x480 batch=1'),
-    'TT100K_L': dict(cfg='TT100K_L', N=16, H=1080, W=1920, name='TT100K LFD_L inference 1920x1080 batch=16 per GPU'),
+    'TT100K_L': dict(cfg='TT100K_L', N=16, H=1080, W=1920, name='TT100K LFD_L inference 1920x1080 batch=16 per GPU', pass_fraction=0.0002, cap=16384),
 }
 POOL = 8          # device-resident input batches rotated through (8 x 22 MB = 177 MB > 126 MB L2)
 IOU_THR = 0.3     # WIDERFACE_train/predict.py:22
@@ -206,6 +206,8 @@ def main():
     model.to(dev)
     model.conv_impl = nat.CONV_SIMT if args.conv_impl == 'simt' else nat.CONV_UMMA
     model.use_cuda_graph = not args.no_graph
+    model.max_detections_per_image = wl.get('cap', 8192)
+    pass_fraction = wl.get('pass_fraction', PASS_FRACTION)
     N, H, W = wl['N'], wl['H'], wl['W']
     g = torch.Generator().manual_seed(1000 + rank)
     host_pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -218,7 +220,7 @@ def main():
     with torch.no_grad():
         cls, _ = plan.forward(pool[0], use_graph=False)
         scores = cls.sigmoid() if plan.cls_channels == model._num_classes else cls.softmax(-1)[..., :-1]
-        score_thr = float(torch.quantile(scores.flatten()[:2000000].float(), 1.0 - PASS_FRACTION))
+        score_thr = float(torch.quantile(scores.flatten()[:2000000].float(), 1.0 - pass_fraction))
     stream = torch.cuda.current_stream()
 
     def step(i):
@@ -335,7 +337,7 @@ def main():
     line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(warmup, POOL), ms_per_step=ms_step,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
                 config=dict(workload=wl['name'], input='uint8 BGR NHWC frames, normalisation fused into the stem kernel',
-                            weights='synthetic (tests/synth.py)', score_thr='%.4f (calibrated: %.1f%% of points pass)' % (score_thr, 100 * PASS_FRACTION),
+                            weights='synthetic (tests/synth.py)', score_thr='%.4f (calibrated: %.2f%% of (point, class) scores pass)' % (score_thr, 100 * pass_fraction),
                             iou_thr=IOU_THR, detections_last_step=counts[:N], parallelism='batch-sharded replicas x%d, no collective' % world,
                             l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
                                % (POOL, POOL * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),

@@ -160,6 +160,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift; p.stats = nullptr;
                 p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
+                if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem conv");
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
             break;
@@ -179,6 +180,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 p.scale = o.scale; p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 p.trace = g_trace;
+                if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for conv %dx%d Cf=%d", o.ksize, o.ksize, p.Cf);
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
             break;

@@ -1,5 +1,6 @@
 // conv_common.cuh -- shared declarations of the convolution kernels (internal, not part of the C-ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -22,7 +23,10 @@ struct ConvGeom {
     int stem;   // 1: 3x3/s2 conv on the raw 3-channel image (K = 27 padded to 32), operand built by the producers
 };
 
-struct UmmaConvParams {
+struct alignas(64) UmmaConvParams {
+    CUtensorMap tm_out;         // TMA descriptor of the stored tensor (epilogue tile store)
+    CUtensorMap tm_res;         // TMA descriptor of the residual tensor (same geometry)
+    int use_tma;                // 0: element-wise cp.async / st.global epilogue (fallback, LFD_B200_NO_TMA=1)
     const __nv_bfloat16* in;
     __nv_bfloat16* out;
     const void* in_raw;         // MODE_STEM: the image, fp32 NCHW (input_format 0) or uint8 NHWC (1)
@@ -55,6 +59,8 @@ struct UmmaConvParams {
 // returns 0 when the geometry is supported by the tcgen05 kernel
 int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid);
 cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st);
+// fills p->tm_out / p->tm_res from p->out / p->res (host, no launch); returns 0 on success
+int umma_conv_encode_maps(UmmaConvParams* p);
 
 // SIMT cross-check kernel (same packed weights, same epilogue semantics); debugging / validation only.
 cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out,

@@ -71,7 +71,7 @@ __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of
 
 template <int MODE, int EPI_WARPS>
 __global__ void __launch_bounds__(EPI_WARPS * 32 + 32 + kProdThreads, (EPI_WARPS == 4 ? 2 : 1))
-conv_umma_kernel(const UmmaConvParams p) {
+conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     constexpr int kEpiThreads = EPI_WARPS * 32;
     constexpr int kMmaWarp = EPI_WARPS;
     constexpr int kThreads = kEpiThreads + 32 + kProdThreads;
@@ -86,7 +86,8 @@ conv_umma_kernel(const UmmaConvParams p) {
     uint64_t* a2_empty = a2_full + 2; //       ... consumed by the tail MMAs
     uint64_t* tfull2 = a2_empty + 2;  //       tail accumulator ready
     uint64_t* tempty2 = tfull2 + 2;   //       tail accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty2 + 2);
+    uint64_t* res_bar = tempty2 + 2;  // residual tile landed (TMA load)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
     float* s_scale = reinterpret_cast<float*>(smem + kSmemScaleOff);
     float* s_shift = s_scale + 128;
     float* s_scale2 = s_shift + 128;
@@ -122,6 +123,7 @@ conv_umma_kernel(const UmmaConvParams p) {
             mbar_init(&tfull2[i], 1);
             mbar_init(&tempty2[i], kEpiThreads);
         }
+        mbar_init(res_bar, 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -195,11 +197,22 @@ conv_umma_kernel(const UmmaConvParams p) {
         // multiple of 8 * (chunks per row) every per-slot quantity is affine in the slot index k: row_k = row_0 + k * rstep.
         const int n_slots = (128 * cpr) / kEpiThreads;
         const int sl_c = tid & (cpr - 1), sl_r0 = tid >> l2cpr, sl_rstep = kEpiThreads >> l2cpr;      // rstep is a multiple of 8
-        const uint32_t sl_stg0 = sl_r0 * row_bytes + ((sl_c ^ ((sl_r0 >> l2rp) & swz_mask)) << 4), sl_dstg = sl_rstep * row_bytes;
+        const uint32_t sl_dstg = sl_rstep * (row_bytes >= 128 ? 128 : row_bytes);   // rstep is a multiple of 8: the XOR term is k-invariant
         const int sl_goff0 = (MODE == MODE_FLAT ? sl_r0 * Cf : ((sl_r0 >> 3) * p.Wo + (sl_r0 & 7)) * Cf) + sl_c * 8;
         const int sl_dgoff = MODE == MODE_FLAT ? sl_rstep * Cf : (sl_rstep >> 3) * p.Wo * Cf;
         const int sl_y0 = MODE == MODE_FLAT ? sl_r0 : (sl_r0 >> 3), sl_dy = MODE == MODE_FLAT ? sl_rstep : (sl_rstep >> 3);
         const int sl_x = sl_r0 & 7;
+        // Staging tile layout == what the TMA engine expects for its swizzle modes: rows of >= 128 B are split into 128-byte
+        // panels [panel][row][128 B] with the 16-byte chunk index XORed by (row & 7) (SWIZZLE_128B); 64 / 32-byte rows use
+        // the 64B / 32B patterns.  The same function serves the element-wise fallback.
+        const bool wide = row_bytes >= 128;
+        auto stg_off = [&](int r, int c) -> uint32_t {
+            if (wide) return (uint32_t)((c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+            return (uint32_t)(r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4));
+        };
+        const int n_panels = wide ? (row_bytes >> 7) : 1;
+        if (p.use_tma && tid == 0 && (stg & 1023u)) __trap();   // swizzle atoms need a 1024-byte aligned staging tile
+
         // scale/shift (+ReLU) of 8 accumulator columns -> packed bf16
         auto affine8 = [&](const float* v, const float* sc, const float* sh, int col, int relu, const uint4* resv) -> uint4 {
             const float4 sc0 = *reinterpret_cast<const float4*>(sc + col), sc1 = *reinterpret_cast<const float4*>(sc + col + 4);
@@ -212,12 +225,13 @@ conv_umma_kernel(const UmmaConvParams p) {
                 o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
                 o[4] += bf16_lo(rv.z); o[5] += bf16_hi(rv.z); o[6] += bf16_lo(rv.w); o[7] += bf16_hi(rv.w);
             }
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
             uint4 ov;
-            ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+            if (relu) {
+                ov.x = pack_bf16x2_relu(o[0], o[1]); ov.y = pack_bf16x2_relu(o[2], o[3]);
+                ov.z = pack_bf16x2_relu(o[4], o[5]); ov.w = pack_bf16x2_relu(o[6], o[7]);
+            } else {
+                ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+            }
             return ov;
         };
 
@@ -272,26 +286,38 @@ conv_umma_kernel(const UmmaConvParams p) {
             const size_t tile_org = (img_out + (MODE == MODE_FLAT ? p0 : oy0 * p.Wo + ox0)) * Cf;
             const int lim_y = MODE == MODE_FLAT ? HoWo - p0 : p.Ho - oy0, lim_x = p.Wo - ox0;
             const bool col_ok = MODE == MODE_FLAT ? true : sl_x < lim_x;
-            if (p.res) {  // residual tile -> staging (coalesced), consumed row-wise below
+            const uint32_t sl_stg0 = stg_off(sl_r0, sl_c);
+            if (p.res) {  // residual tile -> staging, consumed row-wise below
+                if (p.use_tma) {
+                    if (tid == 0) {   // one TMA box per 128-byte panel; out-of-map rows / columns arrive as zeros
+                        mbar_arrive_expect_tx(res_bar, 128 * row_bytes);
+                        for (int pn = 0; pn < n_panels; ++pn) {
+                            if (MODE == MODE_FLAT) tma_load_3d(stg + pn * 16384, &p.tm_res, pn * 64, p0, n, res_bar);
+                            else tma_load_4d(stg + pn * 16384, &p.tm_res, pn * 64, ox0, oy0, n, res_bar);
+                        }
+                    }
+                } else {
 #pragma unroll 4
-                for (int k = 0; k < n_slots; ++k) {
-                    const bool ok = col_ok && (sl_y0 + k * sl_dy) < lim_y;
-                    cp_async16(stg + sl_stg0 + k * sl_dstg, p.res + (ok ? tile_org + sl_goff0 + k * sl_dgoff : 0), ok);
+                    for (int k = 0; k < n_slots; ++k) {
+                        const bool ok = col_ok && (sl_y0 + k * sl_dy) < lim_y;
+                        cp_async16(stg + sl_stg0 + k * sl_dstg, p.res + (ok ? tile_org + sl_goff0 + k * sl_dgoff : 0), ok);
+                    }
+                    cp_async_commit();
                 }
-                cp_async_commit();
             }
             if (tid == 0) LFD_TRACE(2, tc, 0);
             mbar_wait(&bar_full[a], aph);
             tc_fence_after_sync();
             if (tid == 0) LFD_TRACE(2, tc, 1);
             if (p.res) {
-                cp_async_wait<0>();
-                named_bar_sync(1, kEpiThreads);
+                if (p.use_tma) mbar_wait(res_bar, tc & 1);
+                else {
+                    cp_async_wait<0>();
+                    named_bar_sync(1, kEpiThreads);
+                }
             }
             if (tid == 0) LFD_TRACE(3, tc, 0);
             const uint32_t trow = tmem_base + lane_base + col_base + a * Cf + ccol0;
-            uint8_t* my_row = staging + m * row_bytes;
-            const int my_swz = (m >> l2rp) & swz_mask;
             for (int c0 = 0; c0 < ccols; c0 += 32) {
                 float v[32];
                 tmem_ld16(trow + c0, v);
@@ -301,22 +327,30 @@ conv_umma_kernel(const UmmaConvParams p) {
                 for (int h = 0; h < 4; ++h) {
                     if (c0 + h * 8 >= ccols) break;
                     const int col = ccol0 + c0 + h * 8;
-                    uint4* slot = reinterpret_cast<uint4*>(my_row + (((col >> 3) ^ my_swz) << 4));
+                    uint4* slot = reinterpret_cast<uint4*>(staging + stg_off(m, col >> 3));
                     *slot = affine8(v + h * 8, sc, sh, col, relu, p.res ? slot : nullptr);
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(&bar_empty[a]);  // accumulator stage may be overwritten by the next-but-one tile
             if (tid == 0) LFD_TRACE(2, tc, 2);
+            if (p.use_tma) fence_proxy_async_smem();   // st.shared (generic proxy) -> TMA store (async proxy)
             named_bar_sync(1, kEpiThreads);
             if (tid == 0) LFD_TRACE(3, tc, 1);
+            if (p.use_tma && tid == 0) {   // the whole tile leaves through the TMA engine; rows / columns outside the map are clipped
+                for (int pn = 0; pn < n_panels; ++pn) {
+                    if (MODE == MODE_FLAT) tma_store_3d(&p.tm_out, stg + pn * 16384, pn * 64, p0, n);
+                    else tma_store_4d(&p.tm_out, stg + pn * 16384, pn * 64, ox0, oy0, n);
+                }
+                bulk_commit();
+            }
             if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk (16 groups)
                 constexpr int TPG = kEpiThreads / 16;  // threads per group
                 const int g = tid / TPG, sl = tid % TPG;
                 float s1 = 0.f, s2 = 0.f;
                 for (int r = sl; r < 128; r += TPG) {
                     if (row_pixel(r) < 0) continue;
-                    uint4 q = *reinterpret_cast<const uint4*>(staging + r * row_bytes + ((g ^ ((r >> l2rp) & swz_mask)) << 4));
+                    uint4 q = *reinterpret_cast<const uint4*>(staging + stg_off(r, g));
                     float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                   bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
 #pragma unroll
@@ -333,10 +367,14 @@ conv_umma_kernel(const UmmaConvParams p) {
                     atomicAdd(dst + 1, (double)s2);
                 }
             }
+            if (!p.use_tma) {
 #pragma unroll 4
-            for (int k = 0; k < n_slots; ++k)   // coalesced store
-                if (col_ok && (sl_y0 + k * sl_dy) < lim_y)
-                    *reinterpret_cast<uint4*>(p.out + tile_org + sl_goff0 + k * sl_dgoff) = *reinterpret_cast<const uint4*>(staging + sl_stg0 + k * sl_dstg);
+                for (int k = 0; k < n_slots; ++k)   // coalesced store
+                    if (col_ok && (sl_y0 + k * sl_dy) < lim_y)
+                        *reinterpret_cast<uint4*>(p.out + tile_org + sl_goff0 + k * sl_dgoff) = *reinterpret_cast<const uint4*>(staging + sl_stg0 + k * sl_dstg);
+            } else if (tid == 0) {
+                bulk_wait_read_all();        // the TMA engine has finished reading the staging tile
+            }
             if (tid == 0) LFD_TRACE(3, tc, 2);
             named_bar_sync(1, kEpiThreads);  // staging free again
             if (tid == 0) LFD_TRACE(2, tc, 3);
@@ -356,6 +394,7 @@ conv_umma_kernel(const UmmaConvParams p) {
                 if (!has) break;
             }
         }
+        if (p.use_tma && tid == 0) bulk_wait_all();   // all tile stores have been performed before the CTA retires
     } else if (warp == kMmaWarp) {
         // ============================================================== MMA ISSUER
         // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
@@ -706,6 +745,57 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     const int max_ctas = num_sms * p.ctas_per_sm;
     *grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
     *out = p;
+    return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int encode_one(const UmmaConvParams& p, const void* ptr, CUtensorMap* tm) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    const cuuint64_t Cf = p.Cf, HoWo = (cuuint64_t)p.Ho * p.Wo;
+    const cuuint32_t inner = p.Cf < 64 ? p.Cf : 64;
+    const CUtensorMapSwizzle swz = inner * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (inner * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    cuuint32_t rank;
+    if (p.mode == MODE_FLAT) {
+        rank = 3;
+        dims[0] = Cf; dims[1] = HoWo; dims[2] = p.N;
+        strides[0] = Cf * 2; strides[1] = HoWo * Cf * 2;
+        box[0] = inner; box[1] = 128; box[2] = 1;
+    } else {
+        rank = 4;
+        dims[0] = Cf; dims[1] = p.Wo; dims[2] = p.Ho; dims[3] = p.N;
+        strides[0] = Cf * 2; strides[1] = (cuuint64_t)p.Wo * Cf * 2; strides[2] = HoWo * Cf * 2;
+        box[0] = inner; box[1] = 8; box[2] = 16; box[3] = 1;
+    }
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+int umma_conv_encode_maps(UmmaConvParams* p) {
+    static const bool disabled = getenv("LFD_B200_NO_TMA") != nullptr;
+    p->use_tma = 0;
+    if (disabled) return 0;
+    if (encode_one(*p, p->out, &p->tm_out)) return -1;
+    if (p->res && encode_one(*p, p->res, &p->tm_res)) return -1;
+    p->use_tma = 1;
     return 0;
 }
 

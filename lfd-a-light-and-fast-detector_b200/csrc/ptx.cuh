@@ -101,6 +101,32 @@ LFD_DEVINL bool elect_one_sync() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- TMA tensor copies (cp.async.bulk.tensor)
+// tmap: generic address of a CUtensorMap living in kernel-parameter (__grid_constant__) space
+LFD_DEVINL void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(src_smem)
+                 : "memory");
+}
+LFD_DEVINL void tma_store_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3), "r"(src_smem)
+                 : "memory");
+}
+LFD_DEVINL void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+LFD_DEVINL void tma_load_4d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst_smem),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+LFD_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+LFD_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+LFD_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05: TMEM alloc
 // cols: power of two in [32, 512]
 LFD_DEVINL void tmem_alloc(uint32_t* slot_in_smem, uint32_t cols) {  // whole warp, .sync.aligned
@@ -166,6 +192,12 @@ LFD_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 LFD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// max(x, 0) fused into the conversion (cvt.rn.relu)
+LFD_DEVINL uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 LFD_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 LFD_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

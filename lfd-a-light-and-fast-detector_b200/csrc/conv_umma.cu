@@ -483,31 +483,59 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             // im2col of the raw image: K = 27 (kh, kw, ci) padded to 32.  The patch of tile t+1 is fetched into registers
             // while the operand of tile t is assembled from the shared-memory patch of tile t.
             const int my = ptid >> 3, mx = ptid & 7;            // this thread's output pixel inside the 16x8 tile
-            // raw values of the NEXT tile's patch elements (loads are unconditional on clamped addresses so that all of
-            // them are in flight together; out-of-image elements are masked when the patch is written)
+            // raw values of the NEXT tile's patch elements.  Element descriptors are tile invariant and live in registers;
+            // loads are unconditional (clamped addresses) so that all of them are in flight together, out-of-image elements
+            // are masked when the patch is written.  Tiles whose patch lies inside the image skip the clamping.
             uint32_t raw[kStemPerThread];
             uint32_t okmask = 0;
+            int e_off[kStemPerThread];        // element offset of (row, byte/pixel, channel) relative to the patch origin
+            uint16_t e_dst[kStemPerThread];
+            const int row_pitch = p.input_format == 1 ? p.W * 3 : p.W;
+#pragma unroll
+            for (int j = 0; j < kStemPerThread; ++j) {
+                const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];
+                e_dst[j] = se.dst;
+                e_off[j] = se.row * row_pitch + se.off + (p.input_format == 1 ? 0 : (int)se.ci * p.H * p.W);
+            }
+            const int last_cnt = kStemElems - (kStemPerThread - 1) * kProdThreads;   // threads that own an element in the last round
             auto fetch = [&](int tile) {
                 const int n = fast_div(tile, p.magic_tpi), t = tile - n * p.tiles_per_img;
                 const int ty = fast_div(t, p.magic_tx);
                 const int iy0 = 2 * ty * 16 - 1, ix0 = 2 * (t - ty * p.tiles_x) * 8 - 1;
-                okmask = 0;
+                const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + kStemRows <= p.H && ix0 + kStemCols <= p.W;
+                if (p.input_format == 1) {
+                    const uint8_t* org = reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + iy0) * row_pitch + ix0 * 3;
+                    if (interior) {
+                        okmask = 0xffffffffu;
 #pragma unroll
-                for (int j = 0; j < kStemPerThread; ++j) {
-                    const int e = min(ptid + j * kProdThreads, kStemElems - 1);
-                    const StemEntry se = stem_table[e];
-                    const int y = iy0 + se.row;
-                    const int yc = min(max(y, 0), p.H - 1);
-                    if (p.input_format == 1) {
-                        const int b = ix0 * 3 + se.off;
-                        const int bc = min(max(b, 0), p.W * 3 - 1);
-                        if (y == yc && b == bc) okmask |= 1u << j;
-                        raw[j] = __ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + yc) * p.W * 3 + bc);
+                        for (int j = 0; j < kStemPerThread; ++j) raw[j] = __ldg(org + e_off[j]);
                     } else {
-                        const int x = ix0 + se.off;
-                        const int xc = min(max(x, 0), p.W - 1);
-                        if (y == yc && x == xc) okmask |= 1u << j;
-                        raw[j] = __float_as_uint(__ldg(reinterpret_cast<const float*>(p.in_raw) + (((size_t)n * 3 + se.ci) * p.H + yc) * p.W + xc));
+                        okmask = 0;
+#pragma unroll
+                        for (int j = 0; j < kStemPerThread; ++j) {
+                            const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];   // border tiles only
+                            const int y = iy0 + se.row, b = ix0 * 3 + se.off;
+                            const int yc = min(max(y, 0), p.H - 1), bc = min(max(b, 0), row_pitch - 1);
+                            if (y == yc && b == bc) okmask |= 1u << j;
+                            raw[j] = __ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + yc) * row_pitch + bc);
+                        }
+                    }
+                } else {
+                    const float* org = reinterpret_cast<const float*>(p.in_raw) + ((size_t)n * 3 * p.H + iy0) * p.W + ix0;
+                    if (interior) {
+                        okmask = 0xffffffffu;
+#pragma unroll
+                        for (int j = 0; j < kStemPerThread; ++j) raw[j] = __float_as_uint(__ldg(org + e_off[j]));
+                    } else {
+                        okmask = 0;
+#pragma unroll
+                        for (int j = 0; j < kStemPerThread; ++j) {
+                            const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];
+                            const int y = iy0 + se.row, x = ix0 + se.off;
+                            const int yc = min(max(y, 0), p.H - 1), xc = min(max(x, 0), p.W - 1);
+                            if (y == yc && x == xc) okmask |= 1u << j;
+                            raw[j] = __float_as_uint(__ldg(org + e_off[j] + (yc - y) * p.W + (xc - x)));
+                        }
                     }
                 }
             };
@@ -519,11 +547,10 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 __nv_bfloat16* patch = stem_patch + buf * (kStemPatchBytes / 2);
 #pragma unroll
                 for (int j = 0; j < kStemPerThread; ++j) {
-                    const int e = ptid + j * kProdThreads;
-                    if (e < kStemElems) {
+                    if (j < kStemPerThread - 1 || ptid < last_cnt) {
                         float v = p.input_format == 1 ? ((float)raw[j] - 127.5f) * (1.0f / 127.5f) : __uint_as_float(raw[j]);
                         if (!((okmask >> j) & 1u)) v = 0.f;
-                        patch[stem_table[e].dst] = __float2bfloat16_rn(v);   // rounding point R0
+                        patch[e_dst[j]] = __float2bfloat16_rn(v);   // rounding point R0
                     }
                 }
                 named_bar_sync(2, kProdThreads);
@@ -687,8 +714,12 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
         if (st > 4 && stage >= 8192) st = 4;
         return st;
     };
-    for (int want = 3; want >= 2 && !best_cc; --want)
+    // (16-channel chunks mean 32-byte global segments per pixel and twice the barrier round trips per tile: measured
+    //  1600 cycles per 19 KB stage for the 3x3/s2 stem conv, so a 2-deep ring of 32-channel stages beats a 4-deep one of 16)
+    for (int pass = 0; pass < 3 && !best_cc; ++pass)
         for (int ci = 0; ci < 3 && !best_cc; ++ci) {
+            const int want = pass == 0 ? 3 : 2;
+            if (pass < 2 && cands[ci] < 32) continue;
             int st = stages_for(cands[ci], 1);
             if (st >= want) { best_cc = cands[ci]; best_res = 1; best_st = st; }
         }

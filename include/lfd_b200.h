@@ -58,11 +58,13 @@ enum { LFD_INPUT_F32_NCHW = 0, LFD_INPUT_U8_NHWC = 1 };
 enum { LFD_CONV_UMMA = 0, LFD_CONV_SIMT = 1 }; /* SIMT = cross-check kernel, validation only */
 
 /* One fused layer.  Activations are bf16 NHWC at byte offsets into the caller's workspace.
- *   STEM0      3x3/s2 conv on the 3-channel image + scale/shift (+ReLU); in_off ignored (reads the external input);
+ *   STEM0      3x3/s2 conv on the 3-channel image + shift (+ReLU), scale folded into the weights like CONV; in_off ignored (reads the external input);
  *              weight = bf16 packed [4][Cout][8]: k = 8*kc + j with k = (kh*3 + kw)*3 + ci, entries with k >= 27 are 0
  *              (the K = 27 im2col operand, padded to 32, is assembled from the raw image inside the kernel).
- *   CONV       ksize in {1,3}, stride in {1,2}, pad = ksize/2; y = conv(x)*scale + shift (+res) (ReLU) -> bf16;
- *              weight = bf16 packed [Cin/cc][ksize^2][cc/8][Cout][8] with cc from lfd_conv_query;
+ *   CONV       ksize in {1,3}, stride in {1,2}, pad = ksize/2; y = conv(x) + shift (+res) (ReLU) -> bf16;
+ *              weight = bf16 packed [Cin/cc][ksize^2][cc/8][Cout][8] with cc from lfd_conv_query, ALREADY MULTIPLIED by the
+ *              per-output-channel scale (folded BatchNorm); `scale` must be NULL; `shift` (fp32 [Cout], may be NULL) is rounded
+ *              to bf16 and added on the tensor core;
  *              gn_groups > 0: also accumulates sum / sum-of-squares of the stored output per (image, group)
  *              into double[N][gn_groups][2] at stats_off (group size must be 8).
  *   GN_APPLY   y = relu(gamma * (x - mean) * rstd + beta) from the statistics at stats_off, bf16 -> bf16.
@@ -79,12 +81,12 @@ typedef struct lfd_op {
                                  main-stream op that precedes the branch's first op and joined at the end */
     int64_t in_off, out_off, res_off, stats_off; /* bytes; -1 = unused */
     const void* weight;
-    const float* scale;
+    const float* scale; /* HEAD_FINAL: per-output scale; STEM0 / CONV: must be NULL (fold it into the weights) */
     const float* shift;
     const float* gamma;
     const float* beta;
     /* STEM0 / CONV only: a 1x1/s1 conv (Cout -> tail_cout) + scale/shift (+ReLU) fused behind this layer inside the same
-     * kernel; tail_weight = bf16 packed [Cout/8][tail_cout][8].  The stored tensor then has tail_cout channels and
+     * kernel; tail_weight = bf16 packed [Cout/8][tail_cout][8] (scale folded in, tail_scale must be NULL).  The stored tensor then has tail_cout channels and
      * res_off / gn_groups / stats_off refer to it; the Cout-channel intermediate never reaches HBM.  0 = no tail. */
     int32_t tail_cout, tail_relu;
     const void* tail_weight;

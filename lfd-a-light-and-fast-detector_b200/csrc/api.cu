@@ -106,11 +106,13 @@ static int check_op(const lfd_op& o) {
     const int ew = (o.W + 2 * (o.ksize / 2) - o.ksize) / (o.stride > 0 ? o.stride : 1) + 1;
     switch (o.kind) {
         case LFD_OP_STEM0:
+            if (o.scale || o.tail_scale) return fail(LFD_ERR_INVALID, "conv scale must be folded into the packed weights (pass scale = NULL)");
             if (o.Cin != 3 || o.ksize != 3 || o.stride != 2) return fail(LFD_ERR_UNSUPPORTED, "stem0 supports 3x3/s2 on 3 input channels only (got Cin=%d k=%d s=%d)", o.Cin, o.ksize, o.stride);
             if (o.Cout != 16 && o.Cout != 32 && o.Cout != 64) return fail(LFD_ERR_UNSUPPORTED, "stem0 Cout must be 16/32/64 (got %d)", o.Cout);
             if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "stem0 output size mismatch");
             break;
         case LFD_OP_CONV:
+            if (o.scale || o.tail_scale) return fail(LFD_ERR_INVALID, "conv scale must be folded into the packed weights (pass scale = NULL)");
             if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "conv output size mismatch (%dx%d vs %dx%d)", o.Ho, o.Wo, eh, ew);
             if (o.gn_groups && ((o.tail_cout ? o.tail_cout : o.Cout) != o.gn_groups * 8 || o.gn_groups != 16)) return fail(LFD_ERR_UNSUPPORTED, "fused GroupNorm statistics need 16 groups of 8 channels (Cout=%d groups=%d)", o.Cout, o.gn_groups);
             if (o.cc <= 0 || o.Cin % o.cc) return fail(LFD_ERR_INVALID, "conv cc=%d does not divide Cin=%d", o.cc, o.Cin);
@@ -150,16 +152,16 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 if (o.tail_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails");
                 Stem0Params p;
                 p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
-                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift;
+                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.shift = o.shift;
                 p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu;
                 CUDA_TRY(stem0_launch(p, st));
             } else {
                 UmmaConvParams p = po.cp;
                 p.in_raw = input; p.input_format = input_format; p.in = nullptr;
                 p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off); p.res = nullptr;
-                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.scale = o.scale; p.shift = o.shift; p.stats = nullptr;
+                p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.shift = o.shift; p.stats = nullptr;
                 p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace;
-                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
+                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem conv");
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
@@ -172,13 +174,13 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
             double* stats = o.gn_groups ? reinterpret_cast<double*>(ws + o.stats_off) : nullptr;
             if (conv_impl == LFD_CONV_SIMT) {
                 if (o.tail_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails");
-                CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight), o.scale,
+                CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight),
                                           o.shift, stats, o.gn_groups, o.relu, st));
             } else {
                 UmmaConvParams p = po.cp;
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
-                p.scale = o.scale; p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
-                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.scale2 = o.tail_scale; p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
+                p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
+                p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 p.trace = g_trace;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for conv %dx%d Cf=%d", o.ksize, o.ksize, p.Cf);
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));

@@ -13,9 +13,11 @@ enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3, MODE_STEM 
 static constexpr int kMaxStages = 8;
 // dynamic shared memory map of conv_umma_kernel (bytes)
 static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
-static constexpr int kSmemScaleOff = 256;    // scale[128], shift[128], tail scale[128], tail shift[128] fp32
-static constexpr int kSmemTableOff = 2304;   // halo pixel table (<= 561 entries x 8 B)
-static constexpr int kSmemStagingOff = 7168; // epilogue staging tile 128 x Cf bf16
+static constexpr int kSmemOnesOff = 256;      // constant A operand [2 k-chunks][128 rows][16 B]: column 0 = 1, everything else 0
+static constexpr int kSmemTableOff = 4352;    // halo pixel table (<= 561 entries x 8 B)
+static constexpr int kSmemBiasOff = 9216;     // B operand [2][Cout][16 B] holding the per-channel shift in k = 0 (conv), 4 KB
+static constexpr int kSmemBias2Off = 13312;   // same for the fused tail, 4 KB
+static constexpr int kSmemStagingOff = 17408; // epilogue staging tile 128 x Cf bf16 (1024-byte aligned: TMA swizzle atoms)
 
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
@@ -32,12 +34,10 @@ struct alignas(64) UmmaConvParams {
     const void* in_raw;         // MODE_STEM: the image, fp32 NCHW (input_format 0) or uint8 NHWC (1)
     const __nv_bfloat16* res;   // optional residual (same shape as out)
     const __nv_bfloat16* w;     // packed [cc][tap][kc][Cout][8]
-    const float* scale;         // [Cout]
-    const float* shift;         // [Cout]
+    const float* shift;         // [Cout] fp32 or null; added on the tensor core as bf16 (BatchNorm scale is folded into w)
     // fused trailing 1x1 conv ("tail"): out = act2(scale2 * (W2 . act(scale * conv(x) + shift)) + shift2); `out`, `res`,
     // `stats` then refer to the tail's output (Cf channels) and the intermediate never leaves the SM
     const __nv_bfloat16* w2;    // packed [Cout/8][Cout2][8]
-    const float* scale2;
     const float* shift2;
     int Cout2, relu2, Cf;       // Cf = channels of the stored tensor (Cout2 with a tail, else Cout)
     uint32_t smem_w2_off, smem_a2_off, a2_bytes, n_a2;
@@ -64,7 +64,7 @@ int umma_conv_encode_maps(UmmaConvParams* p);
 
 // SIMT cross-check kernel (same packed weights, same epilogue semantics); debugging / validation only.
 cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out,
-                             const __nv_bfloat16* res, const __nv_bfloat16* w, const float* scale, const float* shift,
+                             const __nv_bfloat16* res, const __nv_bfloat16* w, const float* shift,
                              double* stats, int gn_groups, int relu, cudaStream_t st);
 
 }  // namespace lfd

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
     }
     float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = p.scale[g * 8 + j]; sh[j] = p.shift[g * 8 + j]; }
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.0f; sh[j] = p.shift ? bf16_round(p.shift[g * 8 + j]) : 0.f; }
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
         const int lp = ps * PXP + lp0;
@@ -286,8 +286,8 @@ cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
 // ===================================================================================================
 __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, const __nv_bfloat16* __restrict__ in,
                                                         __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ res,
-                                                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ scale,
-                                                        const float* __restrict__ shift, double* stats, int gn_groups, int relu) {
+                                                        const __nv_bfloat16* __restrict__ w, const float* __restrict__ shift,
+                                                        double* stats, int gn_groups, int relu) {
     const int ng = g.Cout >> 3;
     const size_t total = (size_t)g.N * g.Ho * g.Wo * ng;
     const int taps = g.ksize * g.ksize, pad = g.ksize / 2, cpc = Cc >> 3, n_cc = g.Cin / Cc;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, cons
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            o[j] = fmaf(acc[j], scale[og * 8 + j], shift[og * 8 + j]) + rf[j];
+            o[j] = acc[j] + (shift ? bf16_round(shift[og * 8 + j]) : 0.f) + rf[j];
             if (relu) o[j] = fmaxf(o[j], 0.f);
             o[j] = bf16_round(o[j]);
             s1 += o[j];
@@ -341,13 +341,13 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, cons
 }
 
 cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* res,
-                             const __nv_bfloat16* w, const float* scale, const float* shift, double* stats, int gn_groups,
+                             const __nv_bfloat16* w, const float* shift, double* stats, int gn_groups,
                              int relu, cudaStream_t st) {
     const size_t total = (size_t)g.N * g.Ho * g.Wo * (g.Cout >> 3);
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    simt_conv_kernel<<<(int)blocks, 256, 0, st>>>(g, Cc, in, out, res, w, scale, shift, stats, gn_groups, relu);
+    simt_conv_kernel<<<(int)blocks, 256, 0, st>>>(g, Cc, in, out, res, w, shift, stats, gn_groups, relu);
     return cudaGetLastError();
 }
 

@@ -88,10 +88,6 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     uint64_t* tempty2 = tfull2 + 2;   //       tail accumulator drained
     uint64_t* res_bar = tempty2 + 2;  // residual tile landed (TMA load)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
-    float* s_scale = reinterpret_cast<float*>(smem + kSmemScaleOff);
-    float* s_shift = s_scale + 128;
-    float* s_scale2 = s_shift + 128;
-    float* s_shift2 = s_scale2 + 128;
     PxEntry* table = reinterpret_cast<PxEntry*>(smem + kSmemTableOff);
     uint8_t* staging = smem + kSmemStagingOff;
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
@@ -127,15 +123,20 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
-    for (int c = tid; c < p.Cout; c += kThreads) {
-        s_scale[c] = p.scale[c];
-        s_shift[c] = p.shift[c];
+    // The per-channel shift (folded BatchNorm / bias) is added ON THE TENSOR CORE: one extra K=16 MMA per tile of a
+    // constant A operand (column 0 = 1) with a B operand whose k = 0 row holds the bf16 shift.  The epilogue is then just
+    // (+residual) ReLU + convert.
+    for (int i = tid; i < 256; i += kThreads)
+        reinterpret_cast<uint4*>(smem + kSmemOnesOff)[i] = i < 128 ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 2 * p.Cout; i += kThreads) {
+        const uint32_t b = (i < p.Cout && p.shift) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift[i])) : 0u;
+        reinterpret_cast<uint4*>(smem + kSmemBiasOff)[i] = make_uint4(b, 0u, 0u, 0u);
     }
-    if (p.Cout2)
-        for (int c = tid; c < p.Cout2; c += kThreads) {
-            s_scale2[c] = p.scale2[c];
-            s_shift2[c] = p.shift2[c];
-        }
+    for (int i = tid; i < 2 * p.Cout2; i += kThreads) {
+        const uint32_t b = (i < p.Cout2 && p.shift2) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift2[i])) : 0u;
+        reinterpret_cast<uint4*>(smem + kSmemBias2Off)[i] = make_uint4(b, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();   // these operands are read by tcgen05.mma (async proxy)
     StemEntry* stem_table = reinterpret_cast<StemEntry*>(smem + p.smem_stem_off);
     __nv_bfloat16* stem_patch = reinterpret_cast<__nv_bfloat16*>(smem + p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128);
     if (MODE == MODE_STEM) {
@@ -213,13 +214,11 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const int n_panels = wide ? (row_bytes >> 7) : 1;
         if (p.use_tma && tid == 0 && (stg & 1023u)) __trap();   // swizzle atoms need a 1024-byte aligned staging tile
 
-        // scale/shift (+ReLU) of 8 accumulator columns -> packed bf16
-        auto affine8 = [&](const float* v, const float* sc, const float* sh, int col, int relu, const uint4* resv) -> uint4 {
-            const float4 sc0 = *reinterpret_cast<const float4*>(sc + col), sc1 = *reinterpret_cast<const float4*>(sc + col + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(sh + col), sh1 = *reinterpret_cast<const float4*>(sh + col + 4);
+        // (+residual) (+ReLU) of 8 accumulator columns -> packed bf16 (scale and shift were applied by the MMAs)
+        auto finalize8 = [&](const float* v, int relu, const uint4* resv) -> uint4 {
             float o[8];
-            o[0] = fmaf(v[0], sc0.x, sh0.x); o[1] = fmaf(v[1], sc0.y, sh0.y); o[2] = fmaf(v[2], sc0.z, sh0.z); o[3] = fmaf(v[3], sc0.w, sh0.w);
-            o[4] = fmaf(v[4], sc1.x, sh1.x); o[5] = fmaf(v[5], sc1.y, sh1.y); o[6] = fmaf(v[6], sc1.z, sh1.z); o[7] = fmaf(v[7], sc1.w, sh1.w);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = v[j];
             if (resv) {
                 const uint4 rv = *resv;
                 o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
@@ -256,7 +255,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 for (int h = 0; h < 4; ++h) {
                     if (c0 + h * 8 >= ccols) break;
                     const int col = ccol0 + c0 + h * 8;
-                    *reinterpret_cast<uint4*>(dst + (col >> 3) * lbo2) = affine8(v + h * 8, s_scale, s_shift, col, p.relu, nullptr);
+                    *reinterpret_cast<uint4*>(dst + (col >> 3) * lbo2) = finalize8(v + h * 8, p.relu, nullptr);
                 }
             }
             tc_fence_before_sync();
@@ -266,8 +265,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         };
 
         // ---- final phase: accumulator -> scale/shift (+residual) (+ReLU) -> bf16 staging -> (GN statistics) -> global
-        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, const float* sc,
-                               const float* sh, int relu) {
+        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, int relu) {
             const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
             int oy0 = 0, ox0 = 0, p0 = 0;
@@ -328,7 +326,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                     if (c0 + h * 8 >= ccols) break;
                     const int col = ccol0 + c0 + h * 8;
                     uint4* slot = reinterpret_cast<uint4*>(staging + stg_off(m, col >> 3));
-                    *slot = affine8(v + h * 8, sc, sh, col, relu, p.res ? slot : nullptr);
+                    *slot = finalize8(v + h * 8, relu, p.res ? slot : nullptr);
                 }
             }
             tc_fence_before_sync();
@@ -383,14 +381,14 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         if (!p.Cout2) {
             uint32_t tcount = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount)
-                finish_tile(tile, tcount, tfull, tempty, 0, s_scale, s_shift, p.relu);
+                finish_tile(tile, tcount, tfull, tempty, 0, p.relu);
         } else {
             // software pipelined: intermediate of tile t, then the finished tail of tile t-1
             uint32_t tcount = 0;
             for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
                 const bool has = tile < p.num_tiles;
                 if (has) mid_tile(tcount);
-                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout, s_scale2, s_shift2, p.relu2);
+                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout, p.relu2);
                 if (!has) break;
             }
         }
@@ -424,6 +422,9 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         }
         // fused 1x1 tail: D2[128 x Cout2] = A2[128 x Cout] . W2, A2 written by the epilogue warps (mid_tile)
         const uint32_t idesc2 = umma_idesc_bf16(128, p.Cout2 ? p.Cout2 : 16);
+        const uint64_t ones_desc = umma_smem_desc(smem_u32(smem + kSmemOnesOff), 2048, 128);
+        const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + kSmemBiasOff), lbo_b, 128);
+        const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + kSmemBias2Off), p.Cout2 * 16, 128);
         const uint64_t a2desc0 = umma_smem_desc(0, 129 * 16, 128);
         const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), p.Cout2 * 16, 128);
         auto issue_tail = [&](uint32_t u) {
@@ -438,6 +439,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 const uint32_t d2 = tmem_base + 2 * p.Cout + a2s * p.Cout2;
                 for (int k16 = 0; k16 < (p.Cout >> 4); ++k16)
                     umma_bf16(d2, ad2 + (uint32_t)(k16 * ((2 * 129 * 16) >> 4)), b2desc0 + (uint32_t)(k16 * ((2 * p.Cout2 * 16) >> 4)), idesc2, k16 != 0);
+                if (p.shift2) umma_bf16(d2, ones_desc, bias2_desc, idesc2, 1);
                 umma_commit(&tfull2[a2s]);
                 umma_commit(&a2_empty[b]);
             }
@@ -468,7 +470,10 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                             umma_bf16(d_tmem, adk + (uint32_t)tap_view<MODE>(tap), bdk + (uint32_t)(tap * b_tap), idesc, (cc | k16 | tap) != 0);
                     }
                     umma_commit(&empty[s]);
-                    if (cc == n_cc - 1) umma_commit(&tfull[a]);
+                    if (cc == n_cc - 1) {
+                        if (p.shift) umma_bf16(d_tmem, ones_desc, bias_desc, idesc, 1);
+                        umma_commit(&tfull[a]);
+                    }
                 }
                 __syncwarp();
                 if (cc == n_cc - 1 && lane == 0) LFD_TRACE(1, tcount, 3);

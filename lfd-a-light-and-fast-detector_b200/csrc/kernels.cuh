@@ -12,8 +12,7 @@ struct Stem0Params {
     const void* in;            // fp32 NCHW (input_format 0) or u8 NHWC (1)
     __nv_bfloat16* out;        // bf16 NHWC
     const __nv_bfloat16* w;    // packed [4][Cout][8]: element (kc, n, j) = weight of output n for k = 8 kc + j, k = (kh*3 + kw)*3 + ci (k >= 27: 0)
-    const float* scale;
-    const float* shift;
+    const float* shift;        // fp32 [Cout] or null (BatchNorm scale is folded into w); applied as bf16
     int input_format, N, H, W, Ho, Wo, Cout, relu;
 };
 cudaError_t stem0_launch(const Stem0Params& p, cudaStream_t st);

@@ -8,8 +8,9 @@ Replaces the module-by-module execution of LFD.forward (reference lfd/model/lfd.
 
 Rounding points of the bf16 pipeline (mirrored by oracle/lfd_oracle.py forward(emulate_bf16=True)):
   R0  the input image is rounded to bf16 when the stem kernel loads it;
-  Rw  every conv weight is rounded to bf16 (BatchNorm scale/shift, biases, Scale stay fp32 and are applied
-      to the fp32 accumulator in the epilogue);
+  Rw  backbone / neck / tower conv weights are multiplied by the folded BatchNorm scale in fp32 and THEN rounded to bf16;
+      the folded shift (bias) is rounded to bf16 and added on the tensor core (an extra K = 16 MMA against a constant
+      operand), so the accumulator already holds conv*scale + shift; the final head convs keep fp32 bias / Scale;
   Ra  every fused layer output (after scale/shift, residual add, ReLU) is stored as bf16;
   Rg  GroupNorm statistics are taken over the stored (bf16) tensor, the normalised+ReLU'd value is rounded
       to bf16 again; the final cls / reg outputs are fp32.
@@ -35,6 +36,11 @@ def pack_conv_weight(weight, cc):
     cout, cin, k, _ = weight.shape
     wt = weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(k * k, cin // cc, cc // 8, 8, cout)
     return wt.permute(1, 0, 2, 4, 3).contiguous().to(torch.bfloat16)
+
+
+def fold_scale(weight, scale):
+    """BatchNorm folding: per-output-channel scale multiplied into the fp32 weights (they are rounded to bf16 afterwards)."""
+    return weight.detach().float().cpu() * scale.float().reshape(-1, 1, 1, 1)
 
 
 def pack_stem_weight(weight):
@@ -144,8 +150,9 @@ class InferencePlan(object):
         """tail = (conv1x1, norm, relu) fused behind a layer with cmid output channels -> op fields."""
         conv2, norm2, relu2 = tail
         scale2, shift2 = self._fold(conv2, norm2)
-        return dict(tail_cout=conv2.out_channels, tail_relu=int(relu2), tail_w=self._add_bf16(pack_conv_weight(conv2.weight, cmid)),
-                    tail_scale=self._add_f32(scale2), tail_shift=self._add_f32(shift2), tail_modules=(conv2, norm2))
+        return dict(tail_cout=conv2.out_channels, tail_relu=int(relu2),
+                    tail_w=self._add_bf16(pack_conv_weight(fold_scale(conv2.weight, scale2), cmid)),
+                    tail_shift=self._add_f32(shift2), tail_modules=(conv2, norm2))
 
     @staticmethod
     def _can_tail(conv, nxt):
@@ -159,9 +166,9 @@ class InferencePlan(object):
             raise NotImplementedError('the B200 stem kernel handles the 3x3/s2 conv on a 3-channel image only')
         ho, wo = _conv_out(h, 3, 2), _conv_out(w, 3, 2)
         scale, shift = self._fold(conv, norm)
-        wt = pack_stem_weight(conv.weight)
+        wt = pack_stem_weight(fold_scale(conv.weight, scale))
         op = dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2, relu=int(relu),
-                  w_bf16=self._add_bf16(wt), scale=self._add_f32(scale), shift=self._add_f32(shift), modules=(conv, norm))
+                  w_bf16=self._add_bf16(wt), shift=self._add_f32(shift), modules=(conv, norm))
         if tail is not None:
             op.update(self._tail_fields(tail, conv.out_channels))
         op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or conv.out_channels)
@@ -187,12 +194,12 @@ class InferencePlan(object):
                 scale, shift = torch.ones(cout), torch.zeros(cout)
             else:
                 scale, shift = self._fold(conv, norm)
-            w_off, sc_off, sh_off = self._add_bf16(pack_conv_weight(conv.weight, cc)), self._add_f32(scale), self._add_f32(shift)
+            w_off, sc_off, sh_off = self._add_bf16(pack_conv_weight(fold_scale(conv.weight, scale), cc)), None, self._add_f32(shift)
             if cache is not None:
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
                   gn_groups=gn_groups, cc=cc, inp=in_name, res=res,
-                  w_bf16=w_off, scale=sc_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
+                  w_bf16=w_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
         if tail is not None:
             op.update(self._tail_fields(tail, cout))
         op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or cout)
@@ -378,7 +385,7 @@ class InferencePlan(object):
             o.tail_cout, o.tail_relu = op.get('tail_cout', 0), op.get('tail_relu', 0)
             if op.get('tail_cout'):
                 o.tail_weight = bb + 2 * op['tail_w']
-                o.tail_scale, o.tail_shift = fb + 4 * op['tail_scale'], fb + 4 * op['tail_shift']
+                o.tail_shift = fb + 4 * op['tail_shift']
             o.in_off = offsets[op['inp']] if op.get('inp') is not None else -1
             o.out_off = offsets[op['out']] if op.get('out') is not None else -1
             o.res_off = offsets[op['res']] if op.get('res') is not None else -1

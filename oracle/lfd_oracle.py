@@ -119,8 +119,17 @@ class _Net(object):
         return y * scale[None, :, None, None] + shift[None, :, None, None]
 
     def conv_bn(self, x, ckey, nkey, stride, pad, relu, residual=None):
-        y, b = self.conv(x, ckey, stride, pad)
-        y = self.bn(y, nkey, b)
+        if self.emu:   # CUDA path: scale folded into the weights before the bf16 rounding, shift added as bf16 (rounding point Rw)
+            sd = self.sd
+            scale = sd[nkey + '.weight'] / torch.sqrt(sd[nkey + '.running_var'] + BN_EPS)
+            shift = sd[nkey + '.bias'] - sd[nkey + '.running_mean'] * scale
+            if sd.get(ckey + '.bias') is not None:
+                shift = shift + sd[ckey + '.bias'] * scale
+            y = F.conv2d(x, bf16r(sd[ckey + '.weight'] * scale[:, None, None, None]), None, stride=stride, padding=pad)
+            y = y + bf16r(shift)[None, :, None, None]
+        else:
+            y, b = self.conv(x, ckey, stride, pad)
+            y = self.bn(y, nkey, b)
         if residual is not None:
             y = y + residual
         if relu:

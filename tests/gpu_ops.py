@@ -6,7 +6,7 @@ import torch
 import torch.nn.functional as F
 
 from lfd import _native as nat
-from lfd._engine import pack_conv_weight
+from lfd._engine import pack_conv_weight, fold_scale
 
 
 def bf16r(t):
@@ -26,8 +26,8 @@ def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, 
     Ho, Wo = conv_out(H, k, stride), conv_out(W, k, stride)
     Cf = tail[0].shape[0] if tail is not None else Cout
     q = nat.conv_query(N, H, W, Cin, Ho, Wo, Cout, k, stride, Cf if tail is not None else 0)
-    wp = pack_conv_weight(weight, q['cc']).to(dev)
-    sc, sh = scale.float().to(dev).contiguous(), shift.float().to(dev).contiguous()
+    wp = pack_conv_weight(fold_scale(weight, scale), q['cc']).to(dev)   # BatchNorm scale folded before the bf16 rounding
+    sh = shift.float().to(dev).contiguous()
     in_b = x_nhwc.numel() * 2
     out_b = N * Ho * Wo * Cf * 2
     al = lambda v: (v + 255) & ~255
@@ -44,13 +44,13 @@ def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, 
     op.ksize, op.stride, op.relu, op.gn_groups, op.cc = k, stride, int(relu), gn_groups, q['cc']
     op.in_off, op.out_off, op.res_off = off_in, off_out, (off_res if res is not None else -1)
     op.stats_off = 0 if gn_groups else -1
-    op.weight, op.scale, op.shift = wp.data_ptr(), sc.data_ptr(), sh.data_ptr()
+    op.weight, op.shift = wp.data_ptr(), sh.data_ptr()
     if tail is not None:
         w2, sc2, sh2, relu2 = tail
-        w2p = pack_conv_weight(w2, Cout).to(dev)
-        sc2d, sh2d = sc2.float().to(dev).contiguous(), sh2.float().to(dev).contiguous()
+        w2p = pack_conv_weight(fold_scale(w2, sc2), Cout).to(dev)
+        sh2d = sh2.float().to(dev).contiguous()
         op.tail_cout, op.tail_relu = Cf, int(relu2)
-        op.tail_weight, op.tail_scale, op.tail_shift = w2p.data_ptr(), sc2d.data_ptr(), sh2d.data_ptr()
+        op.tail_weight, op.tail_shift = w2p.data_ptr(), sh2d.data_ptr()
     with torch.cuda.device(dev):
         nat.check(nat.lib().lfd_run_op(C.byref(op), None, 0, nat.ptr(ws), None, None, 0, 0, impl, nat.stream_ptr()))
         torch.cuda.synchronize()
@@ -60,11 +60,12 @@ def run_conv(x_nhwc, weight, scale, shift, stride, relu, res=None, gn_groups=0, 
 
 
 def ref_conv(x_nhwc, weight, scale, shift, stride, relu, res=None):
-    """fp32 CPU reference of the fused layer on the same (bf16-representable) operands; result NOT yet rounded."""
+    """fp32 CPU reference of the fused layer on the operands the kernel sees: weights = bf16(weight * scale) (BatchNorm
+    fold, rounding point Rw), shift as bf16; result NOT yet rounded."""
     x = x_nhwc.float().cpu().permute(0, 3, 1, 2)
     k = weight.shape[-1]
-    y = F.conv2d(x, weight.float().cpu(), None, stride=stride, padding=k // 2)
-    y = y * scale.float().cpu()[None, :, None, None] + shift.float().cpu()[None, :, None, None]
+    y = F.conv2d(x, bf16r(fold_scale(weight, scale)), None, stride=stride, padding=k // 2)
+    y = y + bf16r(shift.float().cpu())[None, :, None, None]
     if res is not None:
         y = y + res.float().cpu().permute(0, 3, 1, 2)
     if relu:

@@ -137,13 +137,13 @@ def test_every_layer_within_one_bf16_ulp_teacher_forced(name, monkeypatch):
             src = bf16r(x).permute(0, 2, 3, 1) if kind == nat.OP_STEM0 else plan.tensor(op['inp'])
             res = plan.tensor(op['res']) if op.get('res') is not None else None
             if not op.get('tail_cout'):
-                ref = ref_conv(src, bf16r(conv.weight.detach().cpu()), scale, shift, op['stride'], bool(op['relu']), res=res)
+                ref = ref_conv(src, conv.weight.detach().cpu(), scale, shift, op['stride'], bool(op['relu']), res=res)
                 assert_bf16_close(plan.tensor(op['out']), ref, 'conv %s' % op['out'])
             else:   # conv + fused 1x1 tail: the intermediate (bf16) only exists inside the kernel
                 conv2, norm2 = op['tail_modules']
                 scale2, shift2 = InferencePlan._fold(conv2, norm2)
-                mid = bf16r(ref_conv(src, bf16r(conv.weight.detach().cpu()), scale, shift, op['stride'], bool(op['relu'])))
-                ref = ref_conv(mid, bf16r(conv2.weight.detach().cpu()), scale2, shift2, 1, bool(op['tail_relu']), res=res)
+                mid = bf16r(ref_conv(src, conv.weight.detach().cpu(), scale, shift, op['stride'], bool(op['relu'])))
+                ref = ref_conv(mid, conv2.weight.detach().cpu(), scale2, shift2, 1, bool(op['tail_relu']), res=res)
                 got = plan.tensor(op['out']).float().cpu()
                 tol = ref.abs() * 2.0 ** -7 + 2e-3 * float(ref.abs().max())   # 1-ulp flips of the in-kernel intermediate
                 assert bool(((got - ref).abs() <= tol).all()), ('fused tail', op['out'], float((got - ref).abs().max()))

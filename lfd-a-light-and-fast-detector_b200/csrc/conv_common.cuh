@@ -14,10 +14,8 @@ static constexpr int kMaxStages = 8;
 // dynamic shared memory map of conv_umma_kernel (bytes)
 static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
 static constexpr int kSmemOnesOff = 256;      // constant A operand [2 k-chunks][128 rows][16 B]: column 0 = 1, everything else 0
-static constexpr int kSmemTableOff = 4352;    // halo pixel table (<= 561 entries x 8 B)
-static constexpr int kSmemBiasOff = 9216;     // B operand [2][Cout][16 B] holding the per-channel shift in k = 0 (conv), 4 KB
-static constexpr int kSmemBias2Off = 13312;   // same for the fused tail, 4 KB
-static constexpr int kSmemStagingOff = 17408; // epilogue staging tile 128 x Cf bf16 (1024-byte aligned: TMA swizzle atoms)
+// behind it, at offsets chosen per layer (UmmaConvParams::smem_*_off): halo pixel table (modes that need it), the bias B
+// operands [2][Cout][16 B] of the conv and of the fused tail, then the 1024-byte aligned staging tile
 
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
@@ -52,6 +50,7 @@ struct alignas(64) UmmaConvParams {
     int log2_cpc, log2_cpr, log2_rp128, tmem_cols, ctas_per_sm;
     uint32_t lbo_a, sbo_a;
     uint32_t a_stage_bytes, b_slice_bytes, stage_bytes, w_total_bytes;
+    uint32_t smem_table_off, smem_bias_off, smem_bias2_off, smem_staging_off;
     uint32_t smem_w_off, smem_ring_off, smem_stem_off;
     int input_format;
 };

@@ -88,8 +88,8 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     uint64_t* tempty2 = tfull2 + 2;   //       tail accumulator drained
     uint64_t* res_bar = tempty2 + 2;  // residual tile landed (TMA load)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
-    PxEntry* table = reinterpret_cast<PxEntry*>(smem + kSmemTableOff);
-    uint8_t* staging = smem + kSmemStagingOff;
+    PxEntry* table = reinterpret_cast<PxEntry*>(smem + p.smem_table_off);
+    uint8_t* staging = smem + p.smem_staging_off;
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
     uint8_t* ring = smem + p.smem_ring_off;     // stages: [A chunk | B slice (streaming only)]
 
@@ -130,11 +130,11 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         reinterpret_cast<uint4*>(smem + kSmemOnesOff)[i] = i < 128 ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 2 * p.Cout; i += kThreads) {
         const uint32_t b = (i < p.Cout && p.shift) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift[i])) : 0u;
-        reinterpret_cast<uint4*>(smem + kSmemBiasOff)[i] = make_uint4(b, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(smem + p.smem_bias_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     for (int i = tid; i < 2 * p.Cout2; i += kThreads) {
         const uint32_t b = (i < p.Cout2 && p.shift2) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift2[i])) : 0u;
-        reinterpret_cast<uint4*>(smem + kSmemBias2Off)[i] = make_uint4(b, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(smem + p.smem_bias2_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();   // these operands are read by tcgen05.mma (async proxy)
     StemEntry* stem_table = reinterpret_cast<StemEntry*>(smem + p.smem_stem_off);
@@ -423,8 +423,8 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         // fused 1x1 tail: D2[128 x Cout2] = A2[128 x Cout] . W2, A2 written by the epilogue warps (mid_tile)
         const uint32_t idesc2 = umma_idesc_bf16(128, p.Cout2 ? p.Cout2 : 16);
         const uint64_t ones_desc = umma_smem_desc(smem_u32(smem + kSmemOnesOff), 2048, 128);
-        const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + kSmemBiasOff), lbo_b, 128);
-        const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + kSmemBias2Off), p.Cout2 * 16, 128);
+        const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + p.smem_bias_off), lbo_b, 128);
+        const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), p.Cout2 * 16, 128);
         const uint64_t a2desc0 = umma_smem_desc(0, 129 * 16, 128);
         const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), p.Cout2 * 16, 128);
         auto issue_tail = [&](uint32_t u) {
@@ -693,7 +693,14 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
         if (epi_warps_of(mode) == 8 && g.tail_cout < 32) return -4;
     }
     const size_t staging = (size_t)128 * Cf * 2;
-    const size_t fixed = kSmemStagingOff + staging;
+    // fixed head of the shared-memory map: barriers | ones operand | [halo table] | bias | [tail bias] | staging (1 KB aligned)
+    size_t hoff = kSmemOnesOff + 4096;
+    p.smem_table_off = (uint32_t)hoff;
+    if (mode != MODE_FLAT && mode != MODE_STEM) hoff += ((size_t)p.n_px * 8 + 127) & ~(size_t)127;
+    p.smem_bias_off = (uint32_t)hoff; hoff += (size_t)g.Cout * 32;
+    p.smem_bias2_off = (uint32_t)hoff; hoff += (size_t)g.tail_cout * 32;
+    p.smem_staging_off = (uint32_t)((hoff + 1023) & ~(size_t)1023);
+    const size_t fixed = p.smem_staging_off + staging;
     // everything that lives behind the ring: MODE_STEM patch machinery, fused-tail weights + two operand buffers
     const size_t a2_bytes = g.tail_cout ? ((size_t)(g.Cout / 8) * 129 * 16 + 127) & ~(size_t)127 : 0;
     const size_t w2_bytes = g.tail_cout ? ((size_t)g.Cout * g.tail_cout * 2 + 127) & ~(size_t)127 : 0;

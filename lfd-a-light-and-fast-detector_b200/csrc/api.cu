@@ -12,6 +12,7 @@ using namespace lfd;
 
 static thread_local char g_err[512] = "";
 static long long* g_trace = nullptr;   // debugging: see lfd_debug_set_trace
+static unsigned long long* g_timeline = nullptr;   // debugging: see lfd_debug_set_timeline
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -66,6 +67,10 @@ static constexpr size_t kMaxGraphs = 32;
 
 extern "C" int lfd_debug_set_trace(void* device_buffer) {
     g_trace = reinterpret_cast<long long*>(device_buffer);
+    return LFD_OK;
+}
+extern "C" int lfd_debug_set_timeline(void* device_buffer) {
+    g_timeline = reinterpret_cast<unsigned long long*>(device_buffer);
     return LFD_OK;
 }
 extern "C" int lfd_abi_version(void) { return LFD_B200_ABI_VERSION; }
@@ -142,9 +147,10 @@ static int plan_op(const lfd_op& o, int conv_impl, PlannedOp* out) {
     return LFD_OK;
 }
 
-static int launch_op(const PlannedOp& po, const void* input, int input_format, uint8_t* ws, float* cls, float* reg, int P,
+static int launch_op(const PlannedOp& po, size_t index, const void* input, int input_format, uint8_t* ws, float* cls, float* reg, int P,
                      int cls_channels, int conv_impl, cudaStream_t st) {
     const lfd_op& o = po.op;
+    unsigned long long* tl = g_timeline ? g_timeline + 2 * index : nullptr;
     switch (o.kind) {
         case LFD_OP_STEM0: {
             if (!input) return fail(LFD_ERR_INVALID, "stem0 needs the external input pointer");
@@ -160,7 +166,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 p.in_raw = input; p.input_format = input_format; p.in = nullptr;
                 p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off); p.res = nullptr;
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.shift = o.shift; p.stats = nullptr;
-                p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace;
+                p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace; p.tl = tl;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem conv");
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
@@ -181,7 +187,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
                 p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
-                p.trace = g_trace;
+                p.trace = g_trace; p.tl = tl;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for conv %dx%d Cf=%d", o.ksize, o.ksize, p.Cf);
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
             }
@@ -191,7 +197,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
             GnApplyParams p;
             p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off); p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
             p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
-            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f;
+            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f; p.tl = tl;
             CUDA_TRY(gn_apply_launch(p, sm_count(), st));
             break;
         }
@@ -202,7 +208,7 @@ static int launch_op(const PlannedOp& po, const void* input, int input_format, u
             p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
             p.cls = o.n_cls ? cls : nullptr; p.reg = o.n_reg ? reg : nullptr;
             p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.n_out = o.n_cls + o.n_reg; p.n_cls = o.n_cls;
-            p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f;
+            p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f; p.tl = tl;
             if ((o.n_cls && !cls) || (o.n_reg && !reg)) return fail(LFD_ERR_INVALID, "head_final needs cls/reg output pointers");
             if (o.n_reg && o.n_reg != 4) return fail(LFD_ERR_INVALID, "head_final n_reg must be 0 or 4");
             CUDA_TRY(head_final_launch(p, st));
@@ -270,7 +276,7 @@ static int enqueue_all(lfd_plan* pl, const void* input, int fmt, uint8_t* ws, fl
                 started[b] = true;
             }
         }
-        rc = launch_op(pl->ops[i], input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, s);
+        rc = launch_op(pl->ops[i], i, input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, s);
     }
     for (int b = 1; b < pl->n_branches; ++b)   // join (also on error paths, so that a stream capture can be closed)
         if (started[b]) {
@@ -333,7 +339,7 @@ extern "C" int lfd_plan_profile(lfd_plan* pl, const void* input, int input_forma
     int rc = LFD_OK;
     CUDA_TRY(cudaEventRecord(ev[0], st));
     for (size_t i = 0; i < n && !rc; ++i) {
-        rc = launch_op(pl->ops[i], input, input_format, ws, cls_out, reg_out, pl->P, pl->cls_channels, pl->conv_impl, st);
+        rc = launch_op(pl->ops[i], i, input, input_format, ws, cls_out, reg_out, pl->P, pl->cls_channels, pl->conv_impl, st);
         cudaEventRecord(ev[i + 1], st);
     }
     cudaError_t ce = cudaStreamSynchronize(st);
@@ -353,7 +359,7 @@ extern "C" int lfd_run_op(const lfd_op* op, const void* input, int input_format,
     PlannedOp po;
     int rc = plan_op(*op, conv_impl, &po);
     if (rc) return rc;
-    return launch_op(po, input, input_format, reinterpret_cast<uint8_t*>(workspace), cls_out, reg_out, P, cls_channels, conv_impl,
+    return launch_op(po, 0, input, input_format, reinterpret_cast<uint8_t*>(workspace), cls_out, reg_out, P, cls_channels, conv_impl,
                      reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -13,9 +13,9 @@ enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3, MODE_STEM 
 static constexpr int kMaxStages = 8;
 // dynamic shared memory map of conv_umma_kernel (bytes)
 static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
-static constexpr int kSmemOnesOff = 256;      // constant A operand [2 k-chunks][128 rows][16 B]: column 0 = 1, everything else 0
+static constexpr int kSmemOnesOff = 512;      // constant A operand [2 k-chunks][128 rows][16 B]: column 0 = 1, everything else 0
 // behind it, at offsets chosen per layer (UmmaConvParams::smem_*_off): halo pixel table (modes that need it), the bias B
-// operands [2][Cout][16 B] of the conv and of the fused tail, then the 1024-byte aligned staging tile
+// operands [2][Cout][16 B] of the conv and of the fused tail, then the 1024-byte aligned staging regions [warp][buffer]
 
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
@@ -26,7 +26,7 @@ struct ConvGeom {
 struct alignas(64) UmmaConvParams {
     CUtensorMap tm_out;         // TMA descriptor of the stored tensor (epilogue tile store)
     CUtensorMap tm_res;         // TMA descriptor of the residual tensor (same geometry)
-    int use_tma;                // 0: element-wise cp.async / st.global epilogue (fallback, LFD_B200_NO_TMA=1)
+    int stg_nbuf;               // staging buffers per epilogue warp (2: the store of tile t overlaps the conversion of tile t+1)
     const __nv_bfloat16* in;
     __nv_bfloat16* out;
     const void* in_raw;         // MODE_STEM: the image, fp32 NCHW (input_format 0) or uint8 NHWC (1)
@@ -40,6 +40,7 @@ struct alignas(64) UmmaConvParams {
     int Cout2, relu2, Cf;       // Cf = channels of the stored tensor (Cout2 with a tail, else Cout)
     uint32_t smem_w2_off, smem_a2_off, a2_bytes, n_a2;
     double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
+    unsigned long long* tl;     // debugging: [start, end] of the launch in %globaltimer ns (LFD_B200_TRACE builds), normally null
     long long* trace;           // debugging: clock64() timeline of CTA 0 ([role 0..2][tile < 32][4]), normally null
     int N, H, W, Cin, Ho, Wo, Cout;
     int relu, gn_groups, mode;

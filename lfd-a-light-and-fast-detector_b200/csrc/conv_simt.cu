@@ -136,6 +136,7 @@ __device__ __forceinline__ void gn_mean_rstd(const double* stats, int n, int g, 
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     __shared__ float s_mean[32], s_rstd[32];
+    LFD_TL_BEGIN(p.tl);
     const int n = blockIdx.y;
     if (threadIdx.x < p.groups)
         gn_mean_rstd(p.stats, n, threadIdx.x, p.groups, (double)p.HW * 8.0, p.eps, &s_mean[threadIdx.x], &s_rstd[threadIdx.x]);
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
         o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
         out[i] = o;
     }
+    LFD_TL_END(p.tl);
 }
 
 cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st) {
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
     float* wsm = hf_smem;                                 // [n_out][C]
     float* s_mean = wsm + (size_t)p.n_out * p.C;          // [groups]
     float* s_rstd = s_mean + 32;
+    LFD_TL_BEGIN(p.tl);
     const int n = blockIdx.y;
     for (int i = threadIdx.x; i < p.n_out * p.C; i += kHfThreads) wsm[i] = p.w[i];
     if (threadIdx.x < p.groups)
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
             }
         }
     }
+    LFD_TL_END(p.tl);
 }
 
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {

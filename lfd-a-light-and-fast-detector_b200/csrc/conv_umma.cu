@@ -35,8 +35,13 @@ namespace lfd {
 
 static constexpr int kProdThreads = 128;
 
+// clock64() timeline of CTA 0 (tests/debug_trace.py); compiled in only with -DLFD_B200_TRACE (LFD_B200_TRACE=1 python build.py)
+#ifdef LFD_B200_TRACE
 #define LFD_TRACE(role, idx, slot) \
     do { if (p.trace && blockIdx.x == 0 && (idx) < 32) p.trace[((role) * 32 + (idx)) * 4 + (slot)] = clock64(); } while (0)
+#else
+#define LFD_TRACE(role, idx, slot) ((void)0)
+#endif
 
 // floor(x / d) for 0 <= x < 2^24 via one 32x32->64 multiply; m = ceil(2^40 / d), exact for d < 2^16
 LFD_DEVINL int fast_div(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
@@ -58,6 +63,89 @@ struct StemEntry {   // patch element e: where it comes from (row, offset inside
     uint16_t dst;    // element index in the patch [ci][row][col]
     uint16_t ci;
 };
+
+// pitch (bytes) between the 16-byte channel chunks of the fused tail's A operand [chunk][128 rows + 1][16 B]
+static constexpr uint32_t kA2Pitch = 129 * 16;
+
+// 8 accumulator columns (+ 8 residual values) -> packed bf16; ReLU is fused into the conversion (cvt.rn.relu)
+template <bool RELU>
+LFD_DEVINL uint4 pack8(const float* v) {
+    uint4 o;
+    if (RELU) { o.x = pack_bf16x2_relu(v[0], v[1]); o.y = pack_bf16x2_relu(v[2], v[3]); o.z = pack_bf16x2_relu(v[4], v[5]); o.w = pack_bf16x2_relu(v[6], v[7]); }
+    else { o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]); }
+    return o;
+}
+template <bool RELU>
+LFD_DEVINL uint4 pack8_res(const float* v, uint4 rv) {
+    float o[8] = {v[0] + bf16_lo(rv.x), v[1] + bf16_hi(rv.x), v[2] + bf16_lo(rv.y), v[3] + bf16_hi(rv.y),
+                  v[4] + bf16_lo(rv.z), v[5] + bf16_hi(rv.z), v[6] + bf16_lo(rv.w), v[7] + bf16_hi(rv.w)};
+    return pack8<RELU>(o);
+}
+
+// Epilogue inner loop of one warp: NC accumulator columns of its TMEM lane quarter (row = lane) -> (+residual) (+ReLU) -> bf16
+// -> shared memory, fully unrolled so that every address is `base` plus / xor a literal.
+//   OPERAND = false: staging row in TMA swizzle layout, chunk k (8 channels, 16 B) at (base ^ ((k & 7) << 4)) + (k >> 3) * 4096;
+//                    RES adds the residual chunk found at the same place (TMA-loaded before), STATS accumulates the sum and
+//                    the sum of squares of the stored values per chunk into st[k] / st[NC/8 + k] (rows with !valid count 0)
+//   OPERAND = true : K-major A operand of the fused tail, chunk k at base + k * kA2Pitch
+template <int NC, bool RELU, bool RES, bool STATS, bool OPERAND, int MAXB>
+LFD_DEVINL void drain(uint32_t taddr, uint32_t base, bool valid, float* st) {
+    constexpr int BATCH = NC < MAXB ? NC : MAXB;   // columns in flight per tcgen05.wait::ld
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += BATCH) {
+        float v[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; j += 16) tmem_ld16(taddr + c0 + j, v + j);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < BATCH / 8; ++h) {
+            const int k = (c0 >> 3) + h;
+            const uint32_t addr = OPERAND ? base + k * kA2Pitch : (base ^ (uint32_t)((k & 7) << 4)) + (uint32_t)(k >> 3) * 4096u;
+            const uint4 o = RES ? pack8_res<RELU>(v + h * 8, lds128(addr)) : pack8<RELU>(v + h * 8);
+            sts128(addr, o);
+            if (STATS) {
+                const float f[8] = {bf16_lo(o.x), bf16_hi(o.x), bf16_lo(o.y), bf16_hi(o.y), bf16_lo(o.z), bf16_hi(o.z), bf16_lo(o.w), bf16_hi(o.w)};
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+                st[k] = valid ? s1 : 0.f;
+                st[NC / 8 + k] = valid ? s2 : 0.f;
+            }
+        }
+    }
+}
+
+// Sums NV per-lane values over the 32 lanes of a warp with NV - 1 + log2(32 / NV) shuffles (transposing butterfly: every step
+// halves the number of live values).  Returns, in every lane, the total of value index (lane * NV / 32).
+template <int NV>
+LFD_DEVINL float warp_multi_reduce(float* val, int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = upper ? val[i] : val[i + n / 2];
+            const float keep = upper ? val[i + n / 2] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = val[0];
+#pragma unroll
+    for (int o = 16 / NV; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
+// GroupNorm partial statistics of one warp's NC stored channels: st = [sum per 8-channel chunk | sum of squares per chunk]
+template <int NC>
+LFD_DEVINL void stats_flush(float* st, int lane, double* dst) {   // dst: (sum, sumsq) pair of the warp's first group
+    constexpr int NV = NC / 4, PER = 32 / NV, G = NV / 2;
+    const float r = warp_multi_reduce<NV>(st, lane);
+    if ((lane & (PER - 1)) == 0) {
+        const int idx = lane / PER;
+        atomicAdd(dst + (idx & (G - 1)) * 2 + (idx >= G ? 1 : 0), (double)r);
+    }
+}
 
 template <int MODE>
 __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of tap's shifted view inside a plane
@@ -86,8 +174,8 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     uint64_t* a2_empty = a2_full + 2; //       ... consumed by the tail MMAs
     uint64_t* tfull2 = a2_empty + 2;  //       tail accumulator ready
     uint64_t* tempty2 = tfull2 + 2;   //       tail accumulator drained
-    uint64_t* res_bar = tempty2 + 2;  // residual tile landed (TMA load)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+    uint64_t* res_bar = tempty2 + 2;  // [8] residual rows of one epilogue warp landed (TMA load)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
     PxEntry* table = reinterpret_cast<PxEntry*>(smem + p.smem_table_off);
     uint8_t* staging = smem + p.smem_staging_off;
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
@@ -96,6 +184,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
     // weight fetch) while this one is still running; everything that touches upstream results waits at pdl_wait().
     pdl_launch_dependents();
+    LFD_TL_BEGIN(p.tl);
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
@@ -110,16 +199,16 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], kEpiThreads);
+            mbar_init(&tempty[i], EPI_WARPS);
         }
         mbar_init(wbar, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a2_full[i], kEpiThreads);
+            mbar_init(&a2_full[i], EPI_WARPS);
             mbar_init(&a2_empty[i], 1);
             mbar_init(&tfull2[i], 1);
-            mbar_init(&tempty2[i], kEpiThreads);
+            mbar_init(&tempty2[i], EPI_WARPS);
         }
-        mbar_init(res_bar, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == kMmaWarp) tmem_alloc(tmem_slot, p.tmem_cols);
@@ -182,217 +271,156 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
 
     if (warp < EPI_WARPS) {
         // ============================================================== EPILOGUE
+        // Every warp works on its own: TMEM lane quarter (warp % 4) x a 1/WPQ slice of the columns -> bf16 rows in its OWN
+        // staging region -> its own TMA tensor store (32 rows x cw channels).  No CTA-wide barrier is involved, and with two
+        // staging buffers the store of tile t is still being read by the TMA engine while tile t+1 is converted.
         pdl_wait();                                   // residual reads, output stores and statistics depend on upstream kernels
-        const int m = (warp & 3) * 32 + lane;        // D row == TMEM lane (a warp may only touch lane quarter warp % 4)
-        const int chalf = warp >> 2;                  // EPI_WARPS == 8: second warp of the quarter takes the upper columns
-        const int Cf = p.Cf;                          // channels of the stored tensor
-        const int cpr = Cf >> 3;                      // 16 B chunks per staged row (power of two)
-        const int l2cpr = p.log2_cpr;
-        const int row_bytes = Cf * 2;
-        const int l2rp = p.log2_rp128;                // log2(rows per 128 B): swizzle granularity for rows shorter than 128 B
-        const int swz_mask = (cpr < 8 ? cpr : 8) - 1;
+        constexpr int WPQ = EPI_WARPS / 4;
+        constexpr int MAXB = EPI_WARPS == 4 ? 32 : 64;   // the two-CTAs-per-SM kernels have 96 registers per thread
+        const int quarter = warp & 3, chalf = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;   // a warp may only touch TMEM lanes 32 * (warp % 4) ..
+        const int cw = p.Cf / WPQ;                    // stored channels handled by this warp (16, 32, 64 or 128)
+        const int cw1 = p.Cout / WPQ;                 // tail: channels of the intermediate handled by this warp
+        const int ch0 = chalf * cw;
+        // Staging rows are laid out the way the TMA engine expects for its swizzle modes: 128-byte panels
+        // [panel][32 rows][128 B] with the 16-byte chunk index XORed by (row & 7) (SWIZZLE_128B); 64 / 32-byte rows use the
+        // 64B / 32B patterns.  Row offsets are multiples of the row size, so "+" is "^" and chunk k of this lane's row is at
+        //   (pre ^ ((k & 7) << 4)) + (k >> 3) * 4096        with a per-thread constant `pre`.
+        const int row_bytes = cw >= 64 ? 128 : cw * 2;
+        const uint32_t warp_stg = 64u * cw;           // bytes of one staging buffer of this warp: 32 rows x cw x 2
+        const uint32_t stg0 = smem_u32(staging) + (uint32_t)warp * p.stg_nbuf * warp_stg;
+        const uint32_t swz = row_bytes == 128 ? (lane & 7) : (row_bytes == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        const uint32_t pre = (uint32_t)(lane * row_bytes) ^ (swz << 4);
+        const int n_panels = cw >= 64 ? (cw >> 6) : 1;
         const int HoWo = p.Ho * p.Wo;
-        const uint32_t stg = smem_u32(staging);
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        // Each thread moves the same (row, chunk) slots of the staging tile for every tile, and because the thread count is a
-        // multiple of 8 * (chunks per row) every per-slot quantity is affine in the slot index k: row_k = row_0 + k * rstep.
-        const int n_slots = (128 * cpr) / kEpiThreads;
-        const int sl_c = tid & (cpr - 1), sl_r0 = tid >> l2cpr, sl_rstep = kEpiThreads >> l2cpr;      // rstep is a multiple of 8
-        const uint32_t sl_dstg = sl_rstep * (row_bytes >= 128 ? 128 : row_bytes);   // rstep is a multiple of 8: the XOR term is k-invariant
-        const int sl_goff0 = (MODE == MODE_FLAT ? sl_r0 * Cf : ((sl_r0 >> 3) * p.Wo + (sl_r0 & 7)) * Cf) + sl_c * 8;
-        const int sl_dgoff = MODE == MODE_FLAT ? sl_rstep * Cf : (sl_rstep >> 3) * p.Wo * Cf;
-        const int sl_y0 = MODE == MODE_FLAT ? sl_r0 : (sl_r0 >> 3), sl_dy = MODE == MODE_FLAT ? sl_rstep : (sl_rstep >> 3);
-        const int sl_x = sl_r0 & 7;
-        // Staging tile layout == what the TMA engine expects for its swizzle modes: rows of >= 128 B are split into 128-byte
-        // panels [panel][row][128 B] with the 16-byte chunk index XORed by (row & 7) (SWIZZLE_128B); 64 / 32-byte rows use
-        // the 64B / 32B patterns.  The same function serves the element-wise fallback.
-        const bool wide = row_bytes >= 128;
-        auto stg_off = [&](int r, int c) -> uint32_t {
-            if (wide) return (uint32_t)((c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
-            return (uint32_t)(r * row_bytes + ((c ^ ((r >> l2rp) & swz_mask)) << 4));
-        };
-        const int n_panels = wide ? (row_bytes >> 7) : 1;
-        if (p.use_tma && tid == 0 && (stg & 1023u)) __trap();   // swizzle atoms need a 1024-byte aligned staging tile
-
-        // (+residual) (+ReLU) of 8 accumulator columns -> packed bf16 (scale and shift were applied by the MMAs)
-        auto finalize8 = [&](const float* v, int relu, const uint4* resv) -> uint4 {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[j];
-            if (resv) {
-                const uint4 rv = *resv;
-                o[0] += bf16_lo(rv.x); o[1] += bf16_hi(rv.x); o[2] += bf16_lo(rv.y); o[3] += bf16_hi(rv.y);
-                o[4] += bf16_lo(rv.z); o[5] += bf16_hi(rv.z); o[6] += bf16_lo(rv.w); o[7] += bf16_hi(rv.w);
-            }
-            uint4 ov;
-            if (relu) {
-                ov.x = pack_bf16x2_relu(o[0], o[1]); ov.y = pack_bf16x2_relu(o[2], o[3]);
-                ov.z = pack_bf16x2_relu(o[4], o[5]); ov.w = pack_bf16x2_relu(o[6], o[7]);
-            } else {
-                ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
-            }
-            return ov;
-        };
+        const bool has_res = p.res != nullptr;
+        // code variant of the conversion loop: log2(cw / 16) | relu << 2 | residual << 3, or 16 + log2(cw / 16) with statistics
+        const int l2cw = cw == 16 ? 0 : (cw == 32 ? 1 : (cw == 64 ? 2 : 3));
+        const int l2cw1 = cw1 == 16 ? 0 : (cw1 == 32 ? 1 : (cw1 == 64 ? 2 : 3));
+        const int fin_relu = p.Cout2 ? p.relu2 : p.relu;
+        const int variant = p.stats ? 16 + l2cw : (l2cw | (fin_relu ? 4 : 0) | (has_res ? 8 : 0));
+        const int variant1 = l2cw1 | (p.relu ? 4 : 0);
+        if (lane == 0 && (stg0 & 1023u)) __trap();    // swizzle atoms need 1024-byte aligned staging regions
 
         // ---- tail phase 1: main accumulator -> bf16 operand of the fused 1x1 conv (never leaves the SM)
         auto mid_tile = [&](uint32_t tc) {
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             const uint32_t b = p.n_a2 == 2 ? (tc & 1) : 0;
             const uint32_t use = p.n_a2 == 2 ? (tc >> 1) : tc;       // how often this operand buffer has been filled before
-            const int ccols = p.Cout / (EPI_WARPS / 4), ccol0 = chalf * ccols;
             mbar_wait(&tfull[a], aph);
             mbar_wait(&a2_empty[b], (use & 1) ^ 1);                   // tail MMAs of the previous user of this buffer are done
             tc_fence_after_sync();
-            const uint32_t trow = tmem_base + lane_base + a * p.Cout + ccol0;
-            uint8_t* dst = smem + p.smem_a2_off + b * p.a2_bytes + m * 16;
-            const uint32_t lbo2 = 129 * 16;
-            for (int c0 = 0; c0 < ccols; c0 += 32) {
-                float v[32];
-                tmem_ld16(trow + c0, v);
-                if (c0 + 16 < ccols) tmem_ld16(trow + c0 + 16, v + 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    if (c0 + h * 8 >= ccols) break;
-                    const int col = ccol0 + c0 + h * 8;
-                    *reinterpret_cast<uint4*>(dst + (col >> 3) * lbo2) = finalize8(v + h * 8, p.relu, nullptr);
-                }
+            const uint32_t trow = tmem_base + lane_base + a * p.Cout + chalf * cw1;
+            const uint32_t dst = smem_u32(smem + p.smem_a2_off) + b * p.a2_bytes + (uint32_t)(quarter * 32 + lane) * 16 + (uint32_t)((chalf * cw1) >> 3) * kA2Pitch;
+            switch (variant1) {
+                case 0: drain<16, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 1: drain<32, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 2: drain<64, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 3: drain<128, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 4: drain<16, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 5: drain<32, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 6: drain<64, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                default: drain<128, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
             }
             tc_fence_before_sync();
             fence_proxy_async_smem();           // st.shared (generic proxy) -> tcgen05.mma (async proxy)
-            mbar_arrive(&a2_full[b]);
-            mbar_arrive(&tempty[a]);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&a2_full[b]);
+                mbar_arrive(&tempty[a]);
+            }
         };
 
-        // ---- final phase: accumulator -> scale/shift (+residual) (+ReLU) -> bf16 staging -> (GN statistics) -> global
-        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, int relu) {
+        // ---- final phase: accumulator (+residual) (+ReLU) -> bf16 staging rows -> TMA store (+ GroupNorm statistics)
+        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base) {
             const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
-            int oy0 = 0, ox0 = 0, p0 = 0;
-            if (MODE == MODE_FLAT) p0 = t * 128;
-            else { const int ty = fast_div(t, p.magic_tx); oy0 = ty * 16; ox0 = (t - ty * p.tiles_x) * 8; }
-            const size_t img_out = (size_t)n * HoWo;
-            // pixel index (within the image) of staged row r, or -1 when outside the feature map
-            auto row_pixel = [&](int r) -> int {
-                if (MODE == MODE_FLAT) { int q = p0 + r; return q < HoWo ? q : -1; }
-                int y = oy0 + (r >> 3), x = ox0 + (r & 7);
-                return (y < p.Ho && x < p.Wo) ? y * p.Wo + x : -1;
-            };
+            int c1, c2 = 0;      // coordinates of this warp's first row: pixel index (flat) or (x, y)
+            bool valid;          // this lane's row lies inside the feature map (statistics only; the TMA store clips)
+            if (MODE == MODE_FLAT) { c1 = t * 128 + quarter * 32; valid = c1 + lane < HoWo; }
+            else {
+                const int ty = fast_div(t, p.magic_tx);
+                c2 = ty * 16 + quarter * 4; c1 = (t - ty * p.tiles_x) * 8;
+                valid = (c2 + (lane >> 3) < p.Ho) && (c1 + (lane & 7) < p.Wo);
+            }
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
-            const int ccols = Cf / (EPI_WARPS / 4), ccol0 = chalf * ccols;
-            // first element of the tile in the stored tensor, and the number of rows / columns of the tile inside the map
-            const size_t tile_org = (img_out + (MODE == MODE_FLAT ? p0 : oy0 * p.Wo + ox0)) * Cf;
-            const int lim_y = MODE == MODE_FLAT ? HoWo - p0 : p.Ho - oy0, lim_x = p.Wo - ox0;
-            const bool col_ok = MODE == MODE_FLAT ? true : sl_x < lim_x;
-            const uint32_t sl_stg0 = stg_off(sl_r0, sl_c);
-            if (p.res) {  // residual tile -> staging, consumed row-wise below
-                if (p.use_tma) {
-                    if (tid == 0) {   // one TMA box per 128-byte panel; out-of-map rows / columns arrive as zeros
-                        mbar_arrive_expect_tx(res_bar, 128 * row_bytes);
-                        for (int pn = 0; pn < n_panels; ++pn) {
-                            if (MODE == MODE_FLAT) tma_load_3d(stg + pn * 16384, &p.tm_res, pn * 64, p0, n, res_bar);
-                            else tma_load_4d(stg + pn * 16384, &p.tm_res, pn * 64, ox0, oy0, n, res_bar);
-                        }
+            const uint32_t sbuf = stg0 + (p.stg_nbuf == 2 ? (tc & 1) * warp_stg : 0u);
+            if (lane == 0) {
+                // this staging buffer was the source of an earlier store: the TMA engine must be done reading it
+                if (p.stg_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                if (has_res) {   // residual rows -> staging (out-of-map rows / columns arrive as zeros), added in place below
+                    mbar_arrive_expect_tx(&res_bar[warp], warp_stg);
+                    for (int pn = 0; pn < n_panels; ++pn) {
+                        if (MODE == MODE_FLAT) tma_load_3d(sbuf + pn * 4096, &p.tm_res, ch0 + pn * 64, c1, n, &res_bar[warp]);
+                        else tma_load_4d(sbuf + pn * 4096, &p.tm_res, ch0 + pn * 64, c1, c2, n, &res_bar[warp]);
                     }
-                } else {
-#pragma unroll 4
-                    for (int k = 0; k < n_slots; ++k) {
-                        const bool ok = col_ok && (sl_y0 + k * sl_dy) < lim_y;
-                        cp_async16(stg + sl_stg0 + k * sl_dstg, p.res + (ok ? tile_org + sl_goff0 + k * sl_dgoff : 0), ok);
-                    }
-                    cp_async_commit();
                 }
             }
             if (tid == 0) LFD_TRACE(2, tc, 0);
             mbar_wait(&bar_full[a], aph);
             tc_fence_after_sync();
             if (tid == 0) LFD_TRACE(2, tc, 1);
-            if (p.res) {
-                if (p.use_tma) mbar_wait(res_bar, tc & 1);
-                else {
-                    cp_async_wait<0>();
-                    named_bar_sync(1, kEpiThreads);
+            if (has_res) mbar_wait(&res_bar[warp], tc & 1);
+            else __syncwarp();                    // lane 0 has seen the buffer free
+            const uint32_t trow = tmem_base + lane_base + col_base + a * p.Cf + ch0;
+            const uint32_t base = sbuf + pre;
+            auto publish = [&]() {
+                tc_fence_before_sync();
+                fence_proxy_async_smem();             // st.shared (generic proxy) -> TMA store (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&bar_empty[a]);       // accumulator stage may be overwritten by the next-but-one tile
+                    for (int pn = 0; pn < n_panels; ++pn) {   // rows / columns outside the map are clipped by the TMA engine
+                        if (MODE == MODE_FLAT) tma_store_3d(&p.tm_out, sbuf + pn * 4096, ch0 + pn * 64, c1, n);
+                        else tma_store_4d(&p.tm_out, sbuf + pn * 4096, ch0 + pn * 64, c1, c2, n);
+                    }
+                    bulk_commit();
                 }
+            };
+            // GroupNorm partial sums are taken over the STORED (bf16) values; one group = one 16-byte chunk (8 channels)
+            double* sdst = p.stats ? p.stats + ((size_t)n * p.gn_groups + (ch0 >> 3)) * 2 : nullptr;
+            switch (variant) {
+                case 0: drain<16, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 1: drain<32, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 2: drain<64, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 3: drain<128, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 4: drain<16, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 5: drain<32, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 6: drain<64, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 7: drain<128, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 8: drain<16, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 9: drain<32, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 10: drain<64, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 11: drain<128, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 12: drain<16, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 13: drain<32, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 14: drain<64, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 15: drain<128, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
+                case 16: { float st[4]; drain<16, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<16>(st, lane, sdst); } break;
+                case 17: { float st[8]; drain<32, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<32>(st, lane, sdst); } break;
+                case 18: { float st[16]; drain<64, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<64>(st, lane, sdst); } break;
+                default: { float st[32]; drain<128, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<128>(st, lane, sdst); } break;
             }
-            if (tid == 0) LFD_TRACE(3, tc, 0);
-            const uint32_t trow = tmem_base + lane_base + col_base + a * Cf + ccol0;
-            for (int c0 = 0; c0 < ccols; c0 += 32) {
-                float v[32];
-                tmem_ld16(trow + c0, v);
-                if (c0 + 16 < ccols) tmem_ld16(trow + c0 + 16, v + 16);
-                tmem_ld_wait();
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    if (c0 + h * 8 >= ccols) break;
-                    const int col = ccol0 + c0 + h * 8;
-                    uint4* slot = reinterpret_cast<uint4*>(staging + stg_off(m, col >> 3));
-                    *slot = finalize8(v + h * 8, relu, p.res ? slot : nullptr);
-                }
-            }
-            tc_fence_before_sync();
-            mbar_arrive(&bar_empty[a]);  // accumulator stage may be overwritten by the next-but-one tile
+            if (variant < 16) publish();
             if (tid == 0) LFD_TRACE(2, tc, 2);
-            if (p.use_tma) fence_proxy_async_smem();   // st.shared (generic proxy) -> TMA store (async proxy)
-            named_bar_sync(1, kEpiThreads);
-            if (tid == 0) LFD_TRACE(3, tc, 1);
-            if (p.use_tma && tid == 0) {   // the whole tile leaves through the TMA engine; rows / columns outside the map are clipped
-                for (int pn = 0; pn < n_panels; ++pn) {
-                    if (MODE == MODE_FLAT) tma_store_3d(&p.tm_out, stg + pn * 16384, pn * 64, p0, n);
-                    else tma_store_4d(&p.tm_out, stg + pn * 16384, pn * 64, ox0, oy0, n);
-                }
-                bulk_commit();
-            }
-            if (p.stats) {  // GroupNorm partial sums over the STORED (bf16) values; group = one 16 B chunk (16 groups)
-                constexpr int TPG = kEpiThreads / 16;  // threads per group
-                const int g = tid / TPG, sl = tid % TPG;
-                float s1 = 0.f, s2 = 0.f;
-                for (int r = sl; r < 128; r += TPG) {
-                    if (row_pixel(r) < 0) continue;
-                    uint4 q = *reinterpret_cast<const uint4*>(staging + stg_off(r, g));
-                    float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
-                                  bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
-                }
-#pragma unroll
-                for (int o = 1; o < TPG; o <<= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                }
-                if (sl == 0) {
-                    double* dst = p.stats + ((size_t)n * p.gn_groups + g) * 2;
-                    atomicAdd(dst, (double)s1);
-                    atomicAdd(dst + 1, (double)s2);
-                }
-            }
-            if (!p.use_tma) {
-#pragma unroll 4
-                for (int k = 0; k < n_slots; ++k)   // coalesced store
-                    if (col_ok && (sl_y0 + k * sl_dy) < lim_y)
-                        *reinterpret_cast<uint4*>(p.out + tile_org + sl_goff0 + k * sl_dgoff) = *reinterpret_cast<const uint4*>(staging + sl_stg0 + k * sl_dstg);
-            } else if (tid == 0) {
-                bulk_wait_read_all();        // the TMA engine has finished reading the staging tile
-            }
-            if (tid == 0) LFD_TRACE(3, tc, 2);
-            named_bar_sync(1, kEpiThreads);  // staging free again
             if (tid == 0) LFD_TRACE(2, tc, 3);
         };
 
         if (!p.Cout2) {
             uint32_t tcount = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount)
-                finish_tile(tile, tcount, tfull, tempty, 0, p.relu);
+                finish_tile(tile, tcount, tfull, tempty, 0);
         } else {
             // software pipelined: intermediate of tile t, then the finished tail of tile t-1
             uint32_t tcount = 0;
             for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
                 const bool has = tile < p.num_tiles;
                 if (has) mid_tile(tcount);
-                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout, p.relu2);
+                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout);
                 if (!has) break;
             }
         }
-        if (p.use_tma && tid == 0) bulk_wait_all();   // all tile stores have been performed before the CTA retires
+        if (lane == 0) bulk_wait_all();   // all tile stores have been performed before the CTA retires
     } else if (warp == kMmaWarp) {
         // ============================================================== MMA ISSUER
         // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
@@ -425,7 +453,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const uint64_t ones_desc = umma_smem_desc(smem_u32(smem + kSmemOnesOff), 2048, 128);
         const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + p.smem_bias_off), lbo_b, 128);
         const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), p.Cout2 * 16, 128);
-        const uint64_t a2desc0 = umma_smem_desc(0, 129 * 16, 128);
+        const uint64_t a2desc0 = umma_smem_desc(0, kA2Pitch, 128);
         const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), p.Cout2 * 16, 128);
         auto issue_tail = [&](uint32_t u) {
             const uint32_t b = p.n_a2 == 2 ? (u & 1) : 0, use = p.n_a2 == 2 ? (u >> 1) : u;
@@ -438,7 +466,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 const uint64_t ad2 = a2desc0 + ((smem_u32(smem + p.smem_a2_off) + b * p.a2_bytes) >> 4);
                 const uint32_t d2 = tmem_base + 2 * p.Cout + a2s * p.Cout2;
                 for (int k16 = 0; k16 < (p.Cout >> 4); ++k16)
-                    umma_bf16(d2, ad2 + (uint32_t)(k16 * ((2 * 129 * 16) >> 4)), b2desc0 + (uint32_t)(k16 * ((2 * p.Cout2 * 16) >> 4)), idesc2, k16 != 0);
+                    umma_bf16(d2, ad2 + (uint32_t)(k16 * ((2 * kA2Pitch) >> 4)), b2desc0 + (uint32_t)(k16 * ((2 * p.Cout2 * 16) >> 4)), idesc2, k16 != 0);
                 if (p.shift2) umma_bf16(d2, ones_desc, bias2_desc, idesc2, 1);
                 umma_commit(&tfull2[a2s]);
                 umma_commit(&a2_empty[b]);
@@ -645,6 +673,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, p.tmem_cols);
     }
+    LFD_TL_END(p.tl);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -652,9 +681,10 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
 // ---------------------------------------------------------------------------------------------------
 static int epi_warps_of(int mode) { return (mode == MODE_3X3S1 || mode == MODE_3X3S2) ? 8 : 4; }
 
-int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid) {
+static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvParams* out, size_t* smem_bytes, int* grid) {
     UmmaConvParams p;
     memset(&p, 0, sizeof(p));
+    p.stg_nbuf = nbuf;
     int mode;
     if (g.stem) {
         if (g.ksize != 3 || g.stride != 2 || g.Cin != 32) return -1;   // Cin = 27 taps*channels padded to 32
@@ -692,7 +722,7 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
         if (g.tail_cout % 16 || g.tail_cout > 128 || g.tail_cout < 16 || 2 * (g.Cout + g.tail_cout) > 512) return -4;
         if (epi_warps_of(mode) == 8 && g.tail_cout < 32) return -4;
     }
-    const size_t staging = (size_t)128 * Cf * 2;
+    const size_t staging = (size_t)nbuf * 128 * Cf * 2;   // [epilogue warp][buffer][32 rows][Cf / (warps per quarter)]
     // fixed head of the shared-memory map: barriers | ones operand | [halo table] | bias | [tail bias] | staging (1 KB aligned)
     size_t hoff = kSmemOnesOff + 4096;
     p.smem_table_off = (uint32_t)hoff;
@@ -791,6 +821,22 @@ int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, siz
     return 0;
 }
 
+int umma_conv_configure(const ConvGeom& g, int num_sms, UmmaConvParams* out, size_t* smem_bytes, int* grid) {
+    // a second staging buffer per epilogue warp is taken when it costs neither occupancy, weight residency nor ring depth
+    UmmaConvParams p1, p2;
+    size_t s1 = 0, s2 = 0;
+    int g1 = 0, g2 = 0;
+    const int rc = configure_with(g, num_sms, 1, &p1, &s1, &g1);
+    if (rc) return rc;
+    if (configure_with(g, num_sms, 2, &p2, &s2, &g2) == 0 && p2.ctas_per_sm == p1.ctas_per_sm && p2.b_resident == p1.b_resident &&
+        p2.Cc == p1.Cc && p2.stages >= (p1.stages < 3 ? p1.stages : 3)) {
+        *out = p2; *smem_bytes = s2; *grid = g2;
+    } else {
+        *out = p1; *smem_bytes = s1; *grid = g1;
+    }
+    return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -807,11 +853,14 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// One tensor map per stored tensor; the box is what ONE epilogue warp moves: 32 tile rows (32 pixels of a flat tile, 8 x 4 of
+// a spatial one) x min(64, its channel slice) channels, shared-memory side in the matching swizzle mode.
 static int encode_one(const UmmaConvParams& p, const void* ptr, CUtensorMap* tm) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return -1;
     const cuuint64_t Cf = p.Cf, HoWo = (cuuint64_t)p.Ho * p.Wo;
-    const cuuint32_t inner = p.Cf < 64 ? p.Cf : 64;
+    const int cw = p.Cf / (epi_warps_of(p.mode) / 4);
+    const cuuint32_t inner = cw < 64 ? cw : 64;
     const CUtensorMapSwizzle swz = inner * 2 >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (inner * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     cuuint64_t dims[4], strides[3];
     cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
@@ -820,12 +869,12 @@ static int encode_one(const UmmaConvParams& p, const void* ptr, CUtensorMap* tm)
         rank = 3;
         dims[0] = Cf; dims[1] = HoWo; dims[2] = p.N;
         strides[0] = Cf * 2; strides[1] = HoWo * Cf * 2;
-        box[0] = inner; box[1] = 128; box[2] = 1;
+        box[0] = inner; box[1] = 32; box[2] = 1;
     } else {
         rank = 4;
         dims[0] = Cf; dims[1] = p.Wo; dims[2] = p.Ho; dims[3] = p.N;
         strides[0] = Cf * 2; strides[1] = (cuuint64_t)p.Wo * Cf * 2; strides[2] = HoWo * Cf * 2;
-        box[0] = inner; box[1] = 8; box[2] = 16; box[3] = 1;
+        box[0] = inner; box[1] = 8; box[2] = 4; box[3] = 1;
     }
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -833,12 +882,8 @@ static int encode_one(const UmmaConvParams& p, const void* ptr, CUtensorMap* tm)
 }
 
 int umma_conv_encode_maps(UmmaConvParams* p) {
-    static const bool disabled = getenv("LFD_B200_NO_TMA") != nullptr;
-    p->use_tma = 0;
-    if (disabled) return 0;
     if (encode_one(*p, p->out, &p->tm_out)) return -1;
     if (p->res && encode_one(*p, p->res, &p->tm_res)) return -1;
-    p->use_tma = 1;
     return 0;
 }
 

@@ -25,6 +25,7 @@ struct GnApplyParams {
     const float* beta;
     int N, HW, C, groups;
     float eps;
+    unsigned long long* tl;    // debugging time-line slot or null
 };
 cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st);
 
@@ -40,6 +41,7 @@ struct HeadFinalParams {
     float* reg;                // (N, P, 4) or null
     int N, HW, C, groups, n_out, n_cls, P, point_off, cls_stride;
     float eps;
+    unsigned long long* tl;    // debugging time-line slot or null
 };
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st);
 

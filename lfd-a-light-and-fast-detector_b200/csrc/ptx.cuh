@@ -126,6 +126,9 @@ LFD_DEVINL void tma_load_4d(uint32_t dst_smem, const void* tmap, int c0, int c1,
 LFD_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 LFD_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 LFD_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+LFD_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- tcgen05: TMEM alloc
 // cols: power of two in [32, 512]
@@ -189,6 +192,20 @@ LFD_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
 LFD_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- misc
+// Kernel time-line for tests/debug_trace.py (only with -DLFD_B200_TRACE): tl[0] = earliest CTA start, tl[1] = latest CTA end,
+// in %globaltimer nanoseconds; works inside CUDA-graph replays where events cannot be placed.
+#ifdef LFD_B200_TRACE
+LFD_DEVINL unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define LFD_TL_BEGIN(tl) do { if ((tl) && threadIdx.x == 0) atomicMin((tl), globaltimer_ns()); } while (0)
+#define LFD_TL_END(tl) do { if ((tl) && threadIdx.x == 0) atomicMax((tl) + 1, globaltimer_ns()); } while (0)
+#else
+#define LFD_TL_BEGIN(tl) ((void)0)
+#define LFD_TL_END(tl) ((void)0)
+#endif
 LFD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -198,6 +215,14 @@ LFD_DEVINL uint32_t pack_bf16x2_relu(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+LFD_DEVINL void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+LFD_DEVINL uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 LFD_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 LFD_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }

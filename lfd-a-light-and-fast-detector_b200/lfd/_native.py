@@ -68,6 +68,7 @@ SYMBOLS = {
     'lfd_plan_forward': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),
     'lfd_plan_profile': (_i, [_vp, _vp, _i, _vp, _vp, _vp, C.POINTER(C.c_float), _vp]),
     'lfd_debug_set_trace': (_i, [_vp]),
+    'lfd_debug_set_timeline': (_i, [_vp]),
     'lfd_run_op': (_i, [C.POINTER(Op), _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'lfd_postprocess_workspace_bytes': (C.c_size_t, [C.POINTER(PostCfg)]),
     'lfd_postprocess': (_i, [C.POINTER(PostCfg)] + [_vp] * 11),

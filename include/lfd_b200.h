@@ -115,7 +115,7 @@ int lfd_plan_profile(lfd_plan* plan, const void* input, int input_format, void* 
 /* Debugging aid: device buffer long long[4][32][4] that CTA 0 of every following tcgen05 conv launch fills with a
  * clock64() timeline (role 0 producer / 1 MMA issuer / 2 epilogue, per tile); NULL switches it off. */
 int lfd_debug_set_trace(void* device_buffer);
-/* Debugging aid (LFD_B200_TRACE builds): device buffer unsigned long long[2 * lfd_plan_num_launches()], pre-set by the caller
+/* Debugging aid (LFD_B200_TIMELINE builds): device buffer unsigned long long[2 * lfd_plan_num_launches()], pre-set by the caller
  * to {UINT64_MAX, 0} pairs; op i of every following plan launch (CUDA-graph replays included, when set before the capture)
  * records its earliest CTA start and latest CTA end in %globaltimer nanoseconds.  NULL switches it off. */
 int lfd_debug_set_timeline(void* device_buffer);

@@ -3,8 +3,8 @@
 
     python build.py [--force] [--verbose]
 
-LFD_B200_TRACE=1 compiles the clock64() timeline hooks of the convolution kernel in (tests/debug_trace.py); they are absent
-from the normal build.
+LFD_B200_TRACE=1 compiles the clock64() per-role hooks of the convolution kernel in (tests/debug_trace.py) and
+LFD_B200_TIMELINE=1 the per-launch %globaltimer stamps (tests/debug_timeline.py); both are absent from the normal build.
 """
 import os
 import subprocess
@@ -17,7 +17,8 @@ SOURCES = ['api.cu', 'conv_umma.cu', 'conv_simt.cu', 'postprocess.cu', 'losses.c
 HEADERS = ['ptx.cuh', 'conv_common.cuh', 'kernels.cuh', os.path.join('..', '..', 'include', 'lfd_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
-         '--expt-relaxed-constexpr'] + (['-DLFD_B200_TRACE'] if os.environ.get('LFD_B200_TRACE') else [])
+         '--expt-relaxed-constexpr'] + (['-DLFD_B200_TRACE'] if os.environ.get('LFD_B200_TRACE') else []) + \
+        (['-DLFD_B200_TIMELINE'] if os.environ.get('LFD_B200_TIMELINE') else [])
 
 
 def _stale():

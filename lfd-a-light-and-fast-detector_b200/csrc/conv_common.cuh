@@ -40,7 +40,7 @@ struct alignas(64) UmmaConvParams {
     int Cout2, relu2, Cf;       // Cf = channels of the stored tensor (Cout2 with a tail, else Cout)
     uint32_t smem_w2_off, smem_a2_off, a2_bytes, n_a2;
     double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
-    unsigned long long* tl;     // debugging: [start, end] of the launch in %globaltimer ns (LFD_B200_TRACE builds), normally null
+    unsigned long long* tl;     // debugging: [start, end] of the launch in %globaltimer ns (LFD_B200_TIMELINE builds), normally null
     long long* trace;           // debugging: clock64() timeline of CTA 0 ([role 0..2][tile < 32][4]), normally null
     int N, H, W, Cin, Ho, Wo, Cout;
     int relu, gn_groups, mode;

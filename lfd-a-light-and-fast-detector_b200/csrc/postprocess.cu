@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(256) candidates_kernel(const PostParams p) {
 //              raw mode), count
 static constexpr int kNmsThreads = 1024;
 static constexpr int kNmsSmemSort = 4096;   // candidates sortable / sweepable entirely in shared memory
+static constexpr int kNmsMaskMax = 1024;    // candidates for which the K x K suppression bit matrix fits in shared memory
+static constexpr size_t kNmsMaskOff = 32768;   // smem offset of the bit matrix (behind the 1024-entry sort arrays, 29 KB)
 
 __device__ __forceinline__ float iou_ref(const float4 a, const float aa, const float4 b, const float ab) {
     const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y), xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
@@ -128,14 +130,16 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
     int Kp = 1;
     while (Kp < K) Kp <<= 1;
     const bool in_smem = Kp <= kNmsSmemSort;
+    const bool use_mask = Kp <= kNmsMaskMax;          // the common case: bit-matrix sweep (step 4a)
+    const size_t L = use_mask ? kNmsMaskMax : kNmsSmemSort;   // entries the shared-memory arrays are laid out for
     uint8_t* gscr = p.scratch + (size_t)n * p.scratch_stride;
     unsigned long long* keys = in_smem ? reinterpret_cast<unsigned long long*>(nsm)
                                        : reinterpret_cast<unsigned long long*>(gscr);
-    uint32_t* pay = in_smem ? reinterpret_cast<uint32_t*>(nsm + (size_t)kNmsSmemSort * 8)
+    uint32_t* pay = in_smem ? reinterpret_cast<uint32_t*>(nsm + L * 8)
                             : reinterpret_cast<uint32_t*>(gscr + (size_t)p.cap_pow2 * 8);
-    float4* sbox = in_smem ? reinterpret_cast<float4*>(nsm + (size_t)kNmsSmemSort * 12)
+    float4* sbox = in_smem ? reinterpret_cast<float4*>(nsm + L * 12)
                            : reinterpret_cast<float4*>(gscr + (size_t)p.cap_pow2 * 12);
-    uint8_t* removed = in_smem ? nsm + (size_t)kNmsSmemSort * 28 : gscr + (size_t)p.cap_pow2 * 12 + (size_t)p.cap * 16;
+    uint8_t* removed = in_smem ? nsm + L * 28 : gscr + (size_t)p.cap_pow2 * 12 + (size_t)p.cap * 16;
     const float4* cbox = reinterpret_cast<const float4*>(p.cand_box) + (size_t)n * p.cap;
     const float* cscore = p.cand_score + (size_t)n * p.cap;
     const int* csrc = p.cand_src + (size_t)n * p.cap;
@@ -191,7 +195,65 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
     if (tid == 0) s_keep = 0;
     __syncthreads();
 
-    // 4. greedy sweep (whole CTA in lock step; `removed` is only written between barriers)
+    // 4a. K <= 1024: all pairwise decisions first (mask[i] bit j = "i suppresses j", j > i; fully parallel), then ONE warp walks
+    //     the rows in score order OR-ing the masks of the kept boxes into a 1024-bit register bitmap (one word per lane).
+    //     Same decisions as the sweep below (a box is dropped iff an earlier KEPT box overlaps it by more than iou_thr).
+    if (use_mask) {
+        uint32_t* mask = reinterpret_cast<uint32_t*>(nsm + kNmsMaskOff);   // [K][32 words]
+        int* keep_list = reinterpret_cast<int*>(keys);                    // the sort keys are dead by now
+        const int nw = (K + 31) >> 5;
+        for (int idx = tid; idx < K * nw; idx += kNmsThreads) {
+            const int i = idx / nw, w = idx - i * nw;
+            uint32_t bits = 0;
+            if (w >= (i >> 5)) {
+                const float4 bi = sbox[i];
+                const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                const int j0 = w << 5;
+                for (int b = 0; b < 32; ++b) {
+                    const int j = j0 + b;
+                    if (j > i && j < K) {
+                        const float4 bj = sbox[j];
+                        const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                        if (iou_ref(bi, ai, bj, aj) > p.iou_thr) bits |= 1u << b;
+                    }
+                }
+            }
+            mask[i * 32 + w] = bits;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t rem = 0;     // lane l: boxes 32 l .. 32 l + 31
+            int nkeep = 0;
+            for (int i = 0; i < K; ++i) {
+                const uint32_t wv = __shfl_sync(0xffffffffu, rem, i >> 5);
+                if ((wv >> (i & 31)) & 1u) continue;   // uniform
+                if (tid == 0) keep_list[nkeep] = i;
+                ++nkeep;
+                if (tid < nw) rem |= mask[i * 32 + tid];
+            }
+            if (tid == 0) s_keep = nkeep;
+        }
+        __syncthreads();
+        const int nkeep = s_keep;
+        for (int k = tid; k < nkeep; k += kNmsThreads) {
+            const int i = keep_list[k];
+            const int s = (int)pay[i];
+            const int src = csrc[s];
+            float4 ob = sbox[i];
+            if (!p.class_agnostic) {  // nms.py:155 subtracts the offsets again (fp32 round trip kept)
+                const float off = __fmul_rn((float)(src % p.C), offmul);
+                ob.x = __fsub_rn(ob.x, off); ob.y = __fsub_rn(ob.y, off); ob.z = __fsub_rn(ob.z, off); ob.w = __fsub_rn(ob.w, off);
+            }
+            float* d = p.out_dets + ((size_t)n * p.cap + k) * 5;
+            d[0] = ob.x; d[1] = ob.y; d[2] = ob.z; d[3] = ob.w; d[4] = cscore[s];
+            p.out_label[(size_t)n * p.cap + k] = src % p.C;
+            p.out_src[(size_t)n * p.cap + k] = src;
+        }
+        if (tid == 0) p.out_count[n] = nkeep;
+        return;
+    }
+
+    // 4b. greedy sweep (whole CTA in lock step; `removed` is only written between barriers)
     for (int i = 0; i < K; ++i) {
         if (removed[i]) continue;  // uniform
         const float4 bi = sbox[i];
@@ -232,7 +294,7 @@ size_t nms_scratch_stride(int cap, int cap_pow2) {
 }
 
 cudaError_t nms_launch(const NmsParams& p, int n_images, cudaStream_t st) {
-    const size_t smem = (size_t)kNmsSmemSort * 29 + 16;
+    const size_t smem = kNmsMaskOff + (size_t)kNmsMaskMax * 128;   // 160 KB (>= the 4096-entry sweep layout, 116 KB)
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -192,9 +192,9 @@ LFD_DEVINL void tmem_ld16(uint32_t taddr, float* v) {
 LFD_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- misc
-// Kernel time-line for tests/debug_trace.py (only with -DLFD_B200_TRACE): tl[0] = earliest CTA start, tl[1] = latest CTA end,
+// Kernel time-line for tests/debug_timeline.py (only with -DLFD_B200_TIMELINE): tl[0] = earliest CTA start, tl[1] = latest CTA end,
 // in %globaltimer nanoseconds; works inside CUDA-graph replays where events cannot be placed.
-#ifdef LFD_B200_TRACE
+#ifdef LFD_B200_TIMELINE
 LFD_DEVINL unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -46,11 +46,11 @@ static constexpr int kProdThreads = 128;
 // floor(x / d) for 0 <= x < 2^24 via one 32x32->64 multiply; m = ceil(2^40 / d), exact for d < 2^16
 LFD_DEVINL int fast_div(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
 
-struct PxEntry {  // one halo pixel: where it comes from (relative to the tile's input origin) and where it goes
-    int16_t dy, dx;
-    uint16_t slot;
-    uint16_t pad;
+struct PxEntry {  // one halo pixel: where it comes from and where it goes
+    uint32_t src_off;  // byte offset of the pixel relative to the halo's top-left pixel (tile origin + (dy_min, dx_min))
+    uint32_t dst_off;  // byte offset of its 16-byte slot inside a plane
 };
+struct PxDelta { int8_t dy, dx; };  // the same pixel relative to the tile's input origin, for tiles that touch the border
 
 // MODE_STEM: the raw-image patch of one 16x8 output tile: 33 rows x 17 pixels x 3 channels, kept in shared memory as
 // bf16 [ci][row][col] (already normalised / rounded), double buffered.
@@ -177,6 +177,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     uint64_t* res_bar = tempty2 + 2;  // [8] residual rows of one epilogue warp landed (TMA load)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
     PxEntry* table = reinterpret_cast<PxEntry*>(smem + p.smem_table_off);
+    PxDelta* delta = reinterpret_cast<PxDelta*>(smem + p.smem_table_off + (size_t)p.n_px * sizeof(PxEntry));
     uint8_t* staging = smem + p.smem_staging_off;
     uint8_t* wres = smem + p.smem_w_off;        // resident weights (if any)
     uint8_t* ring = smem + p.smem_ring_off;     // stages: [A chunk | B slice (streaming only)]
@@ -242,23 +243,29 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     // halo pixel table (tile independent)
     if (MODE != MODE_FLAT && MODE != MODE_STEM) {
         for (int i = tid; i < p.n_px; i += kThreads) {
-            PxEntry e;
-            e.pad = 0;
+            int dy, dx, slot;
             if (MODE == MODE_3X3S1) {
                 int r = i / 10, c = i % 10;
-                e.dy = (int16_t)(r - 1); e.dx = (int16_t)(c - 1); e.slot = (uint16_t)i;
+                dy = r - 1; dx = c - 1; slot = i;
             } else if (MODE == MODE_1X1S2) {
                 int r = i >> 3, c = i & 7;
-                e.dy = (int16_t)(2 * r); e.dx = (int16_t)(2 * c); e.slot = (uint16_t)i;
+                dy = 2 * r; dx = 2 * c; slot = i;
             } else {  // MODE_3X3S2: EE(16x8) | EO(16x9) | OE(17x8) | OO(17x9); all planes use pitch 9
                 int j = i, r, c, base, rodd, codd;
                 if (j < 128) { r = j >> 3; c = j & 7; base = 0; rodd = 0; codd = 0; }
                 else if ((j -= 128) < 144) { r = j / 9; c = j % 9; base = 144; rodd = 0; codd = 1; }
                 else if ((j -= 144) < 136) { r = j >> 3; c = j & 7; base = 288; rodd = 1; codd = 0; }
                 else { j -= 136; r = j / 9; c = j % 9; base = 441; rodd = 1; codd = 1; }
-                e.dy = (int16_t)(2 * r - rodd); e.dx = (int16_t)(2 * c - codd); e.slot = (uint16_t)(base + r * 9 + c);
+                dy = 2 * r - rodd; dx = 2 * c - codd; slot = base + r * 9 + c;
             }
+            constexpr int kMin = (MODE == MODE_1X1S2) ? 0 : -1;   // smallest dy / dx of the mode
+            PxEntry e;
+            e.src_off = (uint32_t)(((dy - kMin) * p.W + (dx - kMin)) * p.Cin * 2);
+            e.dst_off = (uint32_t)slot * 16u;
             table[i] = e;
+            PxDelta d;
+            d.dy = (int8_t)dy; d.dx = (int8_t)dx;
+            delta[i] = d;
         }
     }
     tc_fence_before_sync();
@@ -615,6 +622,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const int px0 = ptid >> p.log2_cpc;
         const int pstep = kProdThreads >> p.log2_cpc;
         const uint32_t ch_dst = ch * p.lbo_a;
+        const int my_cnt = (p.n_px - px0 + pstep - 1) / pstep;   // halo pixels this thread copies per stage
         uint32_t it = 0;
         pdl_wait();                                   // the input activations are produced by the previous kernel
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -629,6 +637,15 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 ix0 = (MODE == MODE_3X3S1) ? ox0 : 2 * ox0;
             }
             const __nv_bfloat16* img = p.in + (size_t)n * HW * p.Cin + ch * 8;
+            // tiles whose halo lies inside the image (the vast majority) copy without bounds checks: source = tile origin +
+            // a per-pixel offset from the table
+            constexpr int kDyMin = (MODE == MODE_1X1S2) ? 0 : -1, kDxMin = kDyMin;
+            constexpr int kDyMax = (MODE == MODE_3X3S1) ? 16 : ((MODE == MODE_3X3S2) ? 31 : 30);
+            constexpr int kDxMax = (MODE == MODE_3X3S1) ? 8 : ((MODE == MODE_3X3S2) ? 15 : 14);
+            const bool interior = MODE == MODE_FLAT ? (ix0 + 128 <= HW)
+                                                    : (iy0 + kDyMin >= 0 && ix0 + kDxMin >= 0 && iy0 + kDyMax < p.H && ix0 + kDxMax < p.W);
+            // flat: first pixel of the tile; otherwise the halo's top-left pixel (in range for interior tiles)
+            const __nv_bfloat16* org = img + (ptrdiff_t)(MODE == MODE_FLAT ? ix0 : (iy0 + kDyMin) * p.W + ix0 + kDxMin) * p.Cin;
             for (int cc = 0; cc < n_cc; ++cc, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
                 if (ptid == 0) LFD_TRACE(0, it, 0);
@@ -643,19 +660,35 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 const __nv_bfloat16* src_cc = img + cc * p.Cc;
                 const uint32_t dst_cc = a_base + ch_dst;
                 if (MODE == MODE_FLAT) {
+                    if (interior) {
+                        const __nv_bfloat16* src = org + cc * p.Cc + (size_t)px0 * p.Cin;
+                        const size_t sstep = (size_t)pstep * p.Cin;
+                        uint32_t dst = dst_cc + px0 * 16;
 #pragma unroll 4
-                    for (int pxi = px0; pxi < 128; pxi += pstep) {
-                        const int q = ix0 + pxi;
-                        const bool ok = q < HW;
-                        cp_async16(dst_cc + pxi * 16, src_cc + (ok ? q : 0) * p.Cin, ok);
+                        for (int pxi = px0; pxi < 128; pxi += pstep, src += sstep, dst += pstep * 16) cp_async16_full(dst, src);
+                    } else {
+#pragma unroll 4
+                        for (int pxi = px0; pxi < 128; pxi += pstep) {
+                            const int q = ix0 + pxi;
+                            const bool ok = q < HW;
+                            cp_async16(dst_cc + pxi * 16, src_cc + (ok ? q : 0) * p.Cin, ok);
+                        }
+                    }
+                } else if (interior) {
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(org + cc * p.Cc);
+                    const PxEntry* tp = table + px0;
+#pragma unroll 4
+                    for (int k = 0; k < my_cnt; ++k, tp += pstep) {
+                        const uint2 pe = *reinterpret_cast<const uint2*>(tp);
+                        cp_async16_full(dst_cc + pe.y, src + pe.x);
                     }
                 } else {
-#pragma unroll 4
+#pragma unroll 2
                     for (int pxi = px0; pxi < p.n_px; pxi += pstep) {
-                        const PxEntry pe = table[pxi];
-                        const int y = iy0 + pe.dy, x = ix0 + pe.dx;
+                        const PxDelta pd = delta[pxi];
+                        const int y = iy0 + pd.dy, x = ix0 + pd.dx;
                         const bool ok = ((unsigned)y < (unsigned)p.H) && ((unsigned)x < (unsigned)p.W);
-                        cp_async16(dst_cc + pe.slot * 16, src_cc + (ok ? (y * p.W + x) : 0) * p.Cin, ok);
+                        cp_async16(dst_cc + table[pxi].dst_off, src_cc + (ok ? (y * p.W + x) : 0) * p.Cin, ok);
                     }
                 }
                 cp_async_mbar_arrive(&full[s]);   // arrives when this thread's copies have landed
@@ -726,7 +759,7 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     // fixed head of the shared-memory map: barriers | ones operand | [halo table] | bias | [tail bias] | staging (1 KB aligned)
     size_t hoff = kSmemOnesOff + 4096;
     p.smem_table_off = (uint32_t)hoff;
-    if (mode != MODE_FLAT && mode != MODE_STEM) hoff += ((size_t)p.n_px * 8 + 127) & ~(size_t)127;
+    if (mode != MODE_FLAT && mode != MODE_STEM) hoff += ((size_t)p.n_px * 10 + 127) & ~(size_t)127;   // PxEntry[n_px] | PxDelta[n_px]
     p.smem_bias_off = (uint32_t)hoff; hoff += (size_t)g.Cout * 32;
     p.smem_bias2_off = (uint32_t)hoff; hoff += (size_t)g.tail_cout * 32;
     p.smem_staging_off = (uint32_t)((hoff + 1023) & ~(size_t)1023);

@@ -72,6 +72,9 @@ LFD_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
     uint32_t sz = valid ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
+LFD_DEVINL void cp_async16_full(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 LFD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 LFD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // The mbarrier receives one arrival (counted against its expected-arrival count, hence .noinc) once ALL cp.async

@@ -77,8 +77,11 @@ typedef struct lfd_op {
     int32_t N, H, W, Cin, Ho, Wo, Cout;
     int32_t ksize, stride, relu, gn_groups;
     int32_t n_cls, n_reg, point_off, cc;
-    int32_t branch, reserved; /* branch 0 = main stream; ops of branch b > 0 run on side stream b, forked after the
-                                 main-stream op that precedes the branch's first op and joined at the end */
+    int32_t branch, wait_mask; /* branch 0 = main stream; ops of branch b > 0 run on side stream b, forked after the
+                                 main-stream op that precedes the branch's first op and joined at the end.  wait_mask:
+                                 bit w set = this op additionally waits for everything enqueued so far on branch w
+                                 (mid-graph joins, e.g. a residual block's last conv waiting for its side-branch
+                                 downsample conv, or a side-branch op waiting for a later main-stream tensor) */
     int64_t in_off, out_off, res_off, stats_off; /* bytes; -1 = unused */
     const void* weight;
     const float* scale; /* HEAD_FINAL: per-output scale; STEM0 / CONV: must be NULL (fold it into the weights) */

@@ -61,6 +61,7 @@ struct lfd_plan {
     // side streams for independent branches (the per-level neck + head chains)
     cudaStream_t side[LFD_MAX_BRANCHES];
     cudaEvent_t fork_ev[LFD_MAX_BRANCHES], join_ev[LFD_MAX_BRANCHES];
+    std::vector<cudaEvent_t> dep_ev;   // one per (op, wait_mask bit): mid-graph cross-branch dependencies
     int n_branches;
 };
 static constexpr size_t kMaxGraphs = 32;
@@ -86,7 +87,7 @@ static ConvGeom geom_of(const lfd_op& o) {
     g.N = o.N; g.H = o.H; g.W = o.W; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.ksize = o.ksize; g.stride = o.stride;
     g.stem = o.kind == LFD_OP_STEM0 ? 1 : 0;
     g.tail_cout = o.tail_cout;
-    if (g.stem) g.Cin = 32;   // 27 (kh, kw, ci) taps padded to 32
+    if (g.stem) g.Cin = 16;   // K of one filter row: 4 pixels x 4 (padded) channels
     return g;
 }
 
@@ -232,8 +233,11 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
         if (rc) { delete pl; return rc; }
         if (ops[i].branch < 0 || ops[i].branch >= LFD_MAX_BRANCHES) { delete pl; return fail(LFD_ERR_INVALID, "op %d: branch %d out of range", i, ops[i].branch); }
         if (ops[i].branch + 1 > pl->n_branches) pl->n_branches = ops[i].branch + 1;
+        if (ops[i].wait_mask < 0 || ops[i].wait_mask >= (1 << LFD_MAX_BRANCHES)) { delete pl; return fail(LFD_ERR_INVALID, "op %d: wait_mask 0x%x out of range", i, ops[i].wait_mask); }
         pl->ops.push_back(po);
     }
+    size_t n_dep = 0;
+    for (auto& po : pl->ops) n_dep += (size_t)__builtin_popcount((unsigned)po.op.wait_mask);
     for (int b = 1; b < pl->n_branches; ++b) {
         if (cudaStreamCreateWithFlags(&pl->side[b], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&pl->fork_ev[b], cudaEventDisableTiming) != cudaSuccess ||
@@ -242,6 +246,14 @@ extern "C" int lfd_plan_create(const lfd_op* ops, int n_ops, int N, int P, int c
             lfd_plan_destroy(pl);
             return fail(LFD_ERR_CUDA, "lfd_plan_create: cannot create side streams");
         }
+    }
+    for (size_t i = 0; i < n_dep; ++i) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            lfd_plan_destroy(pl);
+            return fail(LFD_ERR_CUDA, "lfd_plan_create: cannot create dependency events");
+        }
+        pl->dep_ev.push_back(ev);
     }
     *out = pl;
     return LFD_OK;
@@ -255,6 +267,7 @@ extern "C" int lfd_plan_destroy(lfd_plan* plan) {
         cudaEventDestroy(plan->fork_ev[b]);
         cudaEventDestroy(plan->join_ev[b]);
     }
+    for (auto ev : plan->dep_ev) cudaEventDestroy(ev);
     delete plan;
     return LFD_OK;
 }
@@ -265,6 +278,7 @@ static int enqueue_all(lfd_plan* pl, const void* input, int fmt, uint8_t* ws, fl
     if (pl->stats_bytes > 0) CUDA_TRY(cudaMemsetAsync(ws + pl->stats_off, 0, (size_t)pl->stats_bytes, st));
     bool started[LFD_MAX_BRANCHES] = {false};
     int rc = LFD_OK;
+    size_t dep = 0;
     for (size_t i = 0; i < pl->ops.size() && !rc; ++i) {
         const int b = pl->ops[i].op.branch;
         cudaStream_t s = st;
@@ -275,6 +289,13 @@ static int enqueue_all(lfd_plan* pl, const void* input, int fmt, uint8_t* ws, fl
                 CUDA_TRY(cudaStreamWaitEvent(s, pl->fork_ev[b], 0));
                 started[b] = true;
             }
+        }
+        for (int w = 0; w < LFD_MAX_BRANCHES; ++w) {   // explicit cross-branch dependencies
+            if (!((pl->ops[i].op.wait_mask >> w) & 1)) continue;
+            cudaEvent_t ev = pl->dep_ev[dep++];
+            if (w == b || (w > 0 && (w >= pl->n_branches || !started[w]))) continue;   // nothing to wait for
+            CUDA_TRY(cudaEventRecord(ev, w == 0 ? st : pl->side[w]));
+            CUDA_TRY(cudaStreamWaitEvent(s, ev, 0));
         }
         rc = launch_op(pl->ops[i], i, input, fmt, ws, cls, reg, pl->P, pl->cls_channels, pl->conv_impl, s);
     }

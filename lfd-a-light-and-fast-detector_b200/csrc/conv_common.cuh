@@ -52,7 +52,7 @@ struct alignas(64) UmmaConvParams {
     uint32_t lbo_a, sbo_a;
     uint32_t a_stage_bytes, b_slice_bytes, stage_bytes, w_total_bytes;
     uint32_t smem_table_off, smem_bias_off, smem_bias2_off, smem_staging_off;
-    uint32_t smem_w_off, smem_ring_off, smem_stem_off;
+    uint32_t smem_w_off, smem_ring_off;
     int input_format;
 };
 

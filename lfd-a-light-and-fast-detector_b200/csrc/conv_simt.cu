@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
     const int Cout = NG * 8;
     for (int i = tid; i < 27 * Cout; i += kS0Threads) {
         const int k = i / Cout, nn = i % Cout;
-        wsm[i] = __bfloat162float(p.w[((k >> 3) * Cout + nn) * 8 + (k & 7)]);
+        const int kh = k / 9, kw = (k / 3) % 3, ci = k % 3;   // packed [kh][kw / 2][Cout][(kw % 2) * 4 + ci]
+        wsm[i] = __bfloat162float(p.w[(((kh * 2 + (kw >> 1)) * Cout + nn) * 8) + (kw & 1) * 4 + ci]);
     }
     // input patch -> smem, rounded to bf16 (rounding point R0 of DESIGN.md)
     for (int i = tid; i < 3 * kS0PatchH * kS0PatchW; i += kS0Threads) {

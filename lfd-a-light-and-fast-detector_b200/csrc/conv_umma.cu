@@ -52,17 +52,19 @@ struct PxEntry {  // one halo pixel: where it comes from and where it goes
 };
 struct PxDelta { int8_t dy, dx; };  // the same pixel relative to the tile's input origin, for tiles that touch the border
 
-// MODE_STEM: the raw-image patch of one 16x8 output tile: 33 rows x 17 pixels x 3 channels, kept in shared memory as
-// bf16 [ci][row][col] (already normalised / rounded), double buffered.
-static constexpr int kStemRows = 33, kStemCols = 17, kStemElems = 3 * kStemRows * kStemCols;   // 1683
-static constexpr int kStemPerThread = (kStemElems + kProdThreads - 1) / kProdThreads;          // 14
-static constexpr int kStemPatchBytes = ((kStemElems * 2 + 127) / 128) * 128;                   // 3456
-struct StemEntry {   // patch element e: where it comes from (row, offset inside the row) and where it goes
-    int16_t row;     // input row relative to the tile's first input row
-    int16_t off;     // u8 NHWC: byte offset inside the row (pixel*3 + ci); fp32 NCHW: pixel offset
-    uint16_t dst;    // element index in the patch [ci][row][col]
-    uint16_t ci;
-};
+// MODE_STEM: the im2col of the 3-channel stem conv is done by the UMMA address generator.  The producers write the raw-image
+// patch of one 16x8 output tile (33 rows x 18 pixels) to shared memory as bf16 with the channels padded to 4
+// ([row][pixel][b g r 0] = 8 B per pixel, already normalised / rounded = rounding point R0).  Output pixel (oy, ox) and filter row
+// kh need the 3 input pixels 2ox-1 .. 2ox+1 of input row 2oy+kh-1 = 12 of the 16 consecutive bf16 values that start at patch
+// pixel (2oy + kh, 2ox); consecutive ox are 16 B apart, consecutive oy 2 patch rows.  That is exactly a K-major SWIZZLE_NONE A
+// operand with K = 16: core-matrix rows 16 B apart, SBO = 2 rows, LBO (second K chunk) = 16 B (the chunks of neighbouring rows
+// overlap, which a read-only view may).  So the conv is 3 MMAs (one per kh, K = 16) per tile against weights packed
+// [kh][2][Cout][8] with zeros in the 4th pixel / 4th channel positions; the 18th patch column only meets zero weights but
+// must hold finite values.
+static constexpr int kStemRows = 33, kStemCols = 18, kStemPix = kStemRows * kStemCols;          // 594
+static constexpr int kStemRowBytes = kStemCols * 8;                                             // 144
+static constexpr int kStemPerThread = (kStemPix + kProdThreads - 1) / kProdThreads;             // 5
+static constexpr int kStemPatchBytes = ((kStemRows * kStemRowBytes + 127) / 128) * 128;         // 4864
 
 // pitch (bytes) between the 16-byte channel chunks of the fused tail's A operand [chunk][128 rows + 1][16 B]
 static constexpr uint32_t kA2Pitch = 129 * 16;
@@ -154,6 +156,7 @@ __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of
         const int kh = tap / 3, kw = tap % 3;
         return (kh == 1 ? 0 : 288) + (kw == 1 ? 0 : (kh == 1 ? 144 : 153)) + (kh == 2 ? 9 : 0) + (kw == 2 ? 1 : 0);
     }
+    if (MODE == MODE_STEM) return tap * (kStemRowBytes / 16);   // "tap" = filter row kh: one patch row further down
     return 0;
 }
 
@@ -163,7 +166,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     constexpr int kEpiThreads = EPI_WARPS * 32;
     constexpr int kMmaWarp = EPI_WARPS;
     constexpr int kThreads = kEpiThreads + 32 + kProdThreads;
-    constexpr int TAPS = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : 1;
+    constexpr int TAPS = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : (MODE == MODE_STEM ? 3 : 1);
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
     uint64_t* empty = full + kMaxStages;
@@ -227,19 +230,6 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         reinterpret_cast<uint4*>(smem + p.smem_bias2_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();   // these operands are read by tcgen05.mma (async proxy)
-    StemEntry* stem_table = reinterpret_cast<StemEntry*>(smem + p.smem_stem_off);
-    __nv_bfloat16* stem_patch = reinterpret_cast<__nv_bfloat16*>(smem + p.smem_stem_off + ((kStemElems * 8 + 127) / 128) * 128);
-    if (MODE == MODE_STEM) {
-        for (int e = tid; e < kStemElems; e += kThreads) {
-            StemEntry t;
-            int ci, r, c;
-            if (p.input_format == 1) { r = e / (kStemCols * 3); const int b = e % (kStemCols * 3); c = b / 3; ci = b % 3; t.off = (int16_t)b; }
-            else { ci = e / (kStemRows * kStemCols); const int q = e % (kStemRows * kStemCols); r = q / kStemCols; c = q % kStemCols; t.off = (int16_t)c; }
-            t.row = (int16_t)r; t.ci = (uint16_t)ci;
-            t.dst = (uint16_t)((ci * kStemRows + r) * kStemCols + c);
-            stem_table[e] = t;
-        }
-    }
     // halo pixel table (tile independent)
     if (MODE != MODE_FLAT && MODE != MODE_STEM) {
         for (int i = tid; i < p.n_px; i += kThreads) {
@@ -520,101 +510,86 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         // ============================================================== PRODUCERS
         const int ptid = tid - (kEpiThreads + 32);
         if (MODE == MODE_STEM) {
-            // im2col of the raw image: K = 27 (kh, kw, ci) padded to 32.  The patch of tile t+1 is fetched into registers
-            // while the operand of tile t is assembled from the shared-memory patch of tile t.
-            const int my = ptid >> 3, mx = ptid & 7;            // this thread's output pixel inside the 16x8 tile
-            // raw values of the NEXT tile's patch elements.  Element descriptors are tile invariant and live in registers;
-            // loads are unconditional (clamped addresses) so that all of them are in flight together, out-of-image elements
-            // are masked when the patch is written.  Tiles whose patch lies inside the image skip the clamping.
-            uint32_t raw[kStemPerThread];
-            uint32_t okmask = 0;
-            int e_off[kStemPerThread];        // element offset of (row, byte/pixel, channel) relative to the patch origin
-            uint16_t e_dst[kStemPerThread];
-            const int row_pitch = p.input_format == 1 ? p.W * 3 : p.W;
+            // Raw image patch -> normalised bf16 [row][pixel][b g r 0] in the ring stage (see kStem* above).  Every thread owns
+            // up to 5 patch pixels; the raw values of the NEXT tile are fetched into registers right after the current patch
+            // has been written, so the loads fly while the thread waits for the next free stage.
+            const bool u8 = p.input_format == 1;
+            const int plane = p.H * p.W;
+            int rel[kStemPerThread];          // source offset of pixel j relative to the patch origin (bytes for u8, elements for fp32)
+            int prc[kStemPerThread];          // (row << 8) | col
 #pragma unroll
             for (int j = 0; j < kStemPerThread; ++j) {
-                const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];
-                e_dst[j] = se.dst;
-                e_off[j] = se.row * row_pitch + se.off + (p.input_format == 1 ? 0 : (int)se.ci * p.H * p.W);
+                const int q = min(ptid + j * kProdThreads, kStemPix - 1);
+                const int r = q / kStemCols, c = q - r * kStemCols;
+                prc[j] = (r << 8) | c;
+                rel[j] = u8 ? (r * p.W + c) * 3 : r * p.W + c;
             }
-            const int last_cnt = kStemElems - (kStemPerThread - 1) * kProdThreads;   // threads that own an element in the last round
+            const bool last_ok = ptid + (kStemPerThread - 1) * kProdThreads < kStemPix;   // this thread owns a pixel in the last round
+            uint32_t raw[kStemPerThread][3];
+            uint32_t okmask = 0;
             auto fetch = [&](int tile) {
                 const int n = fast_div(tile, p.magic_tpi), t = tile - n * p.tiles_per_img;
                 const int ty = fast_div(t, p.magic_tx);
                 const int iy0 = 2 * ty * 16 - 1, ix0 = 2 * (t - ty * p.tiles_x) * 8 - 1;
                 const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + kStemRows <= p.H && ix0 + kStemCols <= p.W;
-                if (p.input_format == 1) {
-                    const uint8_t* org = reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + iy0) * row_pitch + ix0 * 3;
-                    if (interior) {
-                        okmask = 0xffffffffu;
+                okmask = 0;
+                if (u8) {
+                    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.in_raw) + (size_t)n * plane * 3;
+                    const uint8_t* org = img + ((ptrdiff_t)iy0 * p.W + ix0) * 3;
 #pragma unroll
-                        for (int j = 0; j < kStemPerThread; ++j) raw[j] = __ldg(org + e_off[j]);
-                    } else {
-                        okmask = 0;
-#pragma unroll
-                        for (int j = 0; j < kStemPerThread; ++j) {
-                            const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];   // border tiles only
-                            const int y = iy0 + se.row, b = ix0 * 3 + se.off;
-                            const int yc = min(max(y, 0), p.H - 1), bc = min(max(b, 0), row_pitch - 1);
-                            if (y == yc && b == bc) okmask |= 1u << j;
-                            raw[j] = __ldg(reinterpret_cast<const uint8_t*>(p.in_raw) + ((size_t)n * p.H + yc) * row_pitch + bc);
+                    for (int j = 0; j < kStemPerThread; ++j) {
+                        if (j == kStemPerThread - 1 && !last_ok) break;
+                        const uint8_t* src = org + rel[j];
+                        bool ok = true;
+                        if (!interior) {
+                            const int y = iy0 + (prc[j] >> 8), x = ix0 + (prc[j] & 255);
+                            ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+                            if (!ok) src = img;
                         }
+                        okmask |= (ok ? 1u : 0u) << j;
+                        raw[j][0] = __ldg(src); raw[j][1] = __ldg(src + 1); raw[j][2] = __ldg(src + 2);
                     }
                 } else {
-                    const float* org = reinterpret_cast<const float*>(p.in_raw) + ((size_t)n * 3 * p.H + iy0) * p.W + ix0;
-                    if (interior) {
-                        okmask = 0xffffffffu;
+                    const float* img = reinterpret_cast<const float*>(p.in_raw) + (size_t)n * plane * 3;
+                    const float* org = img + (ptrdiff_t)iy0 * p.W + ix0;
 #pragma unroll
-                        for (int j = 0; j < kStemPerThread; ++j) raw[j] = __float_as_uint(__ldg(org + e_off[j]));
-                    } else {
-                        okmask = 0;
-#pragma unroll
-                        for (int j = 0; j < kStemPerThread; ++j) {
-                            const StemEntry se = stem_table[min(ptid + j * kProdThreads, kStemElems - 1)];
-                            const int y = iy0 + se.row, x = ix0 + se.off;
-                            const int yc = min(max(y, 0), p.H - 1), xc = min(max(x, 0), p.W - 1);
-                            if (y == yc && x == xc) okmask |= 1u << j;
-                            raw[j] = __float_as_uint(__ldg(org + e_off[j] + (yc - y) * p.W + (xc - x)));
+                    for (int j = 0; j < kStemPerThread; ++j) {
+                        if (j == kStemPerThread - 1 && !last_ok) break;
+                        const float* src = org + rel[j];
+                        bool ok = true;
+                        if (!interior) {
+                            const int y = iy0 + (prc[j] >> 8), x = ix0 + (prc[j] & 255);
+                            ok = (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W;
+                            if (!ok) src = img;
                         }
+                        okmask |= (ok ? 1u : 0u) << j;
+                        raw[j][0] = __float_as_uint(__ldg(src)); raw[j][1] = __float_as_uint(__ldg(src + plane));
+                        raw[j][2] = __float_as_uint(__ldg(src + 2 * plane));
                     }
                 }
             };
             uint32_t it = 0;
-            int buf = 0;
             pdl_wait();
             if ((int)blockIdx.x < p.num_tiles) fetch(blockIdx.x);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, buf ^= 1) {
-                __nv_bfloat16* patch = stem_patch + buf * (kStemPatchBytes / 2);
-#pragma unroll
-                for (int j = 0; j < kStemPerThread; ++j) {
-                    if (j < kStemPerThread - 1 || ptid < last_cnt) {
-                        float v = p.input_format == 1 ? ((float)raw[j] - 127.5f) * (1.0f / 127.5f) : __uint_as_float(raw[j]);
-                        if (!((okmask >> j) & 1u)) v = 0.f;
-                        patch[e_dst[j]] = __float2bfloat16_rn(v);   // rounding point R0
-                    }
-                }
-                named_bar_sync(2, kProdThreads);
-                if (tile + (int)gridDim.x < p.num_tiles) fetch(tile + gridDim.x);
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t s = it % SA, ph = (it / SA) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                const uint32_t a_base = smem_u32(ring) + s * p.stage_bytes;
-                const unsigned short* pp = reinterpret_cast<const unsigned short*>(patch) + (2 * my) * kStemCols + 2 * mx;
-                uint32_t w[16];
+                const uint32_t dst0 = smem_u32(ring) + s * p.stage_bytes + ptid * 8;
 #pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    uint32_t lo = 0, hi = 0;
-                    const int k0 = 2 * k2, k1 = 2 * k2 + 1;
-                    if (k0 < 27) lo = pp[((k0 % 3) * kStemRows + (k0 / 9)) * kStemCols + ((k0 / 3) % 3)];
-                    if (k1 < 27) hi = pp[((k1 % 3) * kStemRows + (k1 / 9)) * kStemCols + ((k1 / 3) % 3)];
-                    w[k2] = lo | (hi << 16);
-                }
+                for (int j = 0; j < kStemPerThread; ++j) {
+                    if (j == kStemPerThread - 1 && !last_ok) break;
+                    float f[3];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t dst = a_base + c * p.lbo_a + ptid * 16;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+                    for (int k = 0; k < 3; ++k) {
+                        f[k] = u8 ? ((float)raw[j][k] - 127.5f) * (1.0f / 127.5f) : __uint_as_float(raw[j][k]);
+                        if (!((okmask >> j) & 1u)) f[k] = 0.f;        // conv zero padding (of the normalised image)
+                    }
+                    const uint32_t lo = pack_bf16x2(f[0], f[1]), hi = pack_bf16x2(f[2], 0.f);   // rounding point R0
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst0 + j * (kProdThreads * 8)), "r"(lo), "r"(hi) : "memory");
                 }
                 fence_proxy_async_smem();       // generic-proxy st.shared -> tcgen05.mma reads
                 mbar_arrive(&full[s]);
+                if (tile + (int)gridDim.x < p.num_tiles) fetch(tile + gridDim.x);
             }
         } else {
         // every thread owns ONE 16-byte channel chunk (cpc divides 128) and walks the halo pixels with a fixed stride
@@ -720,7 +695,7 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     p.stg_nbuf = nbuf;
     int mode;
     if (g.stem) {
-        if (g.ksize != 3 || g.stride != 2 || g.Cin != 32) return -1;   // Cin = 27 taps*channels padded to 32
+        if (g.ksize != 3 || g.stride != 2 || g.Cin != 16) return -1;   // "Cin" = K of one filter row: 4 pixels x 4 padded channels
         mode = MODE_STEM;
     } else if (g.ksize == 1 && g.stride == 1) mode = MODE_FLAT;
     else if (g.ksize == 3 && g.stride == 1) mode = MODE_3X3S1;
@@ -731,7 +706,7 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     if (epi_warps_of(mode) == 8 && g.Cout < 32) return -1;   // two epilogue warps per lane quarter need >= 16 columns each
     p.mode = mode;
     p.N = g.N; p.H = g.H; p.W = g.W; p.Cin = g.Cin; p.Ho = g.Ho; p.Wo = g.Wo; p.Cout = g.Cout;
-    const int taps = g.stem ? 1 : g.ksize * g.ksize;
+    const int taps = g.stem ? 3 : g.ksize * g.ksize;   // stem: one MMA group per filter row
     int px_slots;  // plane size in pixels (slots), n_px = pixels actually loaded
     if (mode == MODE_FLAT) {
         p.tiles_x = 0; p.tiles_per_img = (g.Ho * g.Wo + 127) / 128;
@@ -741,11 +716,12 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
         p.tiles_per_img = p.tiles_x * ((g.Ho + 15) / 16);
         if (mode == MODE_3X3S1) { p.n_px = 180; px_slots = 180; p.sbo_a = 160; }
         else if (mode == MODE_3X3S2) { p.n_px = 561; px_slots = 594; p.sbo_a = 144; }
-        else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }   // MODE_1X1S2 and MODE_STEM: one 16x8 plane
+        else { p.n_px = 128; px_slots = 128; p.sbo_a = 128; }   // MODE_1X1S2 (and, overridden below, MODE_STEM)
     }
     // plane pitch = odd multiple of 16 B: the 8 chunks of a pixel fall into 8 distinct 16-byte bank groups
     const int plane_slots = px_slots | 1;
     p.lbo_a = plane_slots * 16;
+    if (mode == MODE_STEM) { p.lbo_a = 16; p.sbo_a = 2 * kStemRowBytes; }   // overlapping view of the 4-channel patch
     p.num_tiles = p.tiles_per_img * g.N;
     if (p.num_tiles >= (1 << 24) || p.tiles_per_img >= (1 << 16)) return -5;
     p.magic_tpi = ((1ull << 40) + p.tiles_per_img - 1) / p.tiles_per_img;
@@ -764,11 +740,10 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     p.smem_bias2_off = (uint32_t)hoff; hoff += (size_t)g.tail_cout * 32;
     p.smem_staging_off = (uint32_t)((hoff + 1023) & ~(size_t)1023);
     const size_t fixed = p.smem_staging_off + staging;
-    // everything that lives behind the ring: MODE_STEM patch machinery, fused-tail weights + two operand buffers
+    // everything that lives behind the ring: fused-tail weights + two operand buffers
     const size_t a2_bytes = g.tail_cout ? ((size_t)(g.Cout / 8) * 129 * 16 + 127) & ~(size_t)127 : 0;
     const size_t w2_bytes = g.tail_cout ? ((size_t)g.Cout * g.tail_cout * 2 + 127) & ~(size_t)127 : 0;
-    const size_t stem_bytes = mode == MODE_STEM ? (size_t)((kStemElems * 8 + 127) / 128) * 128 + 2 * kStemPatchBytes : 0;
-    const size_t post = stem_bytes + w2_bytes + 2 * a2_bytes;
+    const size_t post = w2_bytes + 2 * a2_bytes;
     const size_t budget = 224 * 1024 - post;
     const size_t w_total = (size_t)taps * g.Cin * g.Cout * 2;
     // Choose the channel chunk Cc, weight residency and ring depth.  Preference order:
@@ -778,7 +753,10 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     // Memory-bound 1x1 layers additionally cap the ring so that two CTAs fit on one SM (latency hiding).
     const int cands[3] = {64, 32, 16};
     int best_cc = 0, best_res = 0, best_st = 0;
-    auto a_bytes = [&](int cc) -> size_t { return (((size_t)plane_slots * (cc / 8) * 16) + 127) & ~(size_t)127; };
+    auto a_bytes = [&](int cc) -> size_t {
+        if (mode == MODE_STEM) return kStemPatchBytes;
+        return (((size_t)plane_slots * (cc / 8) * 16) + 127) & ~(size_t)127;
+    };
     auto stages_for = [&](int cc, int resident) -> int {
         if (g.Cin % cc) return 0;
         const size_t b_slice = (size_t)taps * cc * g.Cout * 2;
@@ -798,7 +776,10 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
             int st = stages_for(cands[ci], 1);
             if (st >= want) { best_cc = cands[ci]; best_res = 1; best_st = st; }
         }
-    if (!best_cc || best_st < 3) {
+    // Streaming re-reads the whole filter bank from L2 for every tile, so it is taken only when the weights cannot be
+    // resident next to a ring of >= 2 stages of >= 32 channels (measured on the 3x3/s2 64->64 + tail layer at 180x320:
+    // resident / 32 / 2 stages beats streamed / 16 / 4 stages).
+    if (!best_cc || (best_st < 3 && best_cc < 32)) {
         for (int want = 4; want >= 2; --want) {
             bool found = false;
             for (int ci = 0; ci < 3 && !found; ++ci) {
@@ -840,7 +821,6 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
         p.tmem_cols = cols;
     }
     size_t off = p.smem_ring_off + (size_t)p.stages * p.stage_bytes;
-    if (mode == MODE_STEM) { p.smem_stem_off = (uint32_t)off; off += stem_bytes; }
     if (g.tail_cout) {
         p.smem_w2_off = (uint32_t)off; off += w2_bytes;
         p.smem_a2_off = (uint32_t)off; off += 2 * a2_bytes;

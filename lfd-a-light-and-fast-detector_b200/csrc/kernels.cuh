@@ -11,7 +11,7 @@ static constexpr int kMaxLevels = 8;
 struct Stem0Params {
     const void* in;            // fp32 NCHW (input_format 0) or u8 NHWC (1)
     __nv_bfloat16* out;        // bf16 NHWC
-    const __nv_bfloat16* w;    // packed [4][Cout][8]: element (kc, n, j) = weight of output n for k = 8 kc + j, k = (kh*3 + kw)*3 + ci (k >= 27: 0)
+    const __nv_bfloat16* w;    // packed [kh][2][Cout][8]: element (kh, kc, n, j) = weight (n, ci = j % 4, kh, kw = 2 kc + j / 4), 0 for kw = 3 or ci = 3
     const float* shift;        // fp32 [Cout] or null (BatchNorm scale is folded into w); applied as bf16
     int input_format, N, H, W, Ho, Wo, Cout, relu;
 };

@@ -44,11 +44,17 @@ def fold_scale(weight, scale):
 
 
 def pack_stem_weight(weight):
-    """[Cout, 3, 3, 3] float -> bf16 [4][Cout][8]: k = (kh*3 + kw)*3 + ci padded from 27 to 32 (stem operand order)."""
+    """[Cout, 3, 3, 3] float -> bf16 [kh][2][Cout][8]: element (kh, kc, n, j) is the weight of output n for input channel
+    j % 4 and filter column kw = 2*kc + j // 4 (zero for kw = 3 and for the padded 4th channel) -- the B operand of the stem
+    conv, whose K runs over the 4 pixels x 4 channels that follow a filter row's first input pixel (conv_umma.cu, kStem*)."""
     cout = weight.shape[0]
-    w27 = weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(27, cout)
-    w32 = torch.cat([w27, torch.zeros(5, cout)], 0).reshape(4, 8, cout)
-    return w32.permute(0, 2, 1).contiguous().to(torch.bfloat16)
+    w = weight.detach().float().cpu()                      # [n, ci, kh, kw]
+    full = torch.zeros(3, 4, 4, cout)                      # [kh, pixel, channel, n]
+    full[:, :3, :3, :] = w.permute(2, 3, 1, 0)
+    return full.reshape(3, 2, 8, cout).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+
+
+_AUX_BRANCH = 7      # graph branch of the residual blocks' shortcut convs (LFD_MAX_BRANCHES - 1)
 
 
 class _Arena(object):
@@ -100,6 +106,7 @@ class InferencePlan(object):
         self._tensors = {}                   # name -> bytes
         self._branch = 0                     # branch id given to the ops being emitted (0 = main stream)
         self.concurrent_levels = not os.environ.get('LFD_B200_NO_BRANCHES')
+        self.aux_shortcut = not os.environ.get('LFD_B200_NO_AUX')
         # conv -> 1x1 conv pairs run as ONE kernel (tensor-core kernels only; the SIMT cross-check runs them unfused)
         self.fuse_tails = conv_impl == nat.CONV_UMMA and not os.environ.get('LFD_B200_NO_TAIL')
         self._build(model)
@@ -251,9 +258,18 @@ class InferencePlan(object):
             for bi, block in enumerate(stage):
                 base = 's%db%d' % (si, bi)
                 identity = cur
+                aux = False
                 if block._downsample is not None:
+                    # the 1x1/s2 shortcut conv only depends on the block input: it runs on the auxiliary branch, next to the
+                    # block's first conv, and the block's last conv (which adds it) waits for it
                     ds = list(block._downsample)
+                    aux = self.concurrent_levels and self.aux_shortcut and len(taps) + 1 <= _AUX_BRANCH
+                    if aux:
+                        self._branch = _AUX_BRANCH
                     self._emit_conv(ds[0], ds[1] if len(ds) > 1 else None, False, cur, base + '_id', h, w)
+                    if aux:
+                        self._ops[-1]['wait_mask'] = 1          # the block input comes from the main stream
+                        self._branch = 0
                     identity = base + '_id'
                 pairs = block.conv_norm_pairs()
                 x, hh, ww = cur, h, w
@@ -261,6 +277,8 @@ class InferencePlan(object):
                     last = li == len(pairs) - 1
                     name = base + ('_out' if last else '_c%d' % li)
                     hh, ww = self._emit_conv(conv, norm, True, x, name, hh, ww, res=identity if last else None)
+                    if last and aux:
+                        self._ops[-1]['wait_mask'] = 1 << _AUX_BRANCH
                     x = name
                 cur, h, w = x, hh, ww
                 if (si, bi) in taps:
@@ -382,6 +400,7 @@ class InferencePlan(object):
             o.gn_groups = op.get('gn_groups', 0)
             o.n_cls, o.n_reg, o.point_off, o.cc = op.get('n_cls', 0), op.get('n_reg', 0), op.get('point_off', 0), op.get('cc', 0)
             o.branch = op.get('branch', 0)
+            o.wait_mask = op.get('wait_mask', 0)
             o.tail_cout, o.tail_relu = op.get('tail_cout', 0), op.get('tail_relu', 0)
             if op.get('tail_cout'):
                 o.tail_weight = bb + 2 * op['tail_w']

@@ -31,7 +31,7 @@ class Op(C.Structure):
                 ('Ho', C.c_int32), ('Wo', C.c_int32), ('Cout', C.c_int32),
                 ('ksize', C.c_int32), ('stride', C.c_int32), ('relu', C.c_int32), ('gn_groups', C.c_int32),
                 ('n_cls', C.c_int32), ('n_reg', C.c_int32), ('point_off', C.c_int32), ('cc', C.c_int32),
-                ('branch', C.c_int32), ('reserved', C.c_int32),
+                ('branch', C.c_int32), ('wait_mask', C.c_int32),
                 ('in_off', C.c_int64), ('out_off', C.c_int64), ('res_off', C.c_int64), ('stats_off', C.c_int64),
                 ('weight', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p),
                 ('gamma', C.c_void_p), ('beta', C.c_void_p),

@@ -106,12 +106,22 @@ def test_planner_builds_expected_graph(name, n_conv):
     assert plan.workspace_bytes < plan.activation_bytes + plan.stats_bytes + 65536
     # branches (per-level neck + head chains) run concurrently with the backbone: their buffers must be disjoint from
     # every other branch's, and a tap read across branches is never recycled
+    # (branch 7 holds the residual blocks' shortcut convs, which run next to the block's first conv)
     branches = sorted(set(plan.tensor_branch.values()))
-    assert branches == list(range(len(plan.level_sizes) + 1))
+    assert branches == list(range(len(plan.level_sizes) + 1)) + [7]
     for a in names:
         for b in names:
             if a < b and (plan.tensor_branch[a] != plan.tensor_branch[b] or a in plan.shared_tensors or b in plan.shared_tensors):
                 oa, ob = plan.offsets[a], plan.offsets[b]
                 if plan.tensor_branch[a] != plan.tensor_branch[b] or born[b] >= born[a] and a in plan.shared_tensors or born[a] >= born[b] and b in plan.shared_tensors:
                     assert oa + plan._tensors[a] <= ob or ob + plan._tensors[b] <= oa, (a, b)
-    assert len(plan.shared_tensors) == len(plan.level_sizes)
+    # shared = the level taps + per stage the block input read by the shortcut branch and the shortcut's output
+    n_short = len([o for o in ops if o['branch'] == 7])
+    assert n_short > 0
+    taps_and_inputs = set(o['inp'] for o in ops if o['branch'] == 7) | set(o['out'] for o in ops if o['branch'] == 7)
+    assert plan.shared_tensors >= taps_and_inputs
+    assert len(plan.shared_tensors) <= len(plan.level_sizes) + 2 * n_short
+    # mid-graph dependencies: every shortcut conv waits for the main stream, and exactly one main-stream conv per shortcut waits for it
+    assert all(o.get('wait_mask', 0) == 1 for o in ops if o['branch'] == 7)
+    waiters = [o for o in ops if o.get('wait_mask', 0) == 1 << 7]
+    assert len(waiters) == n_short and all(o['branch'] == 0 and o['res'] is not None for o in waiters)

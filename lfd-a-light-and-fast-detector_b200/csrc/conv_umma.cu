@@ -769,6 +769,11 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     };
     // (16-channel chunks mean 32-byte global segments per pixel and twice the barrier round trips per tile: measured
     //  1600 cycles per 19 KB stage for the 3x3/s2 stem conv, so a 2-deep ring of 32-channel stages beats a 4-deep one of 16)
+    static const int force_cc = getenv("LFD_B200_FORCE_CC") ? atoi(getenv("LFD_B200_FORCE_CC")) : 0;   // experiments only
+    if (force_cc && mode == MODE_3X3S2) {
+        int st = stages_for(force_cc, 1);
+        if (st >= 2) { best_cc = force_cc; best_res = 1; best_st = st; }
+    }
     for (int pass = 0; pass < 3 && !best_cc; ++pass)
         for (int ci = 0; ci < 3 && !best_cc; ++ci) {
             const int want = pass == 0 ? 3 : 2;

@@ -44,7 +44,9 @@ class OptimizerHook(Hook):
         cfg = executor.config_dict
         cfg['optimizer'].zero_grad()
         cfg['loss'].backward()
-        allreduce_gradients(cfg['model'].parameters())          # no-op for a single process
+        # one flat-bucket all-reduce (no-op for a single process); losses already normalised by the global number of
+        # positives (LFD.get_loss) add up over ranks, otherwise the per-rank means are averaged
+        allreduce_gradients(cfg['model'].parameters(), average=not getattr(cfg['model'], 'loss_globally_normalised', False))
         if self._grad_clip_cfg is not None:
             if cfg['epoch'] < self._grad_clip_duration:
                 params = [p for p in cfg['model'].parameters() if p.requires_grad and p.grad is not None]

@@ -113,8 +113,11 @@ class LFD(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('lfd_b200 has no CPU path: move the model and the input to a CUDA (B200) device')
         if self.training:
-            raise NotImplementedError('training-mode forward (conv backward / batch statistics) is not implemented yet; '
-                                      'call model.eval() -- get_loss() and its gradients w.r.t. the outputs are native')
+            # the conv-stack backward is not hand-written yet: ATen / cuDNN evaluate the same module graph (lfd/_train.py)
+            if x.dtype != torch.float32:
+                raise TypeError('training-mode forward takes the float32 NCHW batch of the reference data pipeline')
+            from .._train import train_forward
+            return train_forward(self, x)
         if x.dtype == torch.uint8:
             n, h, w = x.shape[0], x.shape[1], x.shape[2]
         else:
@@ -227,6 +230,15 @@ class LFD(nn.Module):
         gt_b = [a[0] for a in annotation_batch]
         gt_l = [a[1] for a in annotation_batch]
         cls_t, reg_t, label, counters, lv = self._assign(sizes, gt_b, gt_l, device)
+        # Data-parallel training: the reference normalises by the positives of the WHOLE (gathered) batch
+        # (reference :323,340,383 run after the DataParallel gather), so the per-rank counters are summed over the process
+        # group before the loss kernels use them; per-rank losses / gradients then ADD up to the global-batch values and the
+        # gradient all-reduce must sum, not average (`loss_globally_normalised`, read by OptimizerHook).
+        self.loss_globally_normalised = False
+        if self.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(counters, op=torch.distributed.ReduceOp.SUM)
+            self.loss_globally_normalised = True
         N, P = cls_pred.shape[0], cls_pred.shape[1]
         cls_c = cls_pred.detach().float().contiguous()
         reg_c = reg_pred.detach().float().contiguous()

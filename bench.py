@@ -200,7 +200,7 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     from lfd import _native as nat
-    from lfd.pipeline import StreamingDetector
+    from lfd.pipeline import ForwardPostPipeline, StreamingDetector
     import synth
     model, sd = build_model(wl['cfg'])
     model.to(dev)
@@ -221,11 +221,12 @@ def main():
         cls, _ = plan.forward(pool[0], use_graph=False)
         scores = cls.sigmoid() if plan.cls_channels == model._num_classes else cls.softmax(-1)[..., :-1]
         score_thr = float(torch.quantile(scores.flatten()[:2000000].float(), 1.0 - pass_fraction))
-    stream = torch.cuda.current_stream()
+    # one step = forward + post-process of one batch; over consecutive batches the (latency-bound) post-process of batch i
+    # runs on a second stream next to the forward of batch i+1 (lfd/pipeline.py), as a serving loop would do it
+    pipe = ForwardPostPipeline(model, plan, post, score_thr, IOU_THR)
 
     def step(i):
-        c, r = plan.forward(pool[i % POOL], use_graph=model.use_cuda_graph)
-        post.run(c, r, score_thr, IOU_THR)
+        pipe.enqueue(pool[i % POOL])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -241,10 +242,10 @@ def main():
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        e0.record(pipe.fwd_stream)
         for i in range(args.steps):
             step(i)
-        e1.record(stream)
+        e1.record(pipe.post_stream)
         sync_all()
         ms_total = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
@@ -341,7 +342,8 @@ def main():
                             iou_thr=IOU_THR, detections_last_step=counts[:N], parallelism='batch-sharded replicas x%d, no collective' % world,
                             l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
                                % (POOL, POOL * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),
-                            cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl),
+                            cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl,
+                            pipelining='post-process of batch i overlaps the forward of batch i+1 (two streams, two output slots)'),
                 clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps,
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes,
                          note='pinned host uint8 frames -> device -> detections -> pinned host, double buffered'),

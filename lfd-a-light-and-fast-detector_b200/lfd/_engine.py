@@ -420,6 +420,7 @@ class InferencePlan(object):
         self._op_array = arr
         self.cls_out = torch.empty((self.N, self.P, self.cls_channels), dtype=torch.float32, device=dev)
         self.reg_out = torch.empty((self.N, self.P, 4), dtype=torch.float32, device=dev)
+        self._outputs = [(self.cls_out, self.reg_out)]      # slot 1 (second output pair) is allocated on first use
         self.offsets = offsets
         self.handle = None
         if not self.create_native:
@@ -431,8 +432,14 @@ class InferencePlan(object):
         self.handle = handle
         self.num_launches = nat.lib().lfd_plan_num_launches(handle)
 
-    def forward(self, x, use_graph=True):
-        """x: cuda float32 [N,3,H,W] (contiguous) or uint8 [N,H,W,3].  Returns the plan-owned (cls, reg) buffers."""
+    def outputs(self, slot):
+        while len(self._outputs) <= slot:
+            self._outputs.append((torch.empty_like(self.cls_out), torch.empty_like(self.reg_out)))
+        return self._outputs[slot]
+
+    def forward(self, x, use_graph=True, slot=0):
+        """x: cuda float32 [N,3,H,W] (contiguous) or uint8 [N,H,W,3].  Returns the plan-owned (cls, reg) buffers of output
+        `slot` (a second slot lets the post-process of one batch overlap the forward of the next, lfd/pipeline.py)."""
         if x.dtype == torch.float32:
             fmt, ok = nat.INPUT_F32_NCHW, tuple(x.shape) == (self.N, 3, self.H, self.W)
         elif x.dtype == torch.uint8:
@@ -444,10 +451,11 @@ class InferencePlan(object):
         if not ok or not x.is_cuda or not x.is_contiguous():
             raise ValueError('input must be a contiguous CUDA tensor matching the plan shape N=%d H=%d W=%d (got %s)'
                              % (self.N, self.H, self.W, tuple(x.shape)))
+        cls_out, reg_out = self.outputs(slot)
         with torch.cuda.device(self.device):
-            nat.check(nat.lib().lfd_plan_forward(self.handle, nat.ptr(x), fmt, nat.ptr(self.workspace), nat.ptr(self.cls_out),
-                                                 nat.ptr(self.reg_out), int(bool(use_graph)), nat.stream_ptr()))
-        return self.cls_out, self.reg_out
+            nat.check(nat.lib().lfd_plan_forward(self.handle, nat.ptr(x), fmt, nat.ptr(self.workspace), nat.ptr(cls_out),
+                                                 nat.ptr(reg_out), int(bool(use_graph)), nat.stream_ptr()))
+        return cls_out, reg_out
 
     def tensor(self, name):
         """Debug view of an intermediate activation as NHWC bf16 (valid right after an eager forward only if

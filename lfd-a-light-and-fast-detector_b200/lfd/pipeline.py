@@ -1,14 +1,52 @@
 # -*- coding: utf-8 -*-
 """StreamingDetector -- end-to-end batched inference from HOST frames to HOST detections.
 
-Double-buffered: the host->device copy of batch i+1 (copy stream) overlaps the forward + post-process of batch i
-(compute stream); the small device->host read of the results rides on the compute stream.  This is the serving-side
+Pipelined over three streams: the host->device copy of batch i+1 (copy stream) overlaps the forward of batch i (forward
+stream), whose score / decode / NMS and the small device->host read of the results (post stream) in turn overlap the
+forward of batch i+1.  This is the serving-side
 counterpart of the reference's `predict_for_single_image` (lfd/model/lfd.py:544-655), which moves one image at a time
 and synchronises after every stage.
 """
 import torch
 
 from . import _native as nat
+
+
+class ForwardPostPipeline(object):
+    """Software pipeline over batches on two streams: forward(i+1) starts as soon as forward(i) is done, while the (small,
+    latency-bound) score / decode / NMS kernels of batch i run next to it.  The forward writes alternating output slots; a
+    slot is rewritten only after its post-process has finished.  The post-process buffers are single: `consume(results)`
+    is called with the post stream current, enqueue device->host copies (or anything else that reads them) there."""
+
+    def __init__(self, model, plan, post, score_thr, iou_thr):
+        self.model, self.plan, self.post = model, plan, post
+        self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
+        dev = plan.device
+        with torch.cuda.device(dev):
+            self.fwd_stream = torch.cuda.Stream(device=dev)
+            self.post_stream = torch.cuda.Stream(device=dev)
+        self.fwd_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.post_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+
+    def enqueue(self, x, wait_for=None, consume=None):
+        """x: device input of the plan; wait_for: optional event the forward has to wait for (e.g. the H2D copy of x)."""
+        slot = self.k % 2
+        with torch.cuda.stream(self.fwd_stream):
+            if wait_for is not None:
+                self.fwd_stream.wait_event(wait_for)
+            if self.k >= 2:
+                self.fwd_stream.wait_event(self.post_done[slot])
+            cls, reg = self.plan.forward(x, use_graph=self.model.use_cuda_graph, slot=slot)
+            self.fwd_done[slot].record(self.fwd_stream)
+        with torch.cuda.stream(self.post_stream):
+            self.post_stream.wait_event(self.fwd_done[slot])
+            results = self.post.run(cls, reg, self.score_thr, self.iou_thr)
+            if consume is not None:
+                consume(results)
+            self.post_done[slot].record(self.post_stream)
+        self.k += 1
+        return results
 
 
 class StreamingDetector(object):
@@ -22,12 +60,12 @@ class StreamingDetector(object):
         dev = self.device
         with torch.cuda.device(dev):
             self.copy_stream = torch.cuda.Stream(device=dev)
-            self.compute_stream = torch.cuda.Stream(device=dev)
         self.plan = model.inference_plan(batch, height, width, dev)
         for i, hw in enumerate(self.plan.level_sizes):
             model._head_indexes_to_feature_map_sizes[i] = hw
         self.post = model.post_plan(batch, self.plan.level_sizes, dev)
         self.post.set_meta([width] * batch, [height] * batch, [1.0] * batch)
+        self.pipe = ForwardPostPipeline(model, self.plan, self.post, self.score_thr, self.iou_thr)
         self.slots = []
         for _ in range(2):
             self.slots.append(dict(
@@ -48,14 +86,14 @@ class StreamingDetector(object):
         with torch.cuda.stream(self.copy_stream):
             s['x'].copy_(frames_u8, non_blocking=True)
             s['h2d'].record(self.copy_stream)
-        with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(s['h2d'])
-            cls, reg = self.plan.forward(s['x'], use_graph=self.model.use_cuda_graph)
-            dets, labels, _, count = self.post.run(cls, reg, self.score_thr, self.iou_thr)
+        def read_back(results):          # runs with the post-process stream current
+            dets, labels, _, count = results
             s['out_dets'].copy_(dets[:, :self.max_out], non_blocking=True)
             s['out_labels'].copy_(labels[:, :self.max_out], non_blocking=True)
             s['out_count'].copy_(count, non_blocking=True)
-            s['done'].record(self.compute_stream)
+            s['done'].record(self.pipe.post_stream)
+
+        self.pipe.enqueue(s['x'], wait_for=s['h2d'], consume=read_back)
         s['busy'] = True
         self.step += 1
         return (self.step - 1) % 2

@@ -87,6 +87,14 @@ class ClockSampler(object):
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels that can be the most expensive one, from the
+# committed `ncu --set full` capture (profiles/r01_ncu_full_final.md; re-measure with profiles/ncu_run.sh after kernel changes)
+NCU_TRAFFIC = {
+    ('WIDERFACE_S', 'stem0 3x3/s2 3->64 @360x640'): 22303744 + 177991424,
+    ('WIDERFACE_S', 'conv 3x3/s2 64->64 @180x320'): 236171520 + 41846016,
+}
+
+
 def op_algorithmic(row, N, input_bytes_per_px):
     """(bytes, flops) one launch must move / compute: input once, output once, residual once, weights once."""
     k, cin, cout = row['ksize'], row['Cin'], row['Cout']
@@ -160,6 +168,8 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op timing table to stderr')
+    ap.add_argument('--ncu-step', action='store_true',
+                    help='for `ncu --profile-from-start off`: warm up, then ONE eager step between cudaProfilerStart/Stop, and exit')
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -234,6 +244,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.ncu_step:      # profiling aid, prints no bench line
+        model.use_cuda_graph = False
+        with torch.no_grad():
+            for i in range(4):
+                step(i)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            step(4)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return 0
     with torch.no_grad():
         for i in range(max(warmup, POOL)):   # also instantiates one graph per pool buffer
             step(i)
@@ -313,10 +334,12 @@ def main():
     conv_ms = float(sum(r['ms'] for r in table if r['row']['kind'] == 'conv'))
     net_bound_ms = float(sum(r['t_bound_ms'] for r in table))
     total_bytes, total_flops = sum(r['bytes'] for r in table), sum(r['flops'] for r in table)
-    roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=None,
+    kname = '%s %dx%d/s%d %d->%d @%dx%d' % (top['row']['kind'], top['row']['ksize'], top['row']['ksize'], top['row']['stride'],
+                                         top['row']['Cin'], top['row']['Cout'], top['row']['Ho'], top['row']['Wo'])
+    roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
+                    traffic=NCU_TRAFFIC.get((wl['cfg'], kname)),
                     peak_source=pk['source'],
-                    kernel='%s %dx%d/s%d %d->%d @%dx%d' % (top['row']['kind'], top['row']['ksize'], top['row']['ksize'], top['row']['stride'],
-                                                           top['row']['Cin'], top['row']['Cout'], top['row']['Ho'], top['row']['Wo']),
+                    kernel=kname,
                     kernel_ms=top['ms'], kernel_share_of_step=top['ms'] / sum_ms, algorithmic_bytes=top['bytes'], algorithmic_flops=top['flops'],
                     net=dict(layerwise_bound_ms=net_bound_ms, forward_ms_eager_sum=sum_ms, frac_of_layerwise_bound=net_bound_ms / sum_ms,
                              conv_share=conv_ms / sum_ms, algorithmic_gb=total_bytes / 1e9, algorithmic_gflop=total_flops / 1e9,

@@ -105,8 +105,9 @@ def op_algorithmic(row, N, input_bytes_per_px):
     if row['kind'] == 'stem0':
         return px_in * input_bytes_per_px + px_out * cf * 2 + 27 * cout * 2 + tail_b, 2.0 * px_out * cout * 27 + tail_f
     if row['kind'] == 'conv':
-        b = px_in * cin * 2 + px_out * cf * 2 * (2 if row['res'] else 1) + k * k * cin * cout * 2 + tail_b
-        return b, 2.0 * px_out * cout * cin * k * k + tail_f
+        dc = row.get('ds_cout', 0)          # fused shortcut conv: second output, reads the same input
+        b = px_in * cin * 2 + px_out * cf * 2 * (2 if row['res'] else 1) + k * k * cin * cout * 2 + tail_b + px_out * dc * 2 + cin * dc * 2
+        return b, 2.0 * px_out * cout * cin * k * k + tail_f + 2.0 * px_out * dc * cin
     if row['kind'] == 'gn_apply':
         return px_in * cin * 2 * 2, 0.0
     return px_in * cin * 2 + px_out * cout * 4, 2.0 * px_out * cout * cin   # head_final

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LFD_B200_ABI_VERSION 1
+#define LFD_B200_ABI_VERSION 2
 #define LFD_MAX_LEVELS 8
 #define LFD_MAX_BRANCHES 8
 
@@ -95,11 +95,18 @@ typedef struct lfd_op {
     const void* tail_weight;
     const float* tail_scale;
     const float* tail_shift;
+    /* CONV 3x3/s2 only (no tail, no residual): the residual block's 1x1/s2 shortcut conv on the SAME input (Cin -> ds_cout,
+     * ds_cout == Cout) is computed by the same kernel -- its input pixel is this conv's centre tap -- and stored (no ReLU) at
+     * ds_out_off.  ds_weight = bf16 packed [Cin/8][ds_cout][8] with the BatchNorm scale folded in.  0 = none. */
+    int32_t ds_cout, ds_reserved;
+    int64_t ds_out_off;
+    const void* ds_weight;
+    const float* ds_shift;
 } lfd_op;
 
 /* Tile / pipeline configuration the tcgen05 kernel will use for a conv (host only, no launch).
  * cc = input-channel chunk the weights must be packed with. */
-int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int* cc,
+int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int ds_cout, int* cc,
                    int* stages, int* weights_resident, int* num_tiles, int64_t* smem_bytes);
 
 /* The plan copies the op list.  stats_off/stats_bytes: region of the workspace zeroed at the start of each forward. */

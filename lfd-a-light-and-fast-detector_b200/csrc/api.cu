@@ -87,13 +87,14 @@ static ConvGeom geom_of(const lfd_op& o) {
     g.N = o.N; g.H = o.H; g.W = o.W; g.Cin = o.Cin; g.Ho = o.Ho; g.Wo = o.Wo; g.Cout = o.Cout; g.ksize = o.ksize; g.stride = o.stride;
     g.stem = o.kind == LFD_OP_STEM0 ? 1 : 0;
     g.tail_cout = o.tail_cout;
+    g.ds_cout = o.ds_cout;
     if (g.stem) g.Cin = 16;   // K of one filter row: 4 pixels x 4 (padded) channels
     return g;
 }
 
-extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int* cc,
+extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int Cout, int ksize, int stride, int tail_cout, int ds_cout, int* cc,
                               int* stages, int* weights_resident, int* num_tiles, int64_t* smem_bytes) {
-    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, 0};
+    ConvGeom g = {N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, ds_cout, 0};
     UmmaConvParams p;
     size_t smem = 0;
     int grid = 0;
@@ -122,6 +123,8 @@ static int check_op(const lfd_op& o) {
             if (o.Ho != eh || o.Wo != ew) return fail(LFD_ERR_INVALID, "conv output size mismatch (%dx%d vs %dx%d)", o.Ho, o.Wo, eh, ew);
             if (o.gn_groups && ((o.tail_cout ? o.tail_cout : o.Cout) != o.gn_groups * 8 || o.gn_groups != 16)) return fail(LFD_ERR_UNSUPPORTED, "fused GroupNorm statistics need 16 groups of 8 channels (Cout=%d groups=%d)", o.Cout, o.gn_groups);
             if (o.cc <= 0 || o.Cin % o.cc) return fail(LFD_ERR_INVALID, "conv cc=%d does not divide Cin=%d", o.cc, o.Cin);
+            if (o.ds_cout && (o.ksize != 3 || o.stride != 2 || o.tail_cout || o.res_off >= 0 || o.gn_groups || o.ds_cout != o.Cout || !o.ds_weight || o.ds_out_off < 0))
+                return fail(LFD_ERR_INVALID, "a fused shortcut conv needs a 3x3/s2 conv without tail / residual / GroupNorm, ds_cout == Cout, weights and an output offset");
             break;
         case LFD_OP_GN_APPLY:
         case LFD_OP_HEAD_FINAL:
@@ -180,7 +183,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             const __nv_bfloat16* res = o.res_off >= 0 ? reinterpret_cast<const __nv_bfloat16*>(ws + o.res_off) : nullptr;
             double* stats = o.gn_groups ? reinterpret_cast<double*>(ws + o.stats_off) : nullptr;
             if (conv_impl == LFD_CONV_SIMT) {
-                if (o.tail_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails");
+                if (o.tail_cout || o.ds_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails / shortcuts");
                 CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight),
                                           o.shift, stats, o.gn_groups, o.relu, st));
             } else {
@@ -188,6 +191,10 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
                 p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
+                if (o.ds_cout) {
+                    p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.ds_weight); p.shift2 = o.ds_shift; p.relu2 = 0;
+                    p.out3 = reinterpret_cast<__nv_bfloat16*>(ws + o.ds_out_off);
+                }
                 p.trace = g_trace; p.tl = tl;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for conv %dx%d Cf=%d", o.ksize, o.ksize, p.Cf);
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));

@@ -20,12 +20,14 @@ static constexpr int kSmemOnesOff = 512;      // constant A operand [2 k-chunks]
 struct ConvGeom {
     int N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
     int tail_cout;   // > 0: a 1x1/s1 conv (Cout -> tail_cout) is fused behind this conv (second GEMM in the same kernel)
+    int ds_cout;     // > 0 (3x3/s2 only): the residual block's 1x1/s2 shortcut conv (Cin -> ds_cout == Cout) is fused: second output tensor
     int stem;   // 1: 3x3/s2 conv on the raw 3-channel image (K = 27 padded to 32), operand built by the producers
 };
 
 struct alignas(64) UmmaConvParams {
     CUtensorMap tm_out;         // TMA descriptor of the stored tensor (epilogue tile store)
     CUtensorMap tm_res;         // TMA descriptor of the residual tensor (same geometry)
+    CUtensorMap tm_out3;        // TMA descriptor of the fused shortcut conv's output (same geometry)
     int stg_nbuf;               // staging buffers per epilogue warp (2: the store of tile t overlaps the conversion of tile t+1)
     const __nv_bfloat16* in;
     __nv_bfloat16* out;
@@ -38,6 +40,9 @@ struct alignas(64) UmmaConvParams {
     const __nv_bfloat16* w2;    // packed [Cout/8][Cout2][8]
     const float* shift2;
     int Cout2, relu2, Cf;       // Cf = channels of the stored tensor (Cout2 with a tail, else Cout)
+    // fused 1x1/s2 shortcut conv (MODE_3X3S2, no tail): out3 = W3 . x[centre tap] + shift3; its weights / shift travel in w2 / shift2
+    int Cout3;
+    __nv_bfloat16* out3;
     uint32_t smem_w2_off, smem_a2_off, a2_bytes, n_a2;
     double* stats;              // optional [N][groups][2] (sum, sumsq) of the stored output
     unsigned long long* tl;     // debugging: [start, end] of the launch in %globaltimer ns (LFD_B200_TIMELINE builds), normally null

@@ -225,8 +225,9 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const uint32_t b = (i < p.Cout && p.shift) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift[i])) : 0u;
         reinterpret_cast<uint4*>(smem + p.smem_bias_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
-    for (int i = tid; i < 2 * p.Cout2; i += kThreads) {
-        const uint32_t b = (i < p.Cout2 && p.shift2) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift2[i])) : 0u;
+    const int cn2 = p.Cout2 + p.Cout3;      // second GEMM of the launch: fused 1x1 tail or fused 1x1/s2 shortcut (never both)
+    for (int i = tid; i < 2 * cn2; i += kThreads) {
+        const uint32_t b = (i < cn2 && p.shift2) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift2[i])) : 0u;
         reinterpret_cast<uint4*>(smem + p.smem_bias2_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();   // these operands are read by tcgen05.mma (async proxy)
@@ -329,7 +330,9 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         };
 
         // ---- final phase: accumulator (+residual) (+ReLU) -> bf16 staging rows -> TMA store (+ GroupNorm statistics)
-        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base) {
+        uint32_t store_count = 0;   // staging buffers alternate per STORE (a launch with a fused shortcut stores twice per tile)
+        auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, const CUtensorMap* tmap,
+                               int var, bool first, bool last) {
             const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
             int c1, c2 = 0;      // coordinates of this warp's first row: pixel index (flat) or (x, y)
@@ -341,7 +344,10 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 valid = (c2 + (lane >> 3) < p.Ho) && (c1 + (lane & 7) < p.Wo);
             }
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
-            const uint32_t sbuf = stg0 + (p.stg_nbuf == 2 ? (tc & 1) * warp_stg : 0u);
+            // (only the 3x3/s2 mode can store twice per tile; the other instantiations keep using the tile counter, which costs
+            //  them no extra live register -- the two-CTAs-per-SM kernels sit right at their 96-register budget)
+            const uint32_t sbuf = stg0 + (p.stg_nbuf == 2 ? ((MODE == MODE_3X3S2 ? store_count : tc) & 1) * warp_stg : 0u);
+            if (MODE == MODE_3X3S2) ++store_count;
             if (lane == 0) {
                 // this staging buffer was the source of an earlier store: the TMA engine must be done reading it
                 if (p.stg_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
@@ -354,8 +360,10 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 }
             }
             if (tid == 0) LFD_TRACE(2, tc, 0);
-            mbar_wait(&bar_full[a], aph);
-            tc_fence_after_sync();
+            if (first) {
+                mbar_wait(&bar_full[a], aph);
+                tc_fence_after_sync();
+            }
             if (tid == 0) LFD_TRACE(2, tc, 1);
             if (has_res) mbar_wait(&res_bar[warp], tc & 1);
             else __syncwarp();                    // lane 0 has seen the buffer free
@@ -366,17 +374,17 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 fence_proxy_async_smem();             // st.shared (generic proxy) -> TMA store (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&bar_empty[a]);       // accumulator stage may be overwritten by the next-but-one tile
+                    if (last) mbar_arrive(&bar_empty[a]);   // accumulator stage may be overwritten by the next-but-one tile
                     for (int pn = 0; pn < n_panels; ++pn) {   // rows / columns outside the map are clipped by the TMA engine
-                        if (MODE == MODE_FLAT) tma_store_3d(&p.tm_out, sbuf + pn * 4096, ch0 + pn * 64, c1, n);
-                        else tma_store_4d(&p.tm_out, sbuf + pn * 4096, ch0 + pn * 64, c1, c2, n);
+                        if (MODE == MODE_FLAT) tma_store_3d(tmap, sbuf + pn * 4096, ch0 + pn * 64, c1, n);
+                        else tma_store_4d(tmap, sbuf + pn * 4096, ch0 + pn * 64, c1, c2, n);
                     }
                     bulk_commit();
                 }
             };
             // GroupNorm partial sums are taken over the STORED (bf16) values; one group = one 16-byte chunk (8 channels)
             double* sdst = p.stats ? p.stats + ((size_t)n * p.gn_groups + (ch0 >> 3)) * 2 : nullptr;
-            switch (variant) {
+            switch (var) {
                 case 0: drain<16, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
                 case 1: drain<32, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
                 case 2: drain<64, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
@@ -398,22 +406,27 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                 case 18: { float st[16]; drain<64, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<64>(st, lane, sdst); } break;
                 default: { float st[32]; drain<128, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<128>(st, lane, sdst); } break;
             }
-            if (variant < 16) publish();
+            if (var < 16) publish();
             if (tid == 0) LFD_TRACE(2, tc, 2);
             if (tid == 0) LFD_TRACE(2, tc, 3);
         };
 
         if (!p.Cout2) {
             uint32_t tcount = 0;
+            // fused shortcut (3x3/s2 only): a second pass drains the second accumulator of the same stage (same barriers) into
+            // its own tensor, without ReLU.  One call site, so that the lambda stays inlined in every instantiation.
+            const int n_pass = (MODE == MODE_3X3S2 && p.Cout3) ? 2 : 1;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount)
-                finish_tile(tile, tcount, tfull, tempty, 0);
+                for (int ps = 0; ps < n_pass; ++ps)
+                    finish_tile(tile, tcount, tfull, tempty, ps ? 2 * p.Cout : 0, ps ? &p.tm_out3 : &p.tm_out, ps ? l2cw : variant, ps == 0,
+                                ps == n_pass - 1);
         } else {
             // software pipelined: intermediate of tile t, then the finished tail of tile t-1
             uint32_t tcount = 0;
             for (int tile = blockIdx.x;; tile += gridDim.x, ++tcount) {
                 const bool has = tile < p.num_tiles;
                 if (has) mid_tile(tcount);
-                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout);
+                if (tcount >= 1) finish_tile(tile - (int)gridDim.x, tcount - 1, tfull2, tempty2, 2 * p.Cout, &p.tm_out, variant, true, true);
                 if (!has) break;
             }
         }
@@ -431,8 +444,8 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const uint32_t b_k16 = (2 * lbo_b) >> 4;        //   (B)
         const uint32_t b_tap = (cpc * lbo_b) >> 4;      // address-field step per tap (B)
         const int nk16 = p.Cc >> 4;
-        const uint32_t w2_bytes = p.Cout2 ? (uint32_t)(p.Cout * p.Cout2 * 2) : 0u;
-        if (p.b_resident || p.Cout2) {
+        const uint32_t w2_bytes = p.Cout2 ? (uint32_t)(p.Cout * p.Cout2 * 2) : (p.Cout3 ? (uint32_t)(p.Cin * p.Cout3 * 2) : 0u);
+        if (p.b_resident || w2_bytes) {
             if (elect_one_sync()) {
                 const uint32_t w1_bytes = p.b_resident ? p.w_total_bytes : 0u;
                 mbar_arrive_expect_tx(wbar, w1_bytes + w2_bytes);
@@ -446,12 +459,12 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             mbar_wait(wbar, 0);
         }
         // fused 1x1 tail: D2[128 x Cout2] = A2[128 x Cout] . W2, A2 written by the epilogue warps (mid_tile)
-        const uint32_t idesc2 = umma_idesc_bf16(128, p.Cout2 ? p.Cout2 : 16);
+        const uint32_t idesc2 = umma_idesc_bf16(128, cn2 ? cn2 : 16);
         const uint64_t ones_desc = umma_smem_desc(smem_u32(smem + kSmemOnesOff), 2048, 128);
         const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + p.smem_bias_off), lbo_b, 128);
-        const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), p.Cout2 * 16, 128);
+        const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), cn2 * 16, 128);
         const uint64_t a2desc0 = umma_smem_desc(0, kA2Pitch, 128);
-        const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), p.Cout2 * 16, 128);
+        const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), cn2 * 16, 128);
         auto issue_tail = [&](uint32_t u) {
             const uint32_t b = p.n_a2 == 2 ? (u & 1) : 0, use = p.n_a2 == 2 ? (u >> 1) : u;
             const uint32_t a2s = u & 1, a2ph = (u >> 1) & 1;
@@ -493,6 +506,15 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
 #pragma unroll
                         for (int tap = 0; tap < TAPS; ++tap)
                             umma_bf16(d_tmem, adk + (uint32_t)tap_view<MODE>(tap), bdk + (uint32_t)(tap * b_tap), idesc, (cc | k16 | tap) != 0);
+                    }
+                    if (MODE == MODE_3X3S2 && p.Cout3) {
+                        // fused 1x1/s2 shortcut conv of the residual block: its input pixel is this conv's centre tap, so it
+                        // is one more MMA per 16 channels on the operand that is already in shared memory
+                        const uint32_t d3 = tmem_base + 2 * p.Cout + a * p.Cout3;
+                        for (int k16 = 0; k16 < nk16; ++k16)
+                            umma_bf16(d3, ad + (uint32_t)(k16 * a_k16) + (uint32_t)tap_view<MODE>(4),
+                                      b2desc0 + (uint32_t)(((cc * cpc + 2 * k16) * p.Cout3 * 16) >> 4), idesc2, (cc | k16) != 0);
+                        if (cc == n_cc - 1 && p.shift2) umma_bf16(d3, ones_desc, bias2_desc, idesc2, 1);
                     }
                     umma_commit(&empty[s]);
                     if (cc == n_cc - 1) {
@@ -727,6 +749,7 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     p.magic_tpi = ((1ull << 40) + p.tiles_per_img - 1) / p.tiles_per_img;
     p.magic_tx = p.tiles_x ? ((1ull << 40) + p.tiles_x - 1) / p.tiles_x : 0;
     const int Cf = g.tail_cout > 0 ? g.tail_cout : g.Cout;
+    if (g.ds_cout && (mode != MODE_3X3S2 || g.tail_cout || g.ds_cout != g.Cout)) return -6;
     if (g.tail_cout) {
         if (g.tail_cout % 16 || g.tail_cout > 128 || g.tail_cout < 16 || 2 * (g.Cout + g.tail_cout) > 512) return -4;
         if (epi_warps_of(mode) == 8 && g.tail_cout < 32) return -4;
@@ -737,12 +760,13 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     p.smem_table_off = (uint32_t)hoff;
     if (mode != MODE_FLAT && mode != MODE_STEM) hoff += ((size_t)p.n_px * 10 + 127) & ~(size_t)127;   // PxEntry[n_px] | PxDelta[n_px]
     p.smem_bias_off = (uint32_t)hoff; hoff += (size_t)g.Cout * 32;
-    p.smem_bias2_off = (uint32_t)hoff; hoff += (size_t)g.tail_cout * 32;
+    p.smem_bias2_off = (uint32_t)hoff; hoff += (size_t)(g.tail_cout + g.ds_cout) * 32;
     p.smem_staging_off = (uint32_t)((hoff + 1023) & ~(size_t)1023);
     const size_t fixed = p.smem_staging_off + staging;
     // everything that lives behind the ring: fused-tail weights + two operand buffers
     const size_t a2_bytes = g.tail_cout ? ((size_t)(g.Cout / 8) * 129 * 16 + 127) & ~(size_t)127 : 0;
-    const size_t w2_bytes = g.tail_cout ? ((size_t)g.Cout * g.tail_cout * 2 + 127) & ~(size_t)127 : 0;
+    const size_t w2_bytes = g.tail_cout ? ((size_t)g.Cout * g.tail_cout * 2 + 127) & ~(size_t)127
+                                        : (g.ds_cout ? ((size_t)g.Cin * g.ds_cout * 2 + 127) & ~(size_t)127 : 0);
     const size_t post = w2_bytes + 2 * a2_bytes;
     const size_t budget = 224 * 1024 - post;
     const size_t w_total = (size_t)taps * g.Cin * g.Cout * 2;
@@ -817,11 +841,12 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
     p.log2_cpc = ilog2(p.Cc / 8);
     p.Cf = Cf;
     p.Cout2 = g.tail_cout;
+    p.Cout3 = g.ds_cout;
     p.log2_cpr = ilog2(Cf / 8);
     if ((1 << p.log2_cpr) != Cf / 8) return -3;       // stored channel count must be 16/32/64/128
     p.log2_rp128 = Cf * 2 >= 128 ? 0 : ilog2(128 / (Cf * 2));
     {   // TMEM: two accumulator stages of the conv (+ two of the tail); power of two >= 32
-        int need = 2 * g.Cout + 2 * g.tail_cout, cols = 32;
+        int need = 2 * g.Cout + 2 * (g.tail_cout + g.ds_cout), cols = 32;
         while (cols < need) cols <<= 1;
         p.tmem_cols = cols;
     }
@@ -830,6 +855,8 @@ static int configure_with(const ConvGeom& g, int num_sms, int nbuf, UmmaConvPara
         p.smem_w2_off = (uint32_t)off; off += w2_bytes;
         p.smem_a2_off = (uint32_t)off; off += 2 * a2_bytes;
         p.a2_bytes = (uint32_t)a2_bytes; p.n_a2 = 2;
+    } else if (g.ds_cout) {
+        p.smem_w2_off = (uint32_t)off; off += w2_bytes;
     }
     *smem_bytes = off;
     if (p.ctas_per_sm == 2 && 2 * p.tmem_cols > 512) p.ctas_per_sm = 1;
@@ -902,6 +929,7 @@ static int encode_one(const UmmaConvParams& p, const void* ptr, CUtensorMap* tm)
 int umma_conv_encode_maps(UmmaConvParams* p) {
     if (encode_one(*p, p->out, &p->tm_out)) return -1;
     if (p->res && encode_one(*p, p->res, &p->tm_res)) return -1;
+    if (p->Cout3 && encode_one(*p, p->out3, &p->tm_out3)) return -1;
     return 0;
 }
 

@@ -107,6 +107,7 @@ class InferencePlan(object):
         self._branch = 0                     # branch id given to the ops being emitted (0 = main stream)
         self.concurrent_levels = not os.environ.get('LFD_B200_NO_BRANCHES')
         self.aux_shortcut = not os.environ.get('LFD_B200_NO_AUX')
+        self.fuse_shortcuts = conv_impl == nat.CONV_UMMA and not os.environ.get('LFD_B200_NO_FUSED_SHORTCUT')
         # conv -> 1x1 conv pairs run as ONE kernel (tensor-core kernels only; the SIMT cross-check runs them unfused)
         self.fuse_tails = conv_impl == nat.CONV_UMMA and not os.environ.get('LFD_B200_NO_TAIL')
         self._build(model)
@@ -162,6 +163,16 @@ class InferencePlan(object):
                     tail_shift=self._add_f32(shift2), tail_modules=(conv2, norm2))
 
     @staticmethod
+    def _can_fuse_shortcut(block, pairs):
+        """The block's 1x1/s2 shortcut conv reads the same tensor as its first conv; when that is a 3x3/s2 conv with the same
+        number of output channels (every shipped block) the shortcut's input pixel is the 3x3 conv's centre tap."""
+        ds = list(block._downsample)
+        c0, sc = pairs[0][0], ds[0]
+        return (len(pairs) >= 2 and c0.kernel_size == (3, 3) and c0.stride == (2, 2) and sc.kernel_size == (1, 1) and sc.stride == (2, 2)
+                and sc.in_channels == c0.in_channels and sc.out_channels == c0.out_channels and c0.out_channels in (32, 64, 128)
+                and sc.groups == 1 and c0.groups == 1)
+
+    @staticmethod
     def _can_tail(conv, nxt):
         """nxt = (conv, norm, relu): a bias-free-or-not 1x1/s1 conv directly consuming `conv`'s output."""
         c2 = nxt[0]
@@ -182,14 +193,15 @@ class InferencePlan(object):
         self._push(op)
         return ho, wo
 
-    def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None, tail=None):
+    def _emit_conv(self, conv, norm, relu, in_name, out_name, h, w, res=None, gn_groups=0, cache=None, tail=None, shortcut=None):
         k, s = conv.kernel_size[0], conv.stride[0]
         if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or s not in (1, 2) or conv.padding[0] != k // 2 \
                 or conv.groups != 1 or conv.dilation != (1, 1):
             raise NotImplementedError('unsupported conv geometry for the B200 kernels: %r' % (conv,))
         cin, cout = conv.in_channels, conv.out_channels
         ho, wo = _conv_out(h, k, s), _conv_out(w, k, s)
-        q = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s, tail[0].out_channels if tail is not None else 0)
+        q = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s, tail[0].out_channels if tail is not None else 0,
+                           shortcut[0].out_channels if shortcut is not None else 0)
         cc = q['cc']
         key = (id(conv), id(norm), cc)
         if cache is not None and key in cache:
@@ -209,6 +221,12 @@ class InferencePlan(object):
                   w_bf16=w_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
         if tail is not None:
             op.update(self._tail_fields(tail, cout))
+        if shortcut is not None:      # (conv1x1/s2, norm, output name): same input, computed by the same kernel
+            sconv, snorm, sname = shortcut
+            sscale, sshift = self._fold(sconv, snorm)
+            op.update(ds_cout=sconv.out_channels, ds_w=self._add_bf16(pack_conv_weight(fold_scale(sconv.weight, sscale), cin)),
+                      ds_shift=self._add_f32(sshift), ds_modules=(sconv, snorm),
+                      out2=self._tensor(sname, self.N, ho, wo, sconv.out_channels))
         op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or cout)
         if gn_groups:
             op['stats'] = len([o for o in self._ops if o.get('stats') is not None and o['kind'] == nat.OP_CONV])
@@ -259,7 +277,13 @@ class InferencePlan(object):
                 base = 's%db%d' % (si, bi)
                 identity = cur
                 aux = False
-                if block._downsample is not None:
+                pairs = block.conv_norm_pairs()
+                fuse_sc = None
+                if block._downsample is not None and self.fuse_shortcuts and self._can_fuse_shortcut(block, pairs):
+                    ds = list(block._downsample)
+                    fuse_sc = (ds[0], ds[1] if len(ds) > 1 else None, base + '_id')
+                    identity = base + '_id'
+                elif block._downsample is not None:
                     # the 1x1/s2 shortcut conv only depends on the block input: it runs on the auxiliary branch, next to the
                     # block's first conv, and the block's last conv (which adds it) waits for it
                     ds = list(block._downsample)
@@ -271,12 +295,12 @@ class InferencePlan(object):
                         self._ops[-1]['wait_mask'] = 1          # the block input comes from the main stream
                         self._branch = 0
                     identity = base + '_id'
-                pairs = block.conv_norm_pairs()
                 x, hh, ww = cur, h, w
                 for li, (conv, norm) in enumerate(pairs):
                     last = li == len(pairs) - 1
                     name = base + ('_out' if last else '_c%d' % li)
-                    hh, ww = self._emit_conv(conv, norm, True, x, name, hh, ww, res=identity if last else None)
+                    hh, ww = self._emit_conv(conv, norm, True, x, name, hh, ww, res=identity if last else None,
+                                             shortcut=fuse_sc if li == 0 else None)
                     if last and aux:
                         self._ops[-1]['wait_mask'] = 1 << _AUX_BRANCH
                     x = name
@@ -361,6 +385,7 @@ class InferencePlan(object):
         stats_each = self.N * 16 * 2 * 8
         self.stats_bytes = (n_stats * stats_each + 255) & ~255
         producer = {op['out']: op['branch'] for op in self._ops if op.get('out') is not None}
+        producer.update({op['out2']: op['branch'] for op in self._ops if op.get('out2') is not None})
         last_use, shared = {}, set()
         for i, op in enumerate(self._ops):
             for k in ('inp', 'res'):
@@ -373,8 +398,9 @@ class InferencePlan(object):
         local = {}                              # name -> (branch, offset inside the branch's arena)
         no_reuse = bool(os.environ.get('LFD_B200_NO_REUSE'))
         for i, op in enumerate(self._ops):
-            if op.get('out') is not None:
-                local[op['out']] = (op['branch'], arenas[op['branch']].alloc(self._tensors[op['out']]))
+            for key in ('out', 'out2'):
+                if op.get(key) is not None:
+                    local[op[key]] = (op['branch'], arenas[op['branch']].alloc(self._tensors[op[key]]))
             for name, lu in list(last_use.items()):
                 if lu == i:
                     del last_use[name]
@@ -405,6 +431,11 @@ class InferencePlan(object):
             if op.get('tail_cout'):
                 o.tail_weight = bb + 2 * op['tail_w']
                 o.tail_shift = fb + 4 * op['tail_shift']
+            o.ds_cout, o.ds_out_off = op.get('ds_cout', 0), -1
+            if op.get('ds_cout'):
+                o.ds_weight = bb + 2 * op['ds_w']
+                o.ds_shift = fb + 4 * op['ds_shift']
+                o.ds_out_off = offsets[op['out2']]
             o.in_off = offsets[op['inp']] if op.get('inp') is not None else -1
             o.out_off = offsets[op['out']] if op.get('out') is not None else -1
             o.res_off = offsets[op['res']] if op.get('res') is not None else -1
@@ -460,17 +491,18 @@ class InferencePlan(object):
     def tensor(self, name):
         """Debug view of an intermediate activation as NHWC bf16 (valid right after an eager forward only if
         its buffer has not been reused by a later layer)."""
-        op = [o for o in self._ops if o.get('out') == name][0]
-        n = self.N * op['Ho'] * op['Wo'] * op['Cout']
+        op = [o for o in self._ops if name in (o.get('out'), o.get('out2'))][0]
+        c = op['ds_cout'] if op.get('out2') == name else (op.get('tail_cout') or op['Cout'])
+        n = self.N * op['Ho'] * op['Wo'] * c
         raw = self.workspace[self.offsets[name]: self.offsets[name] + 2 * n]
-        return raw.view(torch.bfloat16).view(self.N, op['Ho'], op['Wo'], op['Cout'])
+        return raw.view(torch.bfloat16).view(self.N, op['Ho'], op['Wo'], c)
 
     def describe(self):
         names = {nat.OP_STEM0: 'stem0', nat.OP_CONV: 'conv', nat.OP_GN_APPLY: 'gn_apply', nat.OP_HEAD_FINAL: 'head_final'}
         rows = []
         for op in self._ops:
             rows.append(dict(kind=names[op['kind']], H=op['H'], W=op['W'], Cin=op['Cin'], Ho=op['Ho'], Wo=op['Wo'], Cout=op['Cout'],
-                             ksize=op.get('ksize', 1), stride=op.get('stride', 1), res=op.get('res') is not None, tail_cout=op.get('tail_cout', 0),
+                             ksize=op.get('ksize', 1), stride=op.get('stride', 1), res=op.get('res') is not None, tail_cout=op.get('tail_cout', 0), ds_cout=op.get('ds_cout', 0),
                              out=op.get('out'), query=op.get('query')))
         return rows
 

@@ -36,7 +36,9 @@ class Op(C.Structure):
                 ('weight', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p),
                 ('gamma', C.c_void_p), ('beta', C.c_void_p),
                 ('tail_cout', C.c_int32), ('tail_relu', C.c_int32),
-                ('tail_weight', C.c_void_p), ('tail_scale', C.c_void_p), ('tail_shift', C.c_void_p)]
+                ('tail_weight', C.c_void_p), ('tail_scale', C.c_void_p), ('tail_shift', C.c_void_p),
+                ('ds_cout', C.c_int32), ('ds_reserved', C.c_int32), ('ds_out_off', C.c_int64),
+                ('ds_weight', C.c_void_p), ('ds_shift', C.c_void_p)]
 
 
 class PostCfg(C.Structure):
@@ -61,7 +63,7 @@ SYMBOLS = {
     'lfd_abi_version': (_i, []),
     'lfd_last_error': (C.c_char_p, []),
     'lfd_device_sm_count': (_i, []),
-    'lfd_conv_query': (_i, [_i] * 10 + [C.POINTER(_i)] * 4 + [C.POINTER(_i64)]),
+    'lfd_conv_query': (_i, [_i] * 11 + [C.POINTER(_i)] * 4 + [C.POINTER(_i64)]),
     'lfd_plan_create': (_i, [C.POINTER(Op), _i, _i, _i, _i, _i64, _i64, _i64, _i, C.POINTER(_vp)]),
     'lfd_plan_destroy': (_i, [_vp]),
     'lfd_plan_num_launches': (_i, [_vp]),
@@ -107,7 +109,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.lfd_abi_version() != 1:
+    if L.lfd_abi_version() != 2:
         raise LfdError('liblfd_b200.so ABI version mismatch')
     _lib = L
     return L
@@ -127,9 +129,9 @@ def ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout=0):
+def conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout=0, ds_cout=0):
     cc, st, res, nt = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     smem = C.c_int64()
-    check(lib().lfd_conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, C.byref(cc), C.byref(st), C.byref(res),
+    check(lib().lfd_conv_query(N, H, W, Cin, Ho, Wo, Cout, ksize, stride, tail_cout, ds_cout, C.byref(cc), C.byref(st), C.byref(res),
                                C.byref(nt), C.byref(smem)))
     return dict(cc=cc.value, stages=st.value, weights_resident=res.value, num_tiles=nt.value, smem_bytes=smem.value)

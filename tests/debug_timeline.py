@@ -54,7 +54,7 @@ def main():
         s, e = (int(t[i, 0]) - t0) * 1e-3, (int(t[i, 1]) - t0) * 1e-3
         busy += e - s
         print('%3d  %-10s k%d s%d %3d->%3d%s %4dx%-4d res=%d  start %8.1f us  end %8.1f us  dur %6.1f us  %s' % (
-            i, r['kind'], r['ksize'], r['stride'], r['Cin'], r['Cout'], ('->%3d' % r['tail_cout']) if r['tail_cout'] else '     ',
+            i, r['kind'], r['ksize'], r['stride'], r['Cin'], r['Cout'], ('->%3d' % r['tail_cout']) if r['tail_cout'] else ('+sc  ' if r.get('ds_cout') else '     '),
             r['Ho'], r['Wo'], int(r['res']), s, e, e - s, r.get('query') or ''))
     print('sum of durations %.1f us' % busy)
 

@@ -139,6 +139,11 @@ def test_every_layer_within_one_bf16_ulp_teacher_forced(name, monkeypatch):
             if not op.get('tail_cout'):
                 ref = ref_conv(src, conv.weight.detach().cpu(), scale, shift, op['stride'], bool(op['relu']), res=res)
                 assert_bf16_close(plan.tensor(op['out']), ref, 'conv %s' % op['out'])
+                if op.get('ds_cout'):     # fused 1x1/s2 shortcut conv: second output of the same launch
+                    sconv, snorm = op['ds_modules']
+                    sscale, sshift = InferencePlan._fold(sconv, snorm)
+                    ref2 = ref_conv(src, sconv.weight.detach().cpu(), sscale, sshift, 2, False)
+                    assert_bf16_close(plan.tensor(op['out2']), ref2, 'fused shortcut %s' % op['out2'])
             else:   # conv + fused 1x1 tail: the intermediate (bf16) only exists inside the kernel
                 conv2, norm2 = op['tail_modules']
                 scale2, shift2 = InferencePlan._fold(conv2, norm2)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.lfd_abi_version() == 1
+    assert lib.lfd_abi_version() == 2
 
 
 def test_conv_query_is_host_only_and_rejects_unsupported():
@@ -75,7 +75,8 @@ def test_arena_reuses_and_coalesces():
     assert a.alloc(10) == o3 + 256
 
 
-@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 1 + 2 * 11 + 4 + 5 + 10), ('TT100K_L', 0 + 2 * 12 + 4 + 4 + 16)])   # stem 1x1 convs are fused tails
+# stem 1x1 convs are fused tails, the 4 shortcut convs are fused into their block's first conv
+@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 1 + 2 * 11 + 0 + 5 + 10), ('TT100K_L', 0 + 2 * 12 + 0 + 4 + 16)])
 def test_planner_builds_expected_graph(name, n_conv):
     model, _ = synth_model(name)
     plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
@@ -83,6 +84,7 @@ def test_planner_builds_expected_graph(name, n_conv):
     kinds = [r['kind'] for r in rows]
     assert kinds[0] == 'stem0' and kinds.count('stem0') == 1 and rows[0]['tail_cout'] == 64
     assert kinds.count('conv') == n_conv
+    assert len([r for r in rows if r['ds_cout']]) == 4
     levels = len(plan.level_sizes)
     merged = name.startswith('WIDERFACE')
     assert kinds.count('head_final') == (levels if merged else 2 * levels)
@@ -106,9 +108,11 @@ def test_planner_builds_expected_graph(name, n_conv):
     assert plan.workspace_bytes < plan.activation_bytes + plan.stats_bytes + 65536
     # branches (per-level neck + head chains) run concurrently with the backbone: their buffers must be disjoint from
     # every other branch's, and a tap read across branches is never recycled
-    # (branch 7 holds the residual blocks' shortcut convs, which run next to the block's first conv)
+    # (shortcut convs are fused into the block's first 3x3/s2 conv; where they cannot be, they run on branch 7)
+    fused_sc = [o for o in ops if o.get('ds_cout')]
     branches = sorted(set(plan.tensor_branch.values()))
-    assert branches == list(range(len(plan.level_sizes) + 1)) + [7]
+    assert branches == list(range(len(plan.level_sizes) + 1)) + ([] if fused_sc else [7])
+    assert all(o['ksize'] == 3 and o['stride'] == 2 and o.get('out2') in plan.offsets for o in fused_sc)
     for a in names:
         for b in names:
             if a < b and (plan.tensor_branch[a] != plan.tensor_branch[b] or a in plan.shared_tensors or b in plan.shared_tensors):
@@ -117,7 +121,7 @@ def test_planner_builds_expected_graph(name, n_conv):
                     assert oa + plan._tensors[a] <= ob or ob + plan._tensors[b] <= oa, (a, b)
     # shared = the level taps + per stage the block input read by the shortcut branch and the shortcut's output
     n_short = len([o for o in ops if o['branch'] == 7])
-    assert n_short > 0
+    assert n_short > 0 or fused_sc
     taps_and_inputs = set(o['inp'] for o in ops if o['branch'] == 7) | set(o['out'] for o in ops if o['branch'] == 7)
     assert plan.shared_tensors >= taps_and_inputs
     assert len(plan.shared_tensors) <= len(plan.level_sizes) + 2 * n_short

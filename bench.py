@@ -299,6 +299,14 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N * args.steps / float(te.item())
+    # how long the host->device copy of one batch takes on its own (diagnostic: is e2e bound by the PCIe link?)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(10):
+        det.slots[i % 2]['x'].copy_(host_pool[i % 2], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1) / 10
 
     if rank != 0:
         if world > 1:
@@ -370,7 +378,8 @@ def main():
                             pipelining='post-process of batch i overlaps the forward of batch i+1 (two streams, two output slots)'),
                 clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps,
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes,
-                         note='pinned host uint8 frames -> device -> detections -> pinned host, double buffered'),
+                         h2d_copy_alone_ms=h2d_ms, h2d_gbps=det.h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+                         note='pinned host uint8 frames -> device -> detections -> pinned host; copy / forward / post-process pipelined on three streams'),
                 roofline=roofline)
     if cpu is not None:
         line['cpu_baseline'] = cpu

@@ -59,8 +59,9 @@ enum { LFD_CONV_UMMA = 0, LFD_CONV_SIMT = 1 }; /* SIMT = cross-check kernel, val
 
 /* One fused layer.  Activations are bf16 NHWC at byte offsets into the caller's workspace.
  *   STEM0      3x3/s2 conv on the 3-channel image + shift (+ReLU), scale folded into the weights like CONV; in_off ignored (reads the external input);
- *              weight = bf16 packed [4][Cout][8]: k = 8*kc + j with k = (kh*3 + kw)*3 + ci, entries with k >= 27 are 0
- *              (the K = 27 im2col operand, padded to 32, is assembled from the raw image inside the kernel).
+ *              weight = bf16 packed [kh][2][Cout][8]: element (kh, kc, n, j) = weight of output n, input channel j % 4, filter
+ *              column kw = 2*kc + j/4 (zero for kw = 3 and for the padded 4th channel): the kernel keeps the image patch as
+ *              4-channel bf16 pixels and lets the UMMA address generator do the im2col (K = 16 per filter row).
  *   CONV       ksize in {1,3}, stride in {1,2}, pad = ksize/2; y = conv(x) + shift (+res) (ReLU) -> bf16;
  *              weight = bf16 packed [Cin/cc][ksize^2][cc/8][Cout][8] with cc from lfd_conv_query, ALREADY MULTIPLIED by the
  *              per-output-channel scale (folded BatchNorm); `scale` must be NULL; `shift` (fp32 [Cout], may be NULL) is rounded

@@ -7,13 +7,15 @@
 //
 // Formulation (NHWC bf16 activations, fp32 accumulate in TMEM):
 //   D[128 output pixels, Cout] = sum over taps (kh,kw) and channel chunks of  A_tap[128, 16] * W_tap[16, Cout]
-//   * persistent CTAs (1 per SM for 3x3, 2 per SM for the memory-bound 1x1 layers), warp-specialised:
-//       warps 0..E-1  epilogue   : TMEM -> regs -> scale/shift (+residual) (+ReLU) -> bf16 -> smem -> coalesced store
-//                                  (+ optional GroupNorm partial statistics of the stored tensor);
+//   * persistent CTAs (1 per SM for 3x3, 2 per SM for the 1x1 layers and the stem), warp-specialised:
+//       warps 0..E-1  epilogue   : TMEM -> regs -> (+residual) (+ReLU) -> bf16 -> the warp's own staging rows -> the warp's
+//                                  own TMA tensor store (+ optional GroupNorm partial statistics of the stored tensor);
 //                                  E = 4 (one warp per TMEM lane quarter) or 8 (two warps per quarter, each half the columns)
 //       warp  E       MMA issuer : one lane issues tcgen05.mma with pre-built descriptors, commits to mbarriers
 //       warps E+1..   producers  : cp.async (16 B, zero-fill = conv padding) of the input halo tile into the A ring;
 //                                  completion is signalled by cp.async.mbarrier.arrive (no thread waits on its own copies)
+//   * BatchNorm is folded on the host: scale into the bf16 weights, shift into one extra K=16 MMA against a constant
+//     "ones" operand, so the accumulator already holds scale * conv + shift.
 //   * the input halo tile is loaded ONCE per (tile, channel-chunk) into "pixel planes"
 //       plane[k-chunk][pixel][8 channels = 16 B]
 //     which is exactly the UMMA K-major / no-swizzle canonical layout (8-row core matrices of 16 B rows,
@@ -22,10 +24,14 @@
 //     Stride-2 convolutions de-interleave the halo into 4 row/column parity planes so that every tap is
 //     again a unit-stride view.  The plane pitch (LBO) is an ODD multiple of 16 B so that the 8 channel
 //     chunks of one pixel land in 8 different bank groups (conflict-free cp.async writes).
+//   * MODE_STEM: the 3-channel stem conv's im2col is done by the same address generator (see kStem* below).
+//   * optional second GEMM in the same launch: a trailing 1x1 conv fed from shared memory ("tail": stem0->stem1,
+//     stem2->stem3), or the residual block's 1x1/s2 shortcut conv on the centre tap (MODE_3X3S2, second output tensor).
 //   * weights: pre-packed on the host in [channel-chunk][tap][k-chunk][Cout][8] order and brought in by
 //     the TMA engine as 1-D bulk copies (cp.async.bulk -> UBLKCP), either once (resident) or per stage
 //     (streamed, for 3x3x128x128 which does not fit next to the A ring).
 //   * two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * programmatic dependent launch: the prologue (barriers, TMEM allocation, weight fetch) overlaps the previous layer.
 #include <stdlib.h>
 
 #include "conv_common.cuh"

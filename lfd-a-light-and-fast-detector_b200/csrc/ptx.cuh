@@ -59,9 +59,6 @@ LFD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 LFD_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 LFD_DEVINL void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 LFD_DEVINL void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-LFD_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ---------------------------------------------------------------- programmatic dependent launch
 LFD_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -75,15 +72,12 @@ LFD_DEVINL void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
 LFD_DEVINL void cp_async16_full(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
-LFD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 LFD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // The mbarrier receives one arrival (counted against its expected-arrival count, hence .noinc) once ALL cp.async
 // operations issued so far by this thread have completed -- the thread itself does not wait.
 LFD_DEVINL void cp_async_mbar_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-template <int N>
-LFD_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- 1-D bulk copy (TMA engine, UBLKCP)
 LFD_DEVINL void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -127,7 +121,6 @@ LFD_DEVINL void tma_load_4d(uint32_t dst_smem, const void* tmap, int c0, int c1,
                  : "memory");
 }
 LFD_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-LFD_DEVINL void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 LFD_DEVINL void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // at most N of this thread's bulk groups may still be READING their shared-memory source
 template <int N>

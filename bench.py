@@ -325,13 +325,13 @@ def main():
             det.infer(host_pool[i % 2])
         sync_all()
         t0 = time.perf_counter()
-        pending = None
+        pending = []                           # up to depth - 1 batches stay in flight behind the one being submitted
         for i in range(args.steps):
-            slot = det.submit(host_pool[i % 2])
-            if pending is not None:
-                det.collect(pending)
-            pending = slot
-        out = det.collect(pending)
+            pending.append(det.submit(host_pool[i % 2]))
+            if len(pending) >= det.depth:
+                det.collect(pending.pop(0))
+        while pending:
+            out = det.collect(pending.pop(0))
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

@@ -51,8 +51,9 @@ class ForwardPostPipeline(object):
 
 class StreamingDetector(object):
 
-    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None):
+    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None, depth=3):
         self.model = model
+        self.depth = max(2, int(depth))     # batches in flight: copy of i+2 | forward of i+1 | post-process + read-back of i
         self.device = device if device is not None else next(model.parameters()).device
         self.N, self.H, self.W = batch, height, width
         self.score_thr, self.iou_thr = float(score_thr), float(iou_thr)
@@ -67,7 +68,7 @@ class StreamingDetector(object):
         self.post.set_meta([width] * batch, [height] * batch, [1.0] * batch)
         self.pipe = ForwardPostPipeline(model, self.plan, self.post, self.score_thr, self.iou_thr)
         self.slots = []
-        for _ in range(2):
+        for _ in range(self.depth):
             self.slots.append(dict(
                 x=torch.empty((batch, height, width, 3), dtype=torch.uint8, device=dev),
                 out_dets=torch.empty((batch, self.max_out, 5), dtype=torch.float32).pin_memory(),
@@ -80,7 +81,7 @@ class StreamingDetector(object):
 
     def submit(self, frames_u8):
         """frames_u8: pinned (or pageable) host uint8 [N,H,W,3].  Enqueues copy + compute; returns the slot index."""
-        s = self.slots[self.step % 2]
+        s = self.slots[self.step % self.depth]
         if s['busy']:
             s['done'].synchronize()
         with torch.cuda.stream(self.copy_stream):
@@ -96,7 +97,7 @@ class StreamingDetector(object):
         self.pipe.enqueue(s['x'], wait_for=s['h2d'], consume=read_back)
         s['busy'] = True
         self.step += 1
-        return (self.step - 1) % 2
+        return (self.step - 1) % self.depth
 
     def collect(self, slot):
         """Blocks until the slot's results are on the host.  -> (dets [N,max_out,5], labels [N,max_out], counts [N])."""

@@ -182,3 +182,43 @@ def test_every_layer_within_one_bf16_ulp_teacher_forced(name, monkeypatch):
                 assert e[0] < 2e-3 and e[1] < 2e-4, ('head_final', op['inp'], e)
         checked += 1
     assert checked == len(plan._ops)
+
+
+def test_streaming_detector_matches_synchronous_path():
+    """lfd.pipeline.StreamingDetector (3 batches in flight on copy / forward / post-process streams, two output slots) returns,
+    batch by batch, exactly what the synchronous forward + detect returns -- no buffer is reused before its reader is done."""
+    from lfd.pipeline import StreamingDetector
+    model, _ = synth_model('WIDERFACE_XS', cls_bias=-1.0)
+    model.cuda()
+    n, h, w, iou = 2, 184, 248, 0.3
+    batches = [torch.from_numpy(np.stack([synth.synth_image_u8(h, w, seed=100 * b + i) for i in range(n)])) for b in range(7)]
+    with torch.no_grad():
+        cls, _ = model(batches[0].cuda())
+    thr = float(torch.quantile(cls.sigmoid().flatten().float(), 0.99))
+    ref = []
+    with torch.no_grad():
+        for xb in batches:
+            out = model(xb.cuda())
+            dets, labels, src, count, overflow = model.detect(out, [h] * n, [w] * n, [1.0] * n, thr, iou)
+            assert int(overflow.item()) == 0
+            ref.append((dets.cpu().clone(), labels.cpu().clone(), count.cpu().clone()))
+    det = StreamingDetector(model, n, h, w, thr, iou, max_out=512)
+    got, pending = [], []
+    with torch.no_grad():
+        for xb in batches:
+            pending.append(det.submit(xb.pin_memory()))
+            if len(pending) >= det.depth:
+                d, l, c = det.collect(pending.pop(0))
+                got.append((d.clone(), l.clone(), c.clone()))
+        while pending:
+            d, l, c = det.collect(pending.pop(0))
+            got.append((d.clone(), l.clone(), c.clone()))
+    assert len(got) == len(ref)
+    total = 0
+    for b, ((rd, rl, rc), (gd, gl, gc)) in enumerate(zip(ref, got)):
+        assert rc.tolist() == gc.tolist(), b
+        for i in range(n):
+            k = int(rc[i])
+            total += k
+            assert torch.equal(rd[i, :k], gd[i, :k]) and torch.equal(rl[i, :k].int(), gl[i, :k].int()), (b, i)
+    assert total > 0

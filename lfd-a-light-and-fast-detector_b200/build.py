@@ -29,6 +29,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _check_stack_frames(ptxas_log, limit=64):
+    """The warp-specialised conv kernel keeps everything in registers; a large stack frame means a role lambda was not
+    inlined and its closure lives in local memory (measured: the stem kernel 2.5x slower).  Fail the build instead."""
+    import re
+    name = None
+    for line in ptxas_log.splitlines():
+        m = re.search(r'Function properties for (\S+)', line)
+        if m:
+            name = m.group(1)
+        m = re.search(r'(\d+) bytes stack frame', line)
+        if m and name and 'conv_umma_kernel' in name and int(m.group(1)) > limit:
+            raise RuntimeError('%s has a %s-byte stack frame (limit %d): a role lambda is no longer inlined' % (name, m.group(1), limit))
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return OUT
@@ -36,13 +50,18 @@ def build(force=False, verbose=False):
     procs = []
     for s in SOURCES:
         o = os.path.join(CSRC, s.replace('.cu', '.o'))
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, s), '-o', o]
+        # conv_umma.cu is always compiled with ptxas -v: see _check_stack_frames
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if (verbose or s == 'conv_umma.cu') else []) + ['-c', os.path.join(CSRC, s), '-o', o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(o)
     for s, p in procs:
         out = p.communicate()[0].decode()
         if p.returncode != 0:
             raise RuntimeError('nvcc failed on %s:\n%s' % (s, out))
+        if s == 'conv_umma.cu':
+            _check_stack_frames(out)
+            if not verbose:
+                out = '\n'.join(l for l in out.splitlines() if 'ptxas info' not in l and 'bytes stack frame' not in l)
         if verbose or out.strip():
             sys.stderr.write(out)
     subprocess.check_call([NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart'])

@@ -41,6 +41,11 @@ namespace lfd {
 
 static constexpr int kProdThreads = 128;
 
+// The role bodies are lambdas that capture ~30 locals by reference.  If the compiler decides NOT to inline one of them (it did,
+// as soon as a lambda had three call sites or a second instantiation of the template existed) the closure is materialised in
+// local memory and the kernel runs 2-3x slower (a 230-byte stack frame in ptxas -v is the symptom).  Force it.
+#define LFD_LAMBDA_INLINE __attribute__((always_inline))
+
 // clock64() timeline of CTA 0 (tests/debug_trace.py); compiled in only with -DLFD_B200_TRACE (LFD_B200_TRACE=1 python build.py)
 #ifdef LFD_B200_TRACE
 #define LFD_TRACE(role, idx, slot) \
@@ -307,7 +312,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         if (lane == 0 && (stg0 & 1023u)) __trap();    // swizzle atoms need 1024-byte aligned staging regions
 
         // ---- tail phase 1: main accumulator -> bf16 operand of the fused 1x1 conv (never leaves the SM)
-        auto mid_tile = [&](uint32_t tc) {
+        auto mid_tile = [&](uint32_t tc) LFD_LAMBDA_INLINE {
             const uint32_t a = tc & 1, aph = (tc >> 1) & 1;
             const uint32_t b = p.n_a2 == 2 ? (tc & 1) : 0;
             const uint32_t use = p.n_a2 == 2 ? (tc >> 1) : tc;       // how often this operand buffer has been filled before
@@ -338,7 +343,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         // ---- final phase: accumulator (+residual) (+ReLU) -> bf16 staging rows -> TMA store (+ GroupNorm statistics)
         uint32_t store_count = 0;   // staging buffers alternate per STORE (a launch with a fused shortcut stores twice per tile)
         auto finish_tile = [&](int tile, uint32_t tc, uint64_t* bar_full, uint64_t* bar_empty, uint32_t col_base, const CUtensorMap* tmap,
-                               int var, bool first, bool last) {
+                               int var, bool first, bool last) LFD_LAMBDA_INLINE {
             const int n = fast_div(tile, p.magic_tpi);
             const int t = tile - n * p.tiles_per_img;
             int c1, c2 = 0;      // coordinates of this warp's first row: pixel index (flat) or (x, y)
@@ -375,7 +380,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             else __syncwarp();                    // lane 0 has seen the buffer free
             const uint32_t trow = tmem_base + lane_base + col_base + a * p.Cf + ch0;
             const uint32_t base = sbuf + pre;
-            auto publish = [&]() {
+            auto publish = [&]() LFD_LAMBDA_INLINE {
                 tc_fence_before_sync();
                 fence_proxy_async_smem();             // st.shared (generic proxy) -> TMA store (async proxy)
                 __syncwarp();
@@ -471,7 +476,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), cn2 * 16, 128);
         const uint64_t a2desc0 = umma_smem_desc(0, kA2Pitch, 128);
         const uint64_t b2desc0 = umma_smem_desc(smem_u32(smem + p.smem_w2_off), cn2 * 16, 128);
-        auto issue_tail = [&](uint32_t u) {
+        auto issue_tail = [&](uint32_t u) LFD_LAMBDA_INLINE {
             const uint32_t b = p.n_a2 == 2 ? (u & 1) : 0, use = p.n_a2 == 2 ? (u >> 1) : u;
             const uint32_t a2s = u & 1, a2ph = (u >> 1) & 1;
             mbar_wait(&a2_full[b], use & 1);
@@ -555,7 +560,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             const bool last_ok = ptid + (kStemPerThread - 1) * kProdThreads < kStemPix;   // this thread owns a pixel in the last round
             uint32_t raw[kStemPerThread][3];
             uint32_t okmask = 0;
-            auto fetch = [&](int tile) {
+            auto fetch = [&](int tile) LFD_LAMBDA_INLINE {
                 const int n = fast_div(tile, p.magic_tpi), t = tile - n * p.tiles_per_img;
                 const int ty = fast_div(t, p.magic_tx);
                 const int iy0 = 2 * ty * 16 - 1, ix0 = 2 * (t - ty * p.tiles_x) * 8 - 1;

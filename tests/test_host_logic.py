@@ -129,3 +129,53 @@ def test_planner_builds_expected_graph(name, n_conv):
     assert all(o.get('wait_mask', 0) == 1 for o in ops if o['branch'] == 7)
     waiters = [o for o in ops if o.get('wait_mask', 0) == 1 << 7]
     assert len(waiters) == n_short and all(o['branch'] == 0 and o['res'] is not None for o in waiters)
+
+
+@pytest.mark.parametrize('mode,n_fused', [('fast', 4), ('faster', 4), ('fastest', 0)])
+def test_planner_accepts_every_block_mode(mode, n_fused):
+    """FastBlock / FastestBlock are not used by any shipped config; the layer planner nevertheless builds a
+    valid plan for them (same kernels: 3x3 and 1x1 convs).  FastestBlock's first conv has C/2 outputs, so its shortcut conv
+    cannot ride on it and takes the auxiliary branch instead.  (Host logic only: the oracle restates the shipped configs.)"""
+    from lfd.model.backbone import LFDResNet
+    from lfd.model.neck import SimpleNeck
+    from lfd.model.head import LFDHead
+    from lfd.model.losses import FocalLoss, IoULoss
+    from lfd.model import LFD
+    bb = LFDResNet(block_mode=mode, stem_mode='fast', body_mode=None, input_channels=3, stem_channels=64, body_architecture=[2, 1, 1, 1],
+                   body_channels=[64, 64, 64, 128], out_indices=((0, 1), (1, 0), (2, 0), (3, 0)), frozen_stages=-1,
+                   activation_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='BatchNorm2d'), init_with_weight_file=None, norm_eval=False)
+    neck = SimpleNeck(num_neck_channels=128, num_input_channels_list=bb.num_output_channels_list,
+                      num_input_strides_list=bb.num_output_strides_list, norm_cfg=dict(type='BatchNorm2d'),
+                      activation_cfg=dict(type='ReLU', inplace=True))
+    head = LFDHead(num_classes=1, num_heads=4, num_input_channels=128, num_head_channels=128, num_conv_layers=2,
+                   activation_cfg=dict(type='ReLU', inplace=True), norm_cfg=dict(type='GroupNorm', num_groups=16), share_head_flag=True,
+                   merge_path_flag=True, classification_loss_type='FocalLoss', regression_loss_type='IoULoss')
+    model = LFD(backbone=bb, neck=neck, head=head, num_classes=1, regression_ranges=((0, 16), (16, 32), (32, 64), (64, 128)),
+                gray_range_factors=(0.9, 1.1), range_assign_mode='dist', point_strides=neck.num_output_strides_list,
+                classification_loss_func=FocalLoss(), regression_loss_func=IoULoss(), distance_to_bbox_mode='sigmoid')
+    plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
+    rows = plan.describe()
+    assert sum(1 for r in rows if r['ds_cout']) == n_fused
+    assert sum(1 for r in rows if r['kind'] == 'head_final') == 4
+    per_block = {'fast': 3, 'faster': 2, 'fastest': 2}[mode]
+    n_blocks = 5
+    n_short = 4 - n_fused
+    assert sum(1 for r in rows if r['kind'] == 'conv') == n_blocks * per_block + n_short + 4 + 2 * 4   # + necks + tower convs
+    for o in plan._ops:
+        if o.get('wait_mask') == 1 << 7:
+            assert o['res'] is not None and o['branch'] == 0
+
+
+def test_build_guard_rejects_large_stack_frames():
+    """build.py fails the build when a conv_umma_kernel instantiation has a large stack frame (a role lambda whose closure
+    landed in local memory made the stem kernel 2.5x slower, see conv_umma.cu LFD_LAMBDA_INLINE)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('lfd_build', os.path.join(ROOT, 'lfd-a-light-and-fast-detector_b200', 'build.py'))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    ok = 'ptxas info    : Function properties for _ZN3lfd16conv_umma_kernelILi4ELi4EEEvNS_14UmmaConvParamsE\n    16 bytes stack frame, 12 bytes spill stores, 24 bytes spill loads\n'
+    b._check_stack_frames(ok)
+    bad = ok.replace('16 bytes stack frame', '232 bytes stack frame')
+    with pytest.raises(RuntimeError):
+        b._check_stack_frames(bad)
+    b._check_stack_frames(bad.replace('conv_umma_kernel', 'some_other_kernel'))

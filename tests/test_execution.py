@@ -101,3 +101,37 @@ def test_gloo_world2_flat_bucket_allreduce_and_sharding():
         expect = (1 + 2) * (i + 1) / 2.0 if i < 3 else 1 * (i + 1) / 2.0     # last grad existed on rank 0 only
         assert torch.allclose(a, torch.full_like(a, expect))
     assert r0['shard'] == [0, 1, 2] and r1['shard'] == [3, 4] and r0['total'] == r1['total'] == 5
+
+
+def _worker_hook(rank, world_size, port, out):
+    """OptimizerHook on two gloo ranks: globally normalised losses -> SUM all-reduce; per-rank means -> average."""
+    from lfd.execution.hooks import OptimizerHook
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    res = {}
+    for flag in (True, False):
+        torch.manual_seed(0)
+        net = torch.nn.Linear(3, 1, bias=False)
+        net.loss_globally_normalised = flag
+        opt = torch.optim.SGD(net.parameters(), lr=1.0)
+        x = torch.full((1, 3), float(rank + 1))
+        loss = net(x).sum()                       # d loss / d w = x  -> rank 0: 1, rank 1: 2
+
+        class Ex(object):
+            config_dict = dict(model=net, optimizer=opt, loss=loss, epoch=0)
+        w0 = net.weight.detach().clone()
+        OptimizerHook(None, 10).after_train_iter(Ex())
+        res[flag] = (w0 - net.weight.detach()).clone()      # = the gradient that was applied (lr 1)
+    torch.save(res, out % rank)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_optimizer_hook_sums_globally_normalised_losses():
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'h%d.pt')
+        port = 31500 + os.getpid() % 2000
+        mp.spawn(_worker_hook, args=(2, port, out), nprocs=2, join=True)
+        r0, r1 = torch.load(out % 0, weights_only=False), torch.load(out % 1, weights_only=False)
+    for flag, expect in ((True, 3.0), (False, 1.5)):       # 1 + 2 summed / averaged
+        assert torch.equal(r0[flag], r1[flag])
+        assert torch.allclose(r0[flag], torch.full_like(r0[flag], expect))

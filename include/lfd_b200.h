@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LFD_B200_ABI_VERSION 2
+#define LFD_B200_ABI_VERSION 3
 #define LFD_MAX_LEVELS 8
 #define LFD_MAX_BRANCHES 8
 
@@ -56,6 +56,10 @@ int lfd_device_sm_count(void);
 enum { LFD_OP_STEM0 = 0, LFD_OP_CONV = 1, LFD_OP_GN_APPLY = 2, LFD_OP_HEAD_FINAL = 3 };
 enum { LFD_INPUT_F32_NCHW = 0, LFD_INPUT_U8_NHWC = 1 };
 enum { LFD_CONV_UMMA = 0, LFD_CONV_SIMT = 1 }; /* SIMT = cross-check kernel, validation only */
+/* 16-bit storage type of activations and packed weights (fp32 accumulation either way; same bytes, same tensor-core rate):
+ * bf16 = the north-star dtype; fp16 = 3 more mantissa bits, the variant that meets 1e-3 END TO END (DESIGN.md "Parity") and the
+ * dtype of BASELINE config 5 (WIDERFACE-XS fp16 4K sweep).  "bf16" in the op descriptions below reads "the plan's 16-bit type". */
+enum { LFD_DTYPE_BF16 = 0, LFD_DTYPE_FP16 = 1 };
 
 /* One fused layer.  Activations are bf16 NHWC at byte offsets into the caller's workspace.
  *   STEM0      3x3/s2 conv on the 3-channel image + shift (+ReLU), scale folded into the weights like CONV; in_off ignored (reads the external input);
@@ -99,7 +103,8 @@ typedef struct lfd_op {
     /* CONV 3x3/s2 only (no tail, no residual): the residual block's 1x1/s2 shortcut conv on the SAME input (Cin -> ds_cout,
      * ds_cout == Cout) is computed by the same kernel -- its input pixel is this conv's centre tap -- and stored (no ReLU) at
      * ds_out_off.  ds_weight = bf16 packed [Cin/8][ds_cout][8] with the BatchNorm scale folded in.  0 = none. */
-    int32_t ds_cout, ds_reserved;
+    int32_t ds_cout;
+    int32_t dtype; /* LFD_DTYPE_*: 16-bit type of this op's activations AND packed weights (every op of one plan uses the same) */
     int64_t ds_out_off;
     const void* ds_weight;
     const float* ds_shift;

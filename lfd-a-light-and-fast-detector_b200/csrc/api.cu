@@ -27,13 +27,13 @@ static int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(LFD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
-static int sm_count() {
-    static int cached = -1;
-    if (cached >= 0) return cached;
+static int sm_count() {   // of the CURRENT device (cached per device ordinal)
+    static int cached[kMaxDevices] = {};
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    if (cached[dev] > 0) return cached[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    cached = n;
+    cached[dev] = n;
     return n;
 }
 
@@ -111,6 +111,7 @@ extern "C" int lfd_conv_query(int N, int H, int W, int Cin, int Ho, int Wo, int 
 static int check_op(const lfd_op& o) {
     const int eh = (o.H + 2 * (o.ksize / 2) - o.ksize) / (o.stride > 0 ? o.stride : 1) + 1;
     const int ew = (o.W + 2 * (o.ksize / 2) - o.ksize) / (o.stride > 0 ? o.stride : 1) + 1;
+    if (o.dtype != LFD_DTYPE_BF16 && o.dtype != LFD_DTYPE_FP16) return fail(LFD_ERR_INVALID, "op dtype %d: expected LFD_DTYPE_BF16 or LFD_DTYPE_FP16", o.dtype);
     switch (o.kind) {
         case LFD_OP_STEM0:
             if (o.scale || o.tail_scale) return fail(LFD_ERR_INVALID, "conv scale must be folded into the packed weights (pass scale = NULL)");
@@ -163,14 +164,14 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
                 Stem0Params p;
                 p.in = input; p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.shift = o.shift;
-                p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu;
+                p.input_format = input_format; p.N = o.N; p.H = o.H; p.W = o.W; p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.relu = o.relu; p.f16 = o.dtype;
                 CUDA_TRY(stem0_launch(p, st));
             } else {
                 UmmaConvParams p = po.cp;
                 p.in_raw = input; p.input_format = input_format; p.in = nullptr;
                 p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off); p.res = nullptr;
                 p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight); p.shift = o.shift; p.stats = nullptr;
-                p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace; p.tl = tl;
+                p.relu = o.relu; p.gn_groups = 0; p.trace = g_trace; p.tl = tl; p.f16 = o.dtype;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 if (umma_conv_encode_maps(&p)) return fail(LFD_ERR_CUDA, "cuTensorMapEncodeTiled failed for the stem conv");
                 CUDA_TRY(umma_conv_launch(p, po.smem, po.grid, st));
@@ -185,11 +186,11 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             if (conv_impl == LFD_CONV_SIMT) {
                 if (o.tail_cout || o.ds_cout) return fail(LFD_ERR_UNSUPPORTED, "the SIMT cross-check kernels do not implement fused tails / shortcuts");
                 CUDA_TRY(simt_conv_launch(geom_of(o), o.cc, in, out, res, reinterpret_cast<const __nv_bfloat16*>(o.weight),
-                                          o.shift, stats, o.gn_groups, o.relu, st));
+                                          o.shift, stats, o.gn_groups, o.relu, o.dtype, st));
             } else {
                 UmmaConvParams p = po.cp;
                 p.in = in; p.out = out; p.res = res; p.w = reinterpret_cast<const __nv_bfloat16*>(o.weight);
-                p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups;
+                p.shift = o.shift; p.stats = stats; p.relu = o.relu; p.gn_groups = o.gn_groups; p.f16 = o.dtype;
                 p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.tail_weight); p.shift2 = o.tail_shift; p.relu2 = o.tail_relu;
                 if (o.ds_cout) {
                     p.w2 = reinterpret_cast<const __nv_bfloat16*>(o.ds_weight); p.shift2 = o.ds_shift; p.relu2 = 0;
@@ -205,7 +206,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             GnApplyParams p;
             p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off); p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
             p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
-            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f; p.tl = tl;
+            p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f; p.tl = tl; p.f16 = o.dtype;
             CUDA_TRY(gn_apply_launch(p, sm_count(), st));
             break;
         }
@@ -216,7 +217,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
             p.cls = o.n_cls ? cls : nullptr; p.reg = o.n_reg ? reg : nullptr;
             p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.n_out = o.n_cls + o.n_reg; p.n_cls = o.n_cls;
-            p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f; p.tl = tl;
+            p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f; p.tl = tl; p.f16 = o.dtype;
             if ((o.n_cls && !cls) || (o.n_reg && !reg)) return fail(LFD_ERR_INVALID, "head_final needs cls/reg output pointers");
             if (o.n_reg && o.n_reg != 4) return fail(LFD_ERR_INVALID, "head_final n_reg must be 0 or 4");
             CUDA_TRY(head_final_launch(p, st));

@@ -11,6 +11,7 @@ namespace lfd {
 enum { MODE_FLAT = 0, MODE_3X3S1 = 1, MODE_3X3S2 = 2, MODE_1X1S2 = 3, MODE_STEM = 4 };
 
 static constexpr int kMaxStages = 8;
+static constexpr int kMaxDevices = 64;   // per-device state (function attributes, SM counts) is indexed by the device ordinal
 // dynamic shared memory map of conv_umma_kernel (bytes)
 static constexpr int kSmemBarOff = 0;        // mbarriers + TMEM slot
 static constexpr int kSmemOnesOff = 512;      // constant A operand [2 k-chunks][128 rows][16 B]: column 0 = 1, everything else 0
@@ -59,6 +60,7 @@ struct alignas(64) UmmaConvParams {
     uint32_t smem_table_off, smem_bias_off, smem_bias2_off, smem_staging_off;
     uint32_t smem_w_off, smem_ring_off;
     int input_format;
+    int f16;                    // activation / weight type: 0 = bf16, 1 = IEEE fp16 (same bytes, kind::f16 either way)
 };
 
 // returns 0 when the geometry is supported by the tcgen05 kernel
@@ -70,6 +72,6 @@ int umma_conv_encode_maps(UmmaConvParams* p);
 // SIMT cross-check kernel (same packed weights, same epilogue semantics); debugging / validation only.
 cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out,
                              const __nv_bfloat16* res, const __nv_bfloat16* w, const float* shift,
-                             double* stats, int gn_groups, int relu, cudaStream_t st);
+                             double* stats, int gn_groups, int relu, int f16, cudaStream_t st);
 
 }  // namespace lfd

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
     for (int i = tid; i < 27 * Cout; i += kS0Threads) {
         const int k = i / Cout, nn = i % Cout;
         const int kh = k / 9, kw = (k / 3) % 3, ci = k % 3;   // packed [kh][kw / 2][Cout][(kw % 2) * 4 + ci]
-        wsm[i] = __bfloat162float(p.w[(((kh * 2 + (kw >> 1)) * Cout + nn) * 8) + (kw & 1) * 4 + ci]);
+        wsm[i] = up_lo_rt((uint32_t)reinterpret_cast<const unsigned short*>(p.w)[(((kh * 2 + (kw >> 1)) * Cout + nn) * 8) + (kw & 1) * 4 + ci], p.f16);
     }
     // input patch -> smem, rounded to bf16 (rounding point R0 of DESIGN.md)
     for (int i = tid; i < 3 * kS0PatchH * kS0PatchW; i += kS0Threads) {
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
                 float u = (float)reinterpret_cast<const uint8_t*>(p.in)[(((size_t)n * p.H + y) * p.W + x) * 3 + ci];
                 v = (u - 127.5f) * (1.0f / 127.5f);
             }
-            v = bf16_round(v);
+            v = round16_rt(v, p.f16);
         }
         patch[(ci * kS0PatchH + r) * kS0PatchPitch + c] = v;
     }
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
     }
     float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = 1.0f; sh[j] = p.shift ? bf16_round(p.shift[g * 8 + j]) : 0.f; }
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.0f; sh[j] = p.shift ? round16_rt(p.shift[g * 8 + j], p.f16) : 0.f; }
 #pragma unroll
     for (int ps = 0; ps < PASSES; ++ps) {
         const int lp = ps * PXP + lp0;
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kS0Threads) stem0_kernel(const Stem0Params p) 
             if (p.relu) o[j] = fmaxf(o[j], 0.f);
         }
         uint4 ov;
-        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
-        ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+        ov.x = pack2_rt(o[0], o[1], p.f16); ov.y = pack2_rt(o[2], o[3], p.f16);
+        ov.z = pack2_rt(o[4], o[5], p.f16); ov.w = pack2_rt(o[6], o[7], p.f16);
         *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Ho + oy) * p.Wo + ox) * Cout + g * 8) = ov;
     }
 }
@@ -135,6 +135,7 @@ __device__ __forceinline__ void gn_mean_rstd(const double* stats, int n, int g, 
     *rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     __shared__ float s_mean[32], s_rstd[32];
     LFD_TL_BEGIN(p.tl);
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int g = (int)(i % cpr);
         const uint4 q = in[i];
-        float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+        float f[8] = {up_lo<F16>(q.x), up_hi<F16>(q.x), up_lo<F16>(q.y), up_hi<F16>(q.y), up_lo<F16>(q.z), up_hi<F16>(q.z), up_lo<F16>(q.w), up_hi<F16>(q.w)};
         const float m = s_mean[g], r = s_rstd[g];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyParams p) {
             f[j] = fmaxf(y, 0.f);
         }
         uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        o.x = pack2<F16>(f[0], f[1]); o.y = pack2<F16>(f[2], f[3]); o.z = pack2<F16>(f[4], f[5]); o.w = pack2<F16>(f[6], f[7]);
         out[i] = o;
     }
     LFD_TL_END(p.tl);
@@ -172,7 +173,8 @@ cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st
     const int cap = (8 * num_sms + p.N - 1) / p.N;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    gn_apply_kernel<<<dim3(bx, p.N), 256, 0, st>>>(p);
+    if (p.f16) gn_apply_kernel<true><<<dim3(bx, p.N), 256, 0, st>>>(p);
+    else gn_apply_kernel<false><<<dim3(bx, p.N), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -186,6 +188,7 @@ static constexpr int kHfMaxC = 128;
 
 // 8 threads share one pixel (16 channels each): coalesced 256-byte rows, the 16-channel weight slice of every output
 // is a broadcast-friendly 64-byte shared-memory read, partial dot products are combined with 3 warp shuffles.
+template <bool F16>
 __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalParams p) {
     extern __shared__ __align__(16) float hf_smem[];
     float* wsm = hf_smem;                                 // [n_out][C]
@@ -212,13 +215,13 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
             const uint4* src = reinterpret_cast<const uint4*>(p.in + ((size_t)n * p.HW + pix) * p.C + sl * 16);
             q0 = src[0]; q1 = src[1];
         }
-        float f[16] = {bf16_lo(q0.x), bf16_hi(q0.x), bf16_lo(q0.y), bf16_hi(q0.y), bf16_lo(q0.z), bf16_hi(q0.z), bf16_lo(q0.w), bf16_hi(q0.w),
-                       bf16_lo(q1.x), bf16_hi(q1.x), bf16_lo(q1.y), bf16_hi(q1.y), bf16_lo(q1.z), bf16_hi(q1.z), bf16_lo(q1.w), bf16_hi(q1.w)};
+        float f[16] = {up_lo<F16>(q0.x), up_hi<F16>(q0.x), up_lo<F16>(q0.y), up_hi<F16>(q0.y), up_lo<F16>(q0.z), up_hi<F16>(q0.z), up_lo<F16>(q0.w), up_hi<F16>(q0.w),
+                       up_lo<F16>(q1.x), up_hi<F16>(q1.x), up_lo<F16>(q1.y), up_hi<F16>(q1.y), up_lo<F16>(q1.z), up_hi<F16>(q1.z), up_lo<F16>(q1.w), up_hi<F16>(q1.w)};
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             float y = (f[j] - (j < 8 ? m0 : m1)) * (j < 8 ? r0 : r1);
             y = fmaf(y, ga[j], be[j]);
-            a[k][j] = bf16_round(fmaxf(y, 0.f));          // rounding point Rg
+            a[k][j] = round16<F16>(fmaxf(y, 0.f));        // rounding point Rg
         }
     }
     for (int o0 = 0; o0 < p.n_out; o0 += 8) {
@@ -275,14 +278,19 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
     if (p.C != kHfMaxC || p.groups != 16) return cudaErrorInvalidValue;   // 128 channels, 16 groups of 8 (every shipped head)
     const size_t smem = ((size_t)p.n_out * p.C + 64) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(head_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    static bool attr[kMaxDevices] = {};   // per-device function attribute
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(head_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(head_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr[dev] = true;
     }
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
-    head_final_kernel<<<dim3((p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock, p.N), kHfThreads, smem, st>>>(p);
+    const dim3 grid((p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock, p.N);
+    if (p.f16) head_final_kernel<true><<<grid, kHfThreads, smem, st>>>(p);
+    else head_final_kernel<false><<<grid, kHfThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -292,7 +300,8 @@ cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
 __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, const __nv_bfloat16* __restrict__ in,
                                                         __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ res,
                                                         const __nv_bfloat16* __restrict__ w, const float* __restrict__ shift,
-                                                        double* stats, int gn_groups, int relu) {
+                                                        double* stats, int gn_groups, int relu, int f16i) {
+    const bool f16 = f16i != 0;
     const int ng = g.Cout >> 3;
     const size_t total = (size_t)g.N * g.Ho * g.Wo * ng;
     const int taps = g.ksize * g.ksize, pad = g.ksize / 2, cpc = Cc >> 3, n_cc = g.Cin / Cc;
@@ -308,16 +317,16 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, cons
                 const __nv_bfloat16* ip = in + (((size_t)n * g.H + iy) * g.W + ix) * g.Cin + cc * Cc;
                 for (int kc = 0; kc < cpc; ++kc) {
                     const uint4 xv = *reinterpret_cast<const uint4*>(ip + kc * 8);
-                    const float xf[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
-                                         bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+                    const float xf[8] = {up_lo_rt(xv.x, f16), up_hi_rt(xv.x, f16), up_lo_rt(xv.y, f16), up_hi_rt(xv.y, f16),
+                                         up_lo_rt(xv.z, f16), up_hi_rt(xv.z, f16), up_lo_rt(xv.w, f16), up_hi_rt(xv.w, f16)};
                     const __nv_bfloat16* wp = w + ((((size_t)cc * taps + tap) * cpc + kc) * g.Cout + og * 8) * 8;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint4 wv = *reinterpret_cast<const uint4*>(wp + j * 8);
-                        acc[j] = fmaf(xf[0], bf16_lo(wv.x), acc[j]); acc[j] = fmaf(xf[1], bf16_hi(wv.x), acc[j]);
-                        acc[j] = fmaf(xf[2], bf16_lo(wv.y), acc[j]); acc[j] = fmaf(xf[3], bf16_hi(wv.y), acc[j]);
-                        acc[j] = fmaf(xf[4], bf16_lo(wv.z), acc[j]); acc[j] = fmaf(xf[5], bf16_hi(wv.z), acc[j]);
-                        acc[j] = fmaf(xf[6], bf16_lo(wv.w), acc[j]); acc[j] = fmaf(xf[7], bf16_hi(wv.w), acc[j]);
+                        acc[j] = fmaf(xf[0], up_lo_rt(wv.x, f16), acc[j]); acc[j] = fmaf(xf[1], up_hi_rt(wv.x, f16), acc[j]);
+                        acc[j] = fmaf(xf[2], up_lo_rt(wv.y, f16), acc[j]); acc[j] = fmaf(xf[3], up_hi_rt(wv.y, f16), acc[j]);
+                        acc[j] = fmaf(xf[4], up_lo_rt(wv.z, f16), acc[j]); acc[j] = fmaf(xf[5], up_hi_rt(wv.z, f16), acc[j]);
+                        acc[j] = fmaf(xf[6], up_lo_rt(wv.w, f16), acc[j]); acc[j] = fmaf(xf[7], up_hi_rt(wv.w, f16), acc[j]);
                     }
                 }
             }
@@ -325,18 +334,18 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, cons
         const size_t off = pix * g.Cout + og * 8;
         uint4 rv = make_uint4(0, 0, 0, 0);
         if (res) rv = *reinterpret_cast<const uint4*>(res + off);
-        const float rf[8] = {bf16_lo(rv.x), bf16_hi(rv.x), bf16_lo(rv.y), bf16_hi(rv.y), bf16_lo(rv.z), bf16_hi(rv.z), bf16_lo(rv.w), bf16_hi(rv.w)};
+        const float rf[8] = {up_lo_rt(rv.x, f16), up_hi_rt(rv.x, f16), up_lo_rt(rv.y, f16), up_hi_rt(rv.y, f16), up_lo_rt(rv.z, f16), up_hi_rt(rv.z, f16), up_lo_rt(rv.w, f16), up_hi_rt(rv.w, f16)};
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            o[j] = acc[j] + (shift ? bf16_round(shift[og * 8 + j]) : 0.f) + rf[j];
+            o[j] = acc[j] + (shift ? round16_rt(shift[og * 8 + j], f16) : 0.f) + rf[j];
             if (relu) o[j] = fmaxf(o[j], 0.f);
-            o[j] = bf16_round(o[j]);
+            o[j] = round16_rt(o[j], f16);
             s1 += o[j];
             s2 = fmaf(o[j], o[j], s2);
         }
         uint4 ov;
-        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]); ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+        ov.x = pack2_rt(o[0], o[1], f16); ov.y = pack2_rt(o[2], o[3], f16); ov.z = pack2_rt(o[4], o[5], f16); ov.w = pack2_rt(o[6], o[7], f16);
         *reinterpret_cast<uint4*>(out + off) = ov;
         if (stats) {  // group size 8 == this thread's channel group
             atomicAdd(stats + ((size_t)n * gn_groups + og) * 2, (double)s1);
@@ -347,12 +356,12 @@ __global__ void __launch_bounds__(256) simt_conv_kernel(ConvGeom g, int Cc, cons
 
 cudaError_t simt_conv_launch(const ConvGeom& g, int Cc, const __nv_bfloat16* in, __nv_bfloat16* out, const __nv_bfloat16* res,
                              const __nv_bfloat16* w, const float* shift, double* stats, int gn_groups,
-                             int relu, cudaStream_t st) {
+                             int relu, int f16, cudaStream_t st) {
     const size_t total = (size_t)g.N * g.Ho * g.Wo * (g.Cout >> 3);
     size_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    simt_conv_kernel<<<(int)blocks, 256, 0, st>>>(g, Cc, in, out, res, w, shift, stats, gn_groups, relu);
+    simt_conv_kernel<<<(int)blocks, 256, 0, st>>>(g, Cc, in, out, res, w, shift, stats, gn_groups, relu, f16);
     return cudaGetLastError();
 }
 

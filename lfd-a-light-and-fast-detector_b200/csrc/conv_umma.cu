@@ -81,18 +81,18 @@ static constexpr int kStemPatchBytes = ((kStemRows * kStemRowBytes + 127) / 128)
 static constexpr uint32_t kA2Pitch = 129 * 16;
 
 // 8 accumulator columns (+ 8 residual values) -> packed bf16; ReLU is fused into the conversion (cvt.rn.relu)
-template <bool RELU>
+template <bool RELU, bool F16>
 LFD_DEVINL uint4 pack8(const float* v) {
     uint4 o;
-    if (RELU) { o.x = pack_bf16x2_relu(v[0], v[1]); o.y = pack_bf16x2_relu(v[2], v[3]); o.z = pack_bf16x2_relu(v[4], v[5]); o.w = pack_bf16x2_relu(v[6], v[7]); }
-    else { o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]); }
+    if (RELU) { o.x = pack2_relu<F16>(v[0], v[1]); o.y = pack2_relu<F16>(v[2], v[3]); o.z = pack2_relu<F16>(v[4], v[5]); o.w = pack2_relu<F16>(v[6], v[7]); }
+    else { o.x = pack2<F16>(v[0], v[1]); o.y = pack2<F16>(v[2], v[3]); o.z = pack2<F16>(v[4], v[5]); o.w = pack2<F16>(v[6], v[7]); }
     return o;
 }
-template <bool RELU>
+template <bool RELU, bool F16>
 LFD_DEVINL uint4 pack8_res(const float* v, uint4 rv) {
-    float o[8] = {v[0] + bf16_lo(rv.x), v[1] + bf16_hi(rv.x), v[2] + bf16_lo(rv.y), v[3] + bf16_hi(rv.y),
-                  v[4] + bf16_lo(rv.z), v[5] + bf16_hi(rv.z), v[6] + bf16_lo(rv.w), v[7] + bf16_hi(rv.w)};
-    return pack8<RELU>(o);
+    float o[8] = {v[0] + up_lo<F16>(rv.x), v[1] + up_hi<F16>(rv.x), v[2] + up_lo<F16>(rv.y), v[3] + up_hi<F16>(rv.y),
+                  v[4] + up_lo<F16>(rv.z), v[5] + up_hi<F16>(rv.z), v[6] + up_lo<F16>(rv.w), v[7] + up_hi<F16>(rv.w)};
+    return pack8<RELU, F16>(o);
 }
 
 // Epilogue inner loop of one warp: NC accumulator columns of its TMEM lane quarter (row = lane) -> (+residual) (+ReLU) -> bf16
@@ -101,7 +101,7 @@ LFD_DEVINL uint4 pack8_res(const float* v, uint4 rv) {
 //                    RES adds the residual chunk found at the same place (TMA-loaded before), STATS accumulates the sum and
 //                    the sum of squares of the stored values per chunk into st[k] / st[NC/8 + k] (rows with !valid count 0)
 //   OPERAND = true : K-major A operand of the fused tail, chunk k at base + k * kA2Pitch
-template <int NC, bool RELU, bool RES, bool STATS, bool OPERAND, int MAXB>
+template <int NC, bool RELU, bool RES, bool STATS, bool OPERAND, int MAXB, bool F16>
 LFD_DEVINL void drain(uint32_t taddr, uint32_t base, bool valid, float* st) {
     constexpr int BATCH = NC < MAXB ? NC : MAXB;   // columns in flight per tcgen05.wait::ld
 #pragma unroll
@@ -114,10 +114,10 @@ LFD_DEVINL void drain(uint32_t taddr, uint32_t base, bool valid, float* st) {
         for (int h = 0; h < BATCH / 8; ++h) {
             const int k = (c0 >> 3) + h;
             const uint32_t addr = OPERAND ? base + k * kA2Pitch : (base ^ (uint32_t)((k & 7) << 4)) + (uint32_t)(k >> 3) * 4096u;
-            const uint4 o = RES ? pack8_res<RELU>(v + h * 8, lds128(addr)) : pack8<RELU>(v + h * 8);
+            const uint4 o = RES ? pack8_res<RELU, F16>(v + h * 8, lds128(addr)) : pack8<RELU, F16>(v + h * 8);
             sts128(addr, o);
             if (STATS) {
-                const float f[8] = {bf16_lo(o.x), bf16_hi(o.x), bf16_lo(o.y), bf16_hi(o.y), bf16_lo(o.z), bf16_hi(o.z), bf16_lo(o.w), bf16_hi(o.w)};
+                const float f[8] = {up_lo<F16>(o.x), up_hi<F16>(o.x), up_lo<F16>(o.y), up_hi<F16>(o.y), up_lo<F16>(o.z), up_hi<F16>(o.z), up_lo<F16>(o.w), up_hi<F16>(o.w)};
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
@@ -171,7 +171,7 @@ __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of
     return 0;
 }
 
-template <int MODE, int EPI_WARPS>
+template <int MODE, int EPI_WARPS, bool F16>
 __global__ void __launch_bounds__(EPI_WARPS * 32 + 32 + kProdThreads, (EPI_WARPS == 4 ? 2 : 1))
 conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     constexpr int kEpiThreads = EPI_WARPS * 32;
@@ -231,14 +231,14 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     // constant A operand (column 0 = 1) with a B operand whose k = 0 row holds the bf16 shift.  The epilogue is then just
     // (+residual) ReLU + convert.
     for (int i = tid; i < 256; i += kThreads)
-        reinterpret_cast<uint4*>(smem + kSmemOnesOff)[i] = i < 128 ? make_uint4(0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(smem + kSmemOnesOff)[i] = i < 128 ? make_uint4(F16 ? 0x00003C00u : 0x00003F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 2 * p.Cout; i += kThreads) {
-        const uint32_t b = (i < p.Cout && p.shift) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift[i])) : 0u;
+        const uint32_t b = (i < p.Cout && p.shift) ? bits16<F16>(p.shift[i]) : 0u;
         reinterpret_cast<uint4*>(smem + p.smem_bias_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     const int cn2 = p.Cout2 + p.Cout3;      // second GEMM of the launch: fused 1x1 tail or fused 1x1/s2 shortcut (never both)
     for (int i = tid; i < 2 * cn2; i += kThreads) {
-        const uint32_t b = (i < cn2 && p.shift2) ? (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(p.shift2[i])) : 0u;
+        const uint32_t b = (i < cn2 && p.shift2) ? bits16<F16>(p.shift2[i]) : 0u;
         reinterpret_cast<uint4*>(smem + p.smem_bias2_off)[i] = make_uint4(b, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();   // these operands are read by tcgen05.mma (async proxy)
@@ -322,14 +322,14 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             const uint32_t trow = tmem_base + lane_base + a * p.Cout + chalf * cw1;
             const uint32_t dst = smem_u32(smem + p.smem_a2_off) + b * p.a2_bytes + (uint32_t)(quarter * 32 + lane) * 16 + (uint32_t)((chalf * cw1) >> 3) * kA2Pitch;
             switch (variant1) {
-                case 0: drain<16, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 1: drain<32, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 2: drain<64, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 3: drain<128, false, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 4: drain<16, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 5: drain<32, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                case 6: drain<64, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
-                default: drain<128, true, false, false, true, MAXB>(trow, dst, true, nullptr); break;
+                case 0: drain<16, false, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 1: drain<32, false, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 2: drain<64, false, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 3: drain<128, false, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 4: drain<16, true, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 5: drain<32, true, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                case 6: drain<64, true, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
+                default: drain<128, true, false, false, true, MAXB, F16>(trow, dst, true, nullptr); break;
             }
             tc_fence_before_sync();
             fence_proxy_async_smem();           // st.shared (generic proxy) -> tcgen05.mma (async proxy)
@@ -396,26 +396,26 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             // GroupNorm partial sums are taken over the STORED (bf16) values; one group = one 16-byte chunk (8 channels)
             double* sdst = p.stats ? p.stats + ((size_t)n * p.gn_groups + (ch0 >> 3)) * 2 : nullptr;
             switch (var) {
-                case 0: drain<16, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 1: drain<32, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 2: drain<64, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 3: drain<128, false, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 4: drain<16, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 5: drain<32, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 6: drain<64, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 7: drain<128, true, false, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 8: drain<16, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 9: drain<32, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 10: drain<64, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 11: drain<128, false, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 12: drain<16, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 13: drain<32, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 14: drain<64, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 15: drain<128, true, true, false, false, MAXB>(trow, base, valid, nullptr); break;
-                case 16: { float st[4]; drain<16, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<16>(st, lane, sdst); } break;
-                case 17: { float st[8]; drain<32, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<32>(st, lane, sdst); } break;
-                case 18: { float st[16]; drain<64, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<64>(st, lane, sdst); } break;
-                default: { float st[32]; drain<128, false, false, true, false, MAXB>(trow, base, valid, st); publish(); stats_flush<128>(st, lane, sdst); } break;
+                case 0: drain<16, false, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 1: drain<32, false, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 2: drain<64, false, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 3: drain<128, false, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 4: drain<16, true, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 5: drain<32, true, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 6: drain<64, true, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 7: drain<128, true, false, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 8: drain<16, false, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 9: drain<32, false, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 10: drain<64, false, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 11: drain<128, false, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 12: drain<16, true, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 13: drain<32, true, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 14: drain<64, true, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 15: drain<128, true, true, false, false, MAXB, F16>(trow, base, valid, nullptr); break;
+                case 16: { float st[4]; drain<16, false, false, true, false, MAXB, F16>(trow, base, valid, st); publish(); stats_flush<16>(st, lane, sdst); } break;
+                case 17: { float st[8]; drain<32, false, false, true, false, MAXB, F16>(trow, base, valid, st); publish(); stats_flush<32>(st, lane, sdst); } break;
+                case 18: { float st[16]; drain<64, false, false, true, false, MAXB, F16>(trow, base, valid, st); publish(); stats_flush<64>(st, lane, sdst); } break;
+                default: { float st[32]; drain<128, false, false, true, false, MAXB, F16>(trow, base, valid, st); publish(); stats_flush<128>(st, lane, sdst); } break;
             }
             if (var < 16) publish();
             if (tid == 0) LFD_TRACE(2, tc, 2);
@@ -446,7 +446,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         // ============================================================== MMA ISSUER
         // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; one elected
         // lane issues the tcgen05 instructions.
-        const uint32_t idesc = umma_idesc_bf16(128, p.Cout);
+        const uint32_t idesc = umma_idesc_16(128, p.Cout, F16);
         const uint32_t lbo_b = p.Cout * 16;
         // descriptors differ only in the 14-bit start-address field (bytes >> 4): pre-compute everything else
         const uint64_t adesc0 = umma_smem_desc(0, p.lbo_a, p.sbo_a);
@@ -470,7 +470,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
             mbar_wait(wbar, 0);
         }
         // fused 1x1 tail: D2[128 x Cout2] = A2[128 x Cout] . W2, A2 written by the epilogue warps (mid_tile)
-        const uint32_t idesc2 = umma_idesc_bf16(128, cn2 ? cn2 : 16);
+        const uint32_t idesc2 = umma_idesc_16(128, cn2 ? cn2 : 16, F16);
         const uint64_t ones_desc = umma_smem_desc(smem_u32(smem + kSmemOnesOff), 2048, 128);
         const uint64_t bias_desc = umma_smem_desc(smem_u32(smem + p.smem_bias_off), lbo_b, 128);
         const uint64_t bias2_desc = umma_smem_desc(smem_u32(smem + p.smem_bias2_off), cn2 * 16, 128);
@@ -617,7 +617,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
                         f[k] = u8 ? ((float)raw[j][k] - 127.5f) * (1.0f / 127.5f) : __uint_as_float(raw[j][k]);
                         if (!((okmask >> j) & 1u)) f[k] = 0.f;        // conv zero padding (of the normalised image)
                     }
-                    const uint32_t lo = pack_bf16x2(f[0], f[1]), hi = pack_bf16x2(f[2], 0.f);   // rounding point R0
+                    const uint32_t lo = pack2<F16>(f[0], f[1]), hi = pack2<F16>(f[2], 0.f);   // rounding point R0
                     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst0 + j * (kProdThreads * 8)), "r"(lo), "r"(hi) : "memory");
                 }
                 fence_proxy_async_smem();       // generic-proxy st.shared -> tcgen05.mma reads
@@ -944,13 +944,16 @@ int umma_conv_encode_maps(UmmaConvParams* p) {
     return 0;
 }
 
-template <int MODE, int EPI_WARPS>
-static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
+template <int MODE, int EPI_WARPS, bool F16>
+static cudaError_t launch_mode_t(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one flag per device ordinal
+    static bool configured[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel<MODE, EPI_WARPS, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(224 * 1024));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     static const bool use_pdl = getenv("LFD_B200_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg;
@@ -964,7 +967,12 @@ static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = use_pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, EPI_WARPS>, p);
+    return cudaLaunchKernelEx(&cfg, conv_umma_kernel<MODE, EPI_WARPS, F16>, p);
+}
+
+template <int MODE, int EPI_WARPS>
+static cudaError_t launch_mode(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {
+    return p.f16 ? launch_mode_t<MODE, EPI_WARPS, true>(p, smem, grid, st) : launch_mode_t<MODE, EPI_WARPS, false>(p, smem, grid, st);
 }
 
 cudaError_t umma_conv_launch(const UmmaConvParams& p, size_t smem, int grid, cudaStream_t st) {

@@ -14,6 +14,7 @@ struct Stem0Params {
     const __nv_bfloat16* w;    // packed [kh][2][Cout][8]: element (kh, kc, n, j) = weight (n, ci = j % 4, kh, kw = 2 kc + j / 4), 0 for kw = 3 or ci = 3
     const float* shift;        // fp32 [Cout] or null (BatchNorm scale is folded into w); applied as bf16
     int input_format, N, H, W, Ho, Wo, Cout, relu;
+    int f16;                   // 16-bit type of weights / output: 0 = bf16, 1 = fp16
 };
 cudaError_t stem0_launch(const Stem0Params& p, cudaStream_t st);
 
@@ -25,6 +26,7 @@ struct GnApplyParams {
     const float* beta;
     int N, HW, C, groups;
     float eps;
+    int f16;
     unsigned long long* tl;    // debugging time-line slot or null
 };
 cudaError_t gn_apply_launch(const GnApplyParams& p, int num_sms, cudaStream_t st);
@@ -41,6 +43,7 @@ struct HeadFinalParams {
     float* reg;                // (N, P, 4) or null
     int N, HW, C, groups, n_out, n_cls, P, point_off, cls_stride;
     float eps;
+    int f16;
     unsigned long long* tl;    // debugging time-line slot or null
 };
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st);

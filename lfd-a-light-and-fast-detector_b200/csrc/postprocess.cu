@@ -13,6 +13,7 @@
 //                       score-descending order.
 // Arithmetic that decides kept indices is written with explicit _rn intrinsics so that nvcc cannot contract
 // it into FMAs (the reference computes every step in separately rounded fp32).
+#include "conv_common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -295,11 +296,13 @@ size_t nms_scratch_stride(int cap, int cap_pow2) {
 
 cudaError_t nms_launch(const NmsParams& p, int n_images, cudaStream_t st) {
     const size_t smem = kNmsMaskOff + (size_t)kNmsMaskMax * 128;   // 160 KB (>= the 4096-entry sweep layout, 116 KB)
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[kMaxDevices] = {};   // per-device function attribute
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    if (!attr[dev]) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr[dev] = true;
     }
     nms_kernel<<<n_images, kNmsThreads, smem, st>>>(p);
     return cudaGetLastError();

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace lfd {
@@ -148,13 +149,13 @@ LFD_DEVINL uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint3
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
     return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
-// bf16 x bf16 -> fp32, both operands K-major, M = 128, N = n.
-LFD_DEVINL constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
-    return (1u << 4)            // c_format  = F32
-           | (1u << 7)          // a_format  = BF16
-           | (1u << 10)         // b_format  = BF16
-           | ((n >> 3) << 17)   // N / 8
-           | ((m >> 4) << 24);  // M / 16
+// bf16 x bf16 (or fp16 x fp16) -> fp32, both operands K-major, M = 128, N = n.
+LFD_DEVINL constexpr uint32_t umma_idesc_16(uint32_t m, uint32_t n, bool f16) {
+    return (1u << 4)                    // c_format  = F32
+           | ((f16 ? 0u : 1u) << 7)     // a_format  = F16 (0) / BF16 (1)
+           | ((f16 ? 0u : 1u) << 10)    // b_format
+           | ((n >> 3) << 17)           // N / 8
+           | ((m >> 4) << 24);          // M / 16
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
@@ -223,5 +224,35 @@ LFD_DEVINL uint4 lds128(uint32_t addr) {
 LFD_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 LFD_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 LFD_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ---------------------------------------------------------------- 16-bit activation type: bf16 (F16 = false) or IEEE fp16 (true)
+// Same bytes, same tensor-core rate; fp16 carries 3 more mantissa bits (the values on this path are post-BatchNorm / ReLU
+// activations and folded weights of O(1), far inside the fp16 range).
+LFD_DEVINL uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // saturates at +-65504 instead of producing inf
+    return d;
+}
+LFD_DEVINL uint32_t pack_f16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+LFD_DEVINL float f16_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
+LFD_DEVINL float f16_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+template <bool F16> LFD_DEVINL uint32_t pack2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16> LFD_DEVINL uint32_t pack2_relu(float lo, float hi) { return F16 ? pack_f16x2_relu(lo, hi) : pack_bf16x2_relu(lo, hi); }
+template <bool F16> LFD_DEVINL float up_lo(uint32_t v) { return F16 ? f16_lo(v) : bf16_lo(v); }
+template <bool F16> LFD_DEVINL float up_hi(uint32_t v) { return F16 ? f16_hi(v) : bf16_hi(v); }
+template <bool F16> LFD_DEVINL float round16(float x) { return F16 ? __half2float(__float2half_rn(x)) : bf16_round(x); }
+// the 16 raw bits of x rounded to the activation type
+template <bool F16> LFD_DEVINL uint32_t bits16(float x) {
+    return F16 ? (uint32_t)__half_as_ushort(__float2half_rn(x)) : (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+// run-time flavours for the cross-check kernels
+LFD_DEVINL float up_lo_rt(uint32_t v, bool f16) { return f16 ? f16_lo(v) : bf16_lo(v); }
+LFD_DEVINL float up_hi_rt(uint32_t v, bool f16) { return f16 ? f16_hi(v) : bf16_hi(v); }
+LFD_DEVINL uint32_t pack2_rt(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+LFD_DEVINL float round16_rt(float x, bool f16) { return f16 ? __half2float(__float2half_rn(x)) : bf16_round(x); }
 
 }  // namespace lfd

@@ -30,12 +30,15 @@ def _conv_out(size, k, s):
     return (size + 2 * (k // 2) - k) // s + 1
 
 
-def pack_conv_weight(weight, cc):
-    """[Cout, Cin, k, k] float -> bf16 [Cin/cc][k*k][cc/8][Cout][8], the B-operand order of conv_umma.cu
+ACT_DTYPES = {'bf16': (torch.bfloat16, nat.DTYPE_BF16), 'fp16': (torch.float16, nat.DTYPE_FP16)}
+
+
+def pack_conv_weight(weight, cc, dtype=torch.bfloat16):
+    """[Cout, Cin, k, k] float -> 16-bit [Cin/cc][k*k][cc/8][Cout][8], the B-operand order of conv_umma.cu
     (K-major, no-swizzle core matrices; one contiguous slice per channel chunk so that it can be bulk-copied)."""
     cout, cin, k, _ = weight.shape
     wt = weight.detach().float().cpu().permute(2, 3, 1, 0).reshape(k * k, cin // cc, cc // 8, 8, cout)
-    return wt.permute(1, 0, 2, 4, 3).contiguous().to(torch.bfloat16)
+    return wt.permute(1, 0, 2, 4, 3).contiguous().to(dtype)
 
 
 def fold_scale(weight, scale):
@@ -43,7 +46,7 @@ def fold_scale(weight, scale):
     return weight.detach().float().cpu() * scale.float().reshape(-1, 1, 1, 1)
 
 
-def pack_stem_weight(weight):
+def pack_stem_weight(weight, dtype=torch.bfloat16):
     """[Cout, 3, 3, 3] float -> bf16 [kh][2][Cout][8]: element (kh, kc, n, j) is the weight of output n for input channel
     j % 4 and filter column kw = 2*kc + j // 4 (zero for kw = 3 and for the padded 4th channel) -- the B operand of the stem
     conv, whose K runs over the 4 pixels x 4 channels that follow a filter row's first input pixel (conv_umma.cu, kStem*)."""
@@ -51,7 +54,7 @@ def pack_stem_weight(weight):
     w = weight.detach().float().cpu()                      # [n, ci, kh, kw]
     full = torch.zeros(3, 4, 4, cout)                      # [kh, pixel, channel, n]
     full[:, :3, :3, :] = w.permute(2, 3, 1, 0)
-    return full.reshape(3, 2, 8, cout).permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)
+    return full.reshape(3, 2, 8, cout).permute(0, 1, 3, 2).contiguous().to(dtype)
 
 
 _AUX_BRANCH = 7      # graph branch of the residual blocks' shortcut convs (LFD_MAX_BRANCHES - 1)
@@ -95,8 +98,12 @@ class _Arena(object):
 class InferencePlan(object):
     """One native forward plan for a fixed input shape."""
 
-    def __init__(self, model, N, H, W, device, conv_impl=nat.CONV_UMMA, create_native=True):
+    def __init__(self, model, N, H, W, device, conv_impl=nat.CONV_UMMA, create_native=True, act_dtype='bf16'):
         self.N, self.H, self.W = N, H, W
+        if act_dtype not in ACT_DTYPES:
+            raise ValueError("act_dtype must be 'bf16' or 'fp16' (got %r)" % (act_dtype,))
+        self.act_dtype = act_dtype
+        self.tdtype, self.dtype_code = ACT_DTYPES[act_dtype]   # 16-bit storage type of activations and packed weights
         self.create_native = create_native   # False: host-side planning only (CPU tests of the planner)
         self.device = device
         self.conv_impl = conv_impl
@@ -124,12 +131,13 @@ class InferencePlan(object):
         return off
 
     def _add_bf16(self, t):
-        t = t.detach().to(torch.bfloat16).reshape(-1).cpu()
+        """16-bit parameter staging (bf16 or fp16 bit patterns, kept as int16 so that one buffer serves both types)."""
+        t = t.detach().to(self.tdtype).reshape(-1).cpu().view(torch.int16)
         off = self._bf16_n
         self._bf16.append(t)
         self._bf16_n += (t.numel() + 7) // 8 * 8
         if t.numel() % 8:
-            self._bf16.append(torch.zeros(8 - t.numel() % 8, dtype=torch.bfloat16))
+            self._bf16.append(torch.zeros(8 - t.numel() % 8, dtype=torch.int16))
         return off
 
     @staticmethod
@@ -159,7 +167,7 @@ class InferencePlan(object):
         conv2, norm2, relu2 = tail
         scale2, shift2 = self._fold(conv2, norm2)
         return dict(tail_cout=conv2.out_channels, tail_relu=int(relu2),
-                    tail_w=self._add_bf16(pack_conv_weight(fold_scale(conv2.weight, scale2), cmid)),
+                    tail_w=self._add_bf16(pack_conv_weight(fold_scale(conv2.weight, scale2), cmid, self.tdtype)),
                     tail_shift=self._add_f32(shift2), tail_modules=(conv2, norm2))
 
     @staticmethod
@@ -184,7 +192,7 @@ class InferencePlan(object):
             raise NotImplementedError('the B200 stem kernel handles the 3x3/s2 conv on a 3-channel image only')
         ho, wo = _conv_out(h, 3, 2), _conv_out(w, 3, 2)
         scale, shift = self._fold(conv, norm)
-        wt = pack_stem_weight(fold_scale(conv.weight, scale))
+        wt = pack_stem_weight(fold_scale(conv.weight, scale), self.tdtype)
         op = dict(kind=nat.OP_STEM0, H=h, W=w, Cin=3, Ho=ho, Wo=wo, Cout=conv.out_channels, ksize=3, stride=2, relu=int(relu),
                   w_bf16=self._add_bf16(wt), shift=self._add_f32(shift), modules=(conv, norm))
         if tail is not None:
@@ -213,7 +221,7 @@ class InferencePlan(object):
                 scale, shift = torch.ones(cout), torch.zeros(cout)
             else:
                 scale, shift = self._fold(conv, norm)
-            w_off, sc_off, sh_off = self._add_bf16(pack_conv_weight(fold_scale(conv.weight, scale), cc)), None, self._add_f32(shift)
+            w_off, sc_off, sh_off = self._add_bf16(pack_conv_weight(fold_scale(conv.weight, scale), cc, self.tdtype)), None, self._add_f32(shift)
             if cache is not None:
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
@@ -224,7 +232,7 @@ class InferencePlan(object):
         if shortcut is not None:      # (conv1x1/s2, norm, output name): same input, computed by the same kernel
             sconv, snorm, sname = shortcut
             sscale, sshift = self._fold(sconv, snorm)
-            op.update(ds_cout=sconv.out_channels, ds_w=self._add_bf16(pack_conv_weight(fold_scale(sconv.weight, sscale), cin)),
+            op.update(ds_cout=sconv.out_channels, ds_w=self._add_bf16(pack_conv_weight(fold_scale(sconv.weight, sscale), cin, self.tdtype)),
                       ds_shift=self._add_f32(sshift), ds_modules=(sconv, snorm),
                       out2=self._tensor(sname, self.N, ho, wo, sconv.out_channels))
         op['out'] = self._tensor(out_name, self.N, ho, wo, op.get('tail_cout') or cout)
@@ -345,7 +353,7 @@ class InferencePlan(object):
         def final(raw, stats_id, tnorm, convs, n_cls, n_reg):
             ws, scs, shs = [], [], []
             for (fc, sc) in convs:
-                ws.append(fc.weight.detach().float().cpu().reshape(fc.out_channels, -1).to(torch.bfloat16).float())
+                ws.append(fc.weight.detach().float().cpu().reshape(fc.out_channels, -1).to(self.tdtype).float())
                 b = fc.bias.detach().float().cpu() if fc.bias is not None else torch.zeros(fc.out_channels)
                 scs.append(torch.full((fc.out_channels,), sc))
                 shs.append(b * sc)
@@ -379,7 +387,7 @@ class InferencePlan(object):
     def _finalize(self):
         dev = self.device
         self.params_f32 = torch.cat(self._f32).to(dev) if self._f32 else torch.zeros(4, device=dev)
-        self.params_bf16 = torch.cat(self._bf16).to(dev) if self._bf16 else torch.zeros(8, dtype=torch.bfloat16, device=dev)
+        self.params_bf16 = torch.cat(self._bf16).to(dev) if self._bf16 else torch.zeros(8, dtype=torch.int16, device=dev)
         self._f32, self._bf16 = None, None
         n_stats = len([o for o in self._ops if o['kind'] == nat.OP_CONV and o.get('gn_groups')])
         stats_each = self.N * 16 * 2 * 8
@@ -421,6 +429,7 @@ class InferencePlan(object):
         for i, op in enumerate(self._ops):
             o = arr[i]
             o.kind = op['kind']
+            o.dtype = self.dtype_code
             o.N, o.H, o.W, o.Cin, o.Ho, o.Wo, o.Cout = self.N, op['H'], op['W'], op['Cin'], op['Ho'], op['Wo'], op['Cout']
             o.ksize, o.stride, o.relu = op.get('ksize', 1), op.get('stride', 1), op.get('relu', 0)
             o.gn_groups = op.get('gn_groups', 0)
@@ -489,13 +498,13 @@ class InferencePlan(object):
         return cls_out, reg_out
 
     def tensor(self, name):
-        """Debug view of an intermediate activation as NHWC bf16 (valid right after an eager forward only if
+        """Debug view of an intermediate activation as NHWC bf16 / fp16 (valid right after an eager forward only if
         its buffer has not been reused by a later layer)."""
         op = [o for o in self._ops if name in (o.get('out'), o.get('out2'))][0]
         c = op['ds_cout'] if op.get('out2') == name else (op.get('tail_cout') or op['Cout'])
         n = self.N * op['Ho'] * op['Wo'] * c
         raw = self.workspace[self.offsets[name]: self.offsets[name] + 2 * n]
-        return raw.view(torch.bfloat16).view(self.N, op['Ho'], op['Wo'], c)
+        return raw.view(self.tdtype).view(self.N, op['Ho'], op['Wo'], c)
 
     def describe(self):
         names = {nat.OP_STEM0: 'stem0', nat.OP_CONV: 'conv', nat.OP_GN_APPLY: 'gn_apply', nat.OP_HEAD_FINAL: 'head_final'}

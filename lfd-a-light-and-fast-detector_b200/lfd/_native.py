@@ -16,6 +16,7 @@ MAX_LEVELS = 8
 OP_STEM0, OP_CONV, OP_GN_APPLY, OP_HEAD_FINAL = 0, 1, 2, 3
 INPUT_F32_NCHW, INPUT_U8_NHWC = 0, 1
 CONV_UMMA, CONV_SIMT = 0, 1
+DTYPE_BF16, DTYPE_FP16 = 0, 1
 CLS_SIGMOID, CLS_SOFTMAX = 0, 1
 BBOX_SIGMOID, BBOX_EXP, BBOX_INDEPENDENT = 0, 1, 2
 ASSIGN_DIST, ASSIGN_LONGER, ASSIGN_SHORTER = 0, 1, 2
@@ -37,7 +38,7 @@ class Op(C.Structure):
                 ('gamma', C.c_void_p), ('beta', C.c_void_p),
                 ('tail_cout', C.c_int32), ('tail_relu', C.c_int32),
                 ('tail_weight', C.c_void_p), ('tail_scale', C.c_void_p), ('tail_shift', C.c_void_p),
-                ('ds_cout', C.c_int32), ('ds_reserved', C.c_int32), ('ds_out_off', C.c_int64),
+                ('ds_cout', C.c_int32), ('dtype', C.c_int32), ('ds_out_off', C.c_int64),
                 ('ds_weight', C.c_void_p), ('ds_shift', C.c_void_p)]
 
 
@@ -109,7 +110,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.lfd_abi_version() != 2:
+    if L.lfd_abi_version() != 3:
         raise LfdError('liblfd_b200.so ABI version mismatch')
     _lib = L
     return L

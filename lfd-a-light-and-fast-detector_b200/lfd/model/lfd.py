@@ -83,6 +83,7 @@ class LFD(nn.Module):
         self._post_plans = {}
         self._plan_fingerprint = None
         self.conv_impl = nat.CONV_UMMA
+        self.act_dtype = 'bf16'                # 16-bit storage type of the inference plan: 'bf16' or 'fp16' (lfd/_engine.py)
         self.use_cuda_graph = True
         self.max_detections_per_image = 8192   # candidate / output capacity of the device post-process
 
@@ -102,9 +103,9 @@ class LFD(nn.Module):
         fp = self._fingerprint()
         if fp != self._plan_fingerprint:
             self._plans, self._plan_fingerprint = {}, fp
-        key = (n, h, w, str(device), self.conv_impl)
+        key = (n, h, w, str(device), self.conv_impl, self.act_dtype)
         if key not in self._plans:
-            self._plans[key] = InferencePlan(self, n, h, w, device, self.conv_impl)
+            self._plans[key] = InferencePlan(self, n, h, w, device, self.conv_impl, act_dtype=self.act_dtype)
         return self._plans[key]
 
     def forward(self, x):

@@ -32,11 +32,12 @@ those vectors and against the reference's docstring known-answer vectors.
 The sigmoid focal loss has no CPU implementation in the reference; its
 restatement is pinned against torchvision.ops.sigmoid_focal_loss instead.
 
-Two forward flavours:
-  * forward(..., emulate_bf16=False): the reference arithmetic (fp32).
-  * forward(..., emulate_bf16=True): same graph with bf16 roundings inserted at
-    exactly the points where the CUDA path stores bf16 (see DESIGN.md
-    "rounding points") -- the Gate-B oracle of SURVEY.md section 7.
+Forward flavours:
+  * forward(..., emulate=None): the reference arithmetic (fp32).
+  * forward(..., emulate='bf16' | 'fp16'): same graph with roundings to the CUDA
+    path's 16-bit storage type inserted at exactly the points where the CUDA
+    path stores 16-bit values (see DESIGN.md "rounding points") -- the Gate-B
+    oracle of SURVEY.md section 7.
 """
 import math
 
@@ -89,22 +90,31 @@ def bf16r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def fp16r(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
+_ROUNDERS = {None: None, False: None, True: bf16r, 'bf16': bf16r, 'fp16': fp16r}
+
+
 # ----------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------
 class _Net(object):
     """Walks the reference module graph from a state_dict (reference key names)."""
 
-    def __init__(self, cfg, sd, emulate_bf16, trace=None):
-        self.cfg, self.sd, self.emu = cfg, {k: v.detach().float() for k, v in sd.items()}, emulate_bf16
+    def __init__(self, cfg, sd, emulate, trace=None):
+        self.cfg, self.sd = cfg, {k: v.detach().float() for k, v in sd.items()}
+        self.rnd = _ROUNDERS[emulate]     # rounding to the CUDA path's 16-bit storage type (None: reference fp32 arithmetic)
+        self.emu = self.rnd is not None
         self.trace = trace  # optional dict: conv key -> stored NCHW output of that fused layer (debugging aid)
 
     def r(self, t):
-        return bf16r(t) if self.emu else t
+        return self.rnd(t) if self.emu else t
 
     def w(self, key):
         w = self.sd[key]
-        return bf16r(w) if self.emu else w
+        return self.rnd(w) if self.emu else w
 
     def conv(self, x, key, stride, pad):
         b = self.sd.get(key + '.bias')
@@ -125,8 +135,8 @@ class _Net(object):
             shift = sd[nkey + '.bias'] - sd[nkey + '.running_mean'] * scale
             if sd.get(ckey + '.bias') is not None:
                 shift = shift + sd[ckey + '.bias'] * scale
-            y = F.conv2d(x, bf16r(sd[ckey + '.weight'] * scale[:, None, None, None]), None, stride=stride, padding=pad)
-            y = y + bf16r(shift)[None, :, None, None]
+            y = F.conv2d(x, self.rnd(sd[ckey + '.weight'] * scale[:, None, None, None]), None, stride=stride, padding=pad)
+            y = y + self.rnd(shift)[None, :, None, None]
         else:
             y, b = self.conv(x, ckey, stride, pad)
             y = self.bn(y, nkey, b)
@@ -240,10 +250,14 @@ class _Net(object):
         return torch.cat(cls_list, 1), torch.cat(reg_list, 1), sizes
 
 
-def forward(cfg, state_dict, x, emulate_bf16=False, trace=None):
-    """-> (cls [N,P,C'], reg [N,P,4], [(H_l, W_l)])  C' = C (sigmoid/focal) or C+1 (cross entropy)."""
+def forward(cfg, state_dict, x, emulate_bf16=False, trace=None, emulate=None):
+    """-> (cls [N,P,C'], reg [N,P,4], [(H_l, W_l)])  C' = C (sigmoid/focal) or C+1 (cross entropy).
+    emulate: None (reference fp32), 'bf16' or 'fp16' (roundings of the CUDA path's storage type inserted at its rounding
+    points); emulate_bf16=True is the older spelling of emulate='bf16'."""
+    if emulate is None and emulate_bf16:
+        emulate = 'bf16'
     with torch.no_grad():
-        return _Net(cfg, state_dict, emulate_bf16, trace).forward(x)
+        return _Net(cfg, state_dict, emulate, trace).forward(x)
 
 
 # ----------------------------------------------------------------------------------------------

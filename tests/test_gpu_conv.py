@@ -4,7 +4,7 @@ convolution of the same bf16 operands, through the C-ABI (lfd_run_op)."""
 import pytest
 import torch
 
-from gpu_ops import bf16r, run_conv, ref_conv, assert_bf16_close
+from gpu_ops import bf16r, run_conv, ref_conv, assert_bf16_close, DTYPES
 from lfd import _native as nat
 
 pytestmark = pytest.mark.gpu
@@ -28,28 +28,30 @@ CASES = [
 ]
 
 
-def _make(case, seed=0):
+def _make(case, seed=0, dtype='bf16'):
     N, H, W, Cin, Cout, k, s, relu, use_res, gn = case
+    tdt, rnd = DTYPES[dtype][0], DTYPES[dtype][1]
     g = torch.Generator().manual_seed(seed)
-    x = bf16r(torch.randn((N, H, W, Cin), generator=g)).to(torch.bfloat16).cuda()
-    w = bf16r(torch.randn((Cout, Cin, k, k), generator=g) * (2.0 / (Cin * k * k)) ** 0.5)
+    x = torch.randn((N, H, W, Cin), generator=g).to(tdt).cuda()
+    w = rnd(torch.randn((Cout, Cin, k, k), generator=g) * (2.0 / (Cin * k * k)) ** 0.5)
     scale = torch.rand((Cout,), generator=g) + 0.5
     shift = torch.randn((Cout,), generator=g) * 0.2
     if gn:
         scale, shift = torch.ones(Cout), torch.zeros(Cout)
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-    res = bf16r(torch.randn((N, Ho, Wo, Cout), generator=g)).to(torch.bfloat16).cuda() if use_res else None
+    res = torch.randn((N, Ho, Wo, Cout), generator=g).to(tdt).cuda() if use_res else None
     return x, w, scale, shift, res
 
 
+@pytest.mark.parametrize('dtype', ['bf16', 'fp16'])
 @pytest.mark.parametrize('impl', [nat.CONV_SIMT, nat.CONV_UMMA], ids=['simt', 'umma'])
 @pytest.mark.parametrize('case', CASES, ids=lambda c: 'N%d_%dx%d_%d-%d_k%ds%d_r%d_res%d_gn%d' % c)
-def test_conv_matches_fp32_reference(case, impl):
+def test_conv_matches_fp32_reference(case, impl, dtype):
     N, H, W, Cin, Cout, k, s, relu, use_res, gn = case
-    x, w, scale, shift, res = _make(case)
-    out, stats, q = run_conv(x, w, scale, shift, s, relu, res=res, gn_groups=gn, impl=impl)
-    ref = ref_conv(x, w, scale, shift, s, relu, res=res)
-    assert_bf16_close(out, ref, 'conv %s (plan %s)' % (case, q))
+    x, w, scale, shift, res = _make(case, dtype=dtype)
+    out, stats, q = run_conv(x, w, scale, shift, s, relu, res=res, gn_groups=gn, impl=impl, dtype=dtype)
+    ref = ref_conv(x, w, scale, shift, s, relu, res=res, dtype=dtype)
+    assert_bf16_close(out, ref, 'conv %s %s (plan %s)' % (case, dtype, q), dtype=dtype)
     if gn:
         o = out.float().cpu().reshape(N, -1, gn, Cout // gn).double()
         s1, s2 = o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))
@@ -74,28 +76,30 @@ TAIL_CASES = [   # (N, H, W, Cin, Cmid, k, stride, Cout2, residual on the tail o
 ]
 
 
+@pytest.mark.parametrize('dtype', ['bf16', 'fp16'])
 @pytest.mark.parametrize('case', TAIL_CASES, ids=lambda c: 'N%d_%dx%d_%d-%d_k%ds%d_tail%d_res%d_gn%d' % c)
-def test_conv_with_fused_1x1_tail(case):
+def test_conv_with_fused_1x1_tail(case, dtype):
     """conv + scale/shift + ReLU -> (bf16) -> 1x1 conv + scale/shift (+res) + ReLU in ONE kernel == the two layers run
     one after the other with the intermediate rounded to bf16."""
     N, H, W, Cin, Cmid, k, s, C2, use_res, gn = case
-    x, w, scale, shift, _ = _make((N, H, W, Cin, Cmid, k, s, True, False, 0), seed=5)
+    tdt, rnd, ulp = DTYPES[dtype][0], DTYPES[dtype][1], DTYPES[dtype][2]
+    x, w, scale, shift, _ = _make((N, H, W, Cin, Cmid, k, s, True, False, 0), seed=5, dtype=dtype)
     g = torch.Generator().manual_seed(9)
-    w2 = bf16r(torch.randn((C2, Cmid, 1, 1), generator=g) * (2.0 / Cmid) ** 0.5)
+    w2 = rnd(torch.randn((C2, Cmid, 1, 1), generator=g) * (2.0 / Cmid) ** 0.5)
     sc2, sh2 = torch.rand((C2,), generator=g) + 0.5, torch.randn((C2,), generator=g) * 0.2
     if gn:
         sc2, sh2 = torch.ones(C2), torch.zeros(C2)
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-    res = bf16r(torch.randn((N, Ho, Wo, C2), generator=g)).to(torch.bfloat16).cuda() if use_res else None
-    out, stats, q = run_conv(x, w, scale, shift, s, True, res=res, gn_groups=gn, tail=(w2, sc2, sh2, not gn))
-    mid = bf16r(ref_conv(x, w, scale, shift, s, True))
-    ref = ref_conv(mid.to(torch.bfloat16), w2, sc2, sh2, 1, not gn, res=res)
+    res = torch.randn((N, Ho, Wo, C2), generator=g).to(tdt).cuda() if use_res else None
+    out, stats, q = run_conv(x, w, scale, shift, s, True, res=res, gn_groups=gn, tail=(w2, sc2, sh2, not gn), dtype=dtype)
+    mid = rnd(ref_conv(x, w, scale, shift, s, True, dtype=dtype))
+    ref = ref_conv(mid.to(tdt), w2, sc2, sh2, 1, not gn, res=res, dtype=dtype)
     # the intermediate itself may differ from the CPU one by 1 bf16 ulp on isolated elements (fp32 summation order), which
     # moves isolated outputs by more than one output ulp: allow 2e-3 of the output range on top of the 1-ulp bound
     o, r = out.float().cpu(), ref.float()
-    tol = r.abs() * 2.0 ** -7 + 2e-3 * float(r.abs().max())
+    tol = r.abs() * ulp + 2e-3 * float(r.abs().max()) * (ulp / 2.0 ** -7)
     assert bool(((o - r).abs() <= tol).all()), 'fused tail %s: max err %g (ref max %g) plan %s' % (case, float((o - r).abs().max()), float(r.abs().max()), q)
-    assert float(torch.sqrt(((o - r) ** 2).mean()) / torch.sqrt((r ** 2).mean())) < 3e-3
+    assert float(torch.sqrt(((o - r) ** 2).mean()) / torch.sqrt((r ** 2).mean())) < 3e-3 * (ulp / 2.0 ** -7)
     if gn:
         og = out.float().cpu().reshape(N, -1, gn, C2 // gn).double()
         assert torch.allclose(stats[..., 0].cpu(), og.sum(dim=(1, 3)), rtol=1e-6, atol=1e-3)

@@ -104,3 +104,45 @@ def test_one_720p_frame_against_the_oracle():
     ec, er = rel_err(cls.cpu(), ocls), rel_err(reg.cpu(), oreg)
     print('720p frame vs bf16-emulated oracle: cls max/rms %.2e/%.2e reg %.2e/%.2e' % (ec[0], ec[1], er[0], er[1]))
     assert ec[1] < 2e-2 and er[1] < 2e-2 and ec[0] < 8e-2 and er[0] < 8e-2
+    # fp16 storage: the stated 1e-3 at full resolution, and identical kept indices at the predict / evaluation thresholds
+    model.act_dtype = 'fp16'
+    with torch.no_grad():
+        cls, reg = model(torch.from_numpy(img)[None].cuda())
+    ocls, oreg, sizes = orc.forward(orc.CONFIGS['WIDERFACE_S'], sd, xf, emulate='fp16')
+    ec, er = rel_err(cls.cpu(), ocls), rel_err(reg.cpu(), oreg)
+    print('720p frame, fp16 vs fp16-emulated oracle: cls max/rms %.2e/%.2e reg %.2e/%.2e' % (ec[0], ec[1], er[0], er[1]))
+    assert ec[1] < 1e-3 and ec[0] < 5e-3 and er[1] < 2e-3 and er[0] < 1e-2, (ec, er)
+    meta = [dict(resized_height=720, resized_width=1280, resize_scale=1.0)]
+    model.max_detections_per_image = 32768
+    for (thr, iou) in ((0.5, 0.3), (0.01, 0.4)):       # WIDERFACE_train/predict.py:22, evaluation.py:60-61
+        dets, labels, src, count, overflow = model.detect((cls, reg), [720], [1280], [1.0], thr, iou)
+        assert int(overflow.item()) == 0
+        _, osrc = orc.get_results(orc.CONFIGS['WIDERFACE_S'], ocls, oreg, sizes, meta, thr, iou)
+        k = int(count[0].item())
+        assert src[0, :k].cpu().tolist() == osrc[0].tolist(), (thr, iou, k, len(osrc[0]))
+        print('   thr %.2f / iou %.1f: %d detections, identical indices' % (thr, iou, k))
+
+
+def test_fp16_activation_range_is_safe():
+    """max-abs trace of every stored tensor of the fp16 plan (WIDERFACE-S 720p, TT100K-L 1080p crops): orders of magnitude inside
+    the fp16 range (65504) -- the values are post-BatchNorm / ReLU activations; the conversion saturates instead of overflowing."""
+    import os
+    os.environ['LFD_B200_NO_REUSE'] = '1'
+    try:
+        for name, h, w in (('WIDERFACE_S', 720, 1280), ('TT100K_L', 544, 960)):
+            model, _ = synth_model(name, cls_bias=-2.0)
+            model.cuda()
+            model.act_dtype, model.use_cuda_graph = 'fp16', False
+            x = torch.from_numpy(synth.synth_image_u8(h, w, seed=7))[None].cuda()
+            with torch.no_grad():
+                cls, reg = model(x)
+            plan = list(model._plans.values())[0]
+            worst = 0.0
+            for op in plan._ops:
+                for key in ('out', 'out2'):
+                    if op.get(key) is not None:
+                        worst = max(worst, float(plan.tensor(op[key]).float().abs().max()))
+            print('%s fp16 plan: largest stored activation %.1f' % (name, worst))
+            assert worst < 2048.0 and torch.isfinite(cls).all() and torch.isfinite(reg).all()
+    finally:
+        del os.environ['LFD_B200_NO_REUSE']

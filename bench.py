@@ -32,9 +32,14 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOADS = {
-    'WIDERFACE_S': dict(cfg='WIDERFACE_S', N=8, H=720, W=1280, name='WIDERFACE-S inference 1280x720 batch=8 per GPU'),
-    'WIDERFACE_XS': dict(cfg='WIDERFACE_XS', N=1, H=480, W=640, name='WIDERFACE-XS inference 640x480 batch=1'),
-    'TT100K_L': dict(cfg='TT100K_L', N=16, H=1080, W=1920, name='TT100K LFD_L inference 1920x1080 batch=16 per GPU', pass_fraction=0.0002, cap=16384),
+    # BASELINE.json configs[1]: the workload `metric` is quoted on (default)
+    'WIDERFACE_S': dict(cfg='WIDERFACE_S', N=8, H=720, W=1280, dtype='bf16', name='WIDERFACE-S inference 1280x720 batch=8 per GPU'),
+    # configs[0] geometry on the GPU (the CPU-runnable plumbing case)
+    'WIDERFACE_XS': dict(cfg='WIDERFACE_XS', N=1, H=480, W=640, dtype='bf16', name='WIDERFACE-XS inference 640x480 batch=1'),
+    # configs[3]
+    'TT100K_L': dict(cfg='TT100K_L', N=16, H=1080, W=1920, dtype='bf16', name='TT100K LFD_L inference 1920x1080 batch=16 per GPU', pass_fraction=0.0002, cap=16384),
+    # configs[4]: fp16 4K throughput sweep, batch-sharded (2 frames per GPU per step)
+    'WIDERFACE_XS_4K': dict(cfg='WIDERFACE_XS', N=2, H=2160, W=3840, dtype='fp16', name='WIDERFACE-XS inference 3840x2160 batch=2 per GPU', pool=4),
 }
 POOL = 8          # device-resident input batches rotated through (8 x 22 MB = 177 MB > 126 MB L2)
 IOU_THR = 0.3     # WIDERFACE_train/predict.py:22
@@ -126,12 +131,19 @@ class ClockSampler(object):
                     source='nvidia-smi')
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels that can be the most expensive one, from the
-# committed `ncu --set full` capture (profiles/r01_ncu_full_final.md; re-measure with profiles/ncu_run.sh after kernel changes)
-NCU_TRAFFIC = {
-    ('WIDERFACE_S', 'stem0 3x3/s2 3->64 @360x640'): 22303744 + 177991424,
-    ('WIDERFACE_S', 'conv 3x3/s2 64->64 @180x320'): 236171520 + 41846016,
-}
+def ncu_traffic(cfg, dtype, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` capture:
+    profiles/ncu_traffic.json is written by profiles/ncu_parse.py from the .ncu-rep that profiles/ncu_run.sh produces
+    (re-run both after a kernel change).  None when that kernel has no capture."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None
+    e = table.get('%s/%s' % (cfg, dtype), {}).get(kernel)
+    return None if e is None else int(e['dram_bytes_read'] + e['dram_bytes_write'])
 
 
 def op_algorithmic(row, N, input_bytes_per_px):
@@ -152,38 +164,88 @@ def op_algorithmic(row, N, input_bytes_per_px):
     return px_in * cin * 2 + px_out * cout * 4, 2.0 * px_out * cout * cin   # head_final
 
 
+def op_name(row):
+    return '%s %dx%d/s%d %d->%d @%dx%d' % (row['kind'], row['ksize'], row['ksize'], row['stride'], row['Cin'], row['Cout'], row['Ho'], row['Wo'])
+
+
+def init_nccl(dev):
+    """NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line."""
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group('nccl', device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+TRAIN_WORKLOADS = {}
+
+
+def train_main(args):
+    raise SystemExit('no training workload registered')
+
+
 def build_model(cfg_name):
     from helpers import synth_model
     model, sd = synth_model(cfg_name, cls_bias=-1.0)
     return model, sd
 
 
+def reference_nms():
+    """The REFERENCE's own compiled CPU NMS (lfd/model/utils/build/nms/src/cpu/nms_cpu.cpp, built by oracle/build_ref.py into
+    oracle/_ref/nms_ext_ref.so, which travels to the GPU box) as a drop-in for the oracle's numpy NMS; None when absent."""
+    try:
+        from oracle import build_ref
+        mod = build_ref.load_module()
+    except Exception:
+        mod = None
+    if mod is None:
+        return None, None
+    return (lambda dets, thr: mod.nms(torch.from_numpy(np.ascontiguousarray(dets, np.float32)), float(thr)).numpy()), build_ref.so_path()
+
+
 def cpu_leg(wl, sd, steps, warmup, frames_per_step, budget_s=25.0):
-    """The reference's CPU arithmetic (oracle port: same ATen conv / norm calls as the reference modules, fp32) +
-    oracle decode + NMS (the reference's own compiled nms_cpu.cpp from oracle/_ref when present)."""
+    """The reference's CPU path for this workload: fp32 forward (oracle PORT: the same ATen conv / norm calls the reference
+    modules make -- /root/reference itself does not exist on the GPU box) + decode + class-aware NMS with the REFERENCE's
+    compiled nms_cpu.cpp when oracle/_ref/nms_ext_ref.so is present (numpy restatement otherwise)."""
     import synth
     from oracle import lfd_oracle as orc
     cfg = orc.CONFIGS[wl['cfg']]
     x = synth.synth_input(frames_per_step, wl['H'], wl['W'])
-    # "all the host threads it can use": PyTorch's CPU convs stop scaling (and then collapse) well before 128 threads
-    # on these small feature maps, so the thread count is calibrated once on a 1-frame forward and reported as `cores`.
+    nms_fn, nms_so = reference_nms()
+    # "all the host threads it can use": PyTorch's CPU convs stop scaling (and then collapse) well before 128 threads on these
+    # feature maps, so the thread count is calibrated on the REAL step batch (second of two forwards) and reported as `cores`.
     ncpu = os.cpu_count() or 1
     best = (None, 1e30)
+    t_cal = time.time()
     for nt in sorted(set([min(ncpu, c) for c in (8, 16, 32, 64, ncpu)])):
         torch.set_num_threads(nt)
         orc.forward(cfg, sd, x[:1])
         t0 = time.time()
-        orc.forward(cfg, sd, x[:1])
+        orc.forward(cfg, sd, x)
         dt = time.time() - t0
         if dt < best[1]:
             best = (nt, dt)
+        if time.time() - t_cal > 0.4 * budget_s:
+            break
     torch.set_num_threads(best[0])
     meta = [dict(resized_height=wl['H'], resized_width=wl['W'], resize_scale=1.0) for _ in range(frames_per_step)]
+    pf = wl.get('pass_fraction', PASS_FRACTION)
 
     def step():
         cls, reg, sizes = orc.forward(cfg, sd, x)
-        thr = float(torch.quantile(cls.sigmoid().flatten()[:200000], 1.0 - PASS_FRACTION)) if cfg['head']['classification_loss_type'] == 'FocalLoss' else 0.1
-        orc.get_results(cfg, cls, reg, sizes, meta, thr, IOU_THR)
+        if cfg['head']['classification_loss_type'] == 'FocalLoss':
+            sc = cls.sigmoid()
+        else:
+            sc = cls.softmax(-1)[..., :-1]
+        thr = float(torch.quantile(sc.flatten()[:200000], 1.0 - pf))
+        orc.get_results(cfg, cls, reg, sizes, meta, thr, IOU_THR, nms_fn=nms_fn)
     for _ in range(warmup):
         step()
     t0 = time.time()
@@ -194,7 +256,18 @@ def cpu_leg(wl, sd, steps, warmup, frames_per_step, budget_s=25.0):
         if time.time() - t0 > budget_s and done >= 2:
             break
     dt = time.time() - t0
-    return frames_per_step * done / dt, dt / done * 1e3, done
+    return dict(ips=frames_per_step * done / dt, ms=dt / done * 1e3, done=done, cores=best[0],
+                nms='reference nms_cpu.cpp (oracle/_ref/nms_ext_ref.so)' if nms_fn is not None else 'oracle numpy restatement',
+                native_so=nms_so)
+
+
+def workload_config(wl, dtype, world):
+    """The keys both arms (ours and --impl reference) print under `config`: what is computed, not how."""
+    return dict(workload=wl['name'], model=wl['cfg'], frames_per_step_per_gpu=wl['N'], height=wl['H'], width=wl['W'], dtype=dtype,
+                input='synthetic uint8 BGR frames (tests/synth.py weights; no network for datasets / checkpoints)',
+                step='forward (backbone + neck + head) + score / decode / class-aware NMS of one batch',
+                score_thr='calibrated so that %.3f%% of the (point, class) scores pass' % (100 * wl.get('pass_fraction', PASS_FRACTION)),
+                iou_thr=IOU_THR, parallelism='batch-sharded replicas x%d, no collective on the inference path' % world)
 
 
 def main():
@@ -203,32 +276,42 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='WIDERFACE_S', choices=sorted(WORKLOADS))
+    ap.add_argument('--config', default='WIDERFACE_S', choices=sorted(WORKLOADS) + sorted(TRAIN_WORKLOADS))
+    ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16'], help="16-bit storage type of the plan (default: the workload's)")
     ap.add_argument('--conv-impl', default='umma', choices=['umma', 'simt'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--min-timed-s', type=float, default=0.5, help='the K-step timed block is repeated until this much time has been timed')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op timing table to stderr')
     ap.add_argument('--ncu-step', action='store_true',
                     help='for `ncu --profile-from-start off`: warm up, then ONE eager step between cudaProfilerStart/Stop, and exit')
     args = ap.parse_args()
+    if args.config in TRAIN_WORKLOADS:
+        return train_main(args)
     wl = WORKLOADS[args.config]
+    dtype = args.dtype or wl['dtype']
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     warmup = max(args.warmup, 3)
-    metric = 'images/sec %s bf16' % wl['name']
+    metric = 'images/sec %s %s' % (wl['name'], dtype)
+    config = workload_config(wl, dtype, max(world, args.gpus))
 
     if args.impl == 'reference':
         if rank != 0:
             return 0
         model, sd = build_model(wl['cfg'])
         frames = wl['N']
-        ips, ms, done = cpu_leg(wl, sd, args.steps, min(warmup, 1), frames, budget_s=150.0)
-        cores = torch.get_num_threads()
-        line = dict(metric=metric, value=ips, unit='images/s', n_gpus=args.gpus, steps=done, warmup=min(warmup, 1), ms_per_step=ms,
+        r = cpu_leg(wl, sd, args.steps, warmup, frames, budget_s=150.0)
+        line = dict(metric=metric, value=r['ips'], unit='images/s', n_gpus=args.gpus, steps=r['done'], warmup=warmup, ms_per_step=r['ms'],
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                    config=dict(workload=wl['name'], note='CPU path of the reference (PyTorch fp32 forward + decode + CPU NMS) via the oracle port'),
-                    cpu_baseline=dict(value=ips, unit='images/s', cores=cores, kind='port', sample='%d frames per step, %d steps' % (frames, done)),
-                    e2e=dict(value=ips, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                    config=config,
+                    impl_detail=dict(note='CPU path of the reference: PyTorch fp32 forward (oracle port of the reference modules; /root/reference '
+                                          'does not exist on the GPU box) + decode + class-aware NMS', nms=r['nms'],
+                                     steps_requested=args.steps, steps_timed=r['done'], time_budget_s=150.0,
+                                     threads='calibrated on the %d-frame step batch over {8,16,32,64,all} host threads' % frames),
+                    cpu_baseline=dict(value=r['ips'], unit='images/s', cores=r['cores'], kind='port',
+                                      sample='%d frames per step, %d steps; NMS: %s' % (frames, r['done'], r['nms'])),
+                    e2e=dict(value=r['ips'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line))
         return 0
 
@@ -237,31 +320,23 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group('nccl', device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        init_nccl(dev)
     from lfd import _native as nat
-    from lfd.pipeline import ForwardPostPipeline, StreamingDetector
+    from lfd.pipeline import ForwardPostPipeline, StreamingDetector, bind_host_to_gpu_numa_node
     import synth
+    numa_node = bind_host_to_gpu_numa_node(dev)     # before any pinned allocation: host pools land on the GPU's NUMA node
     model, sd = build_model(wl['cfg'])
     model.to(dev)
     model.conv_impl = nat.CONV_SIMT if args.conv_impl == 'simt' else nat.CONV_UMMA
+    model.act_dtype = dtype
     model.use_cuda_graph = not args.no_graph
     model.max_detections_per_image = wl.get('cap', 8192)
     pass_fraction = wl.get('pass_fraction', PASS_FRACTION)
     N, H, W = wl['N'], wl['H'], wl['W']
+    npool = wl.get('pool', POOL)
     g = torch.Generator().manual_seed(1000 + rank)
     host_pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(POOL)]
+    pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(npool)]
     plan = model.inference_plan(N, H, W, dev)
     for i, hw in enumerate(plan.level_sizes):
         model._head_indexes_to_feature_map_sizes[i] = hw
@@ -276,7 +351,7 @@ def main():
     pipe = ForwardPostPipeline(model, plan, post, score_thr, IOU_THR)
 
     def step(i):
-        pipe.enqueue(pool[i % POOL])
+        pipe.enqueue(pool[i % npool])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -296,37 +371,55 @@ def main():
             torch.cuda.profiler.stop()
         return 0
     with torch.no_grad():
-        for i in range(max(warmup, POOL)):   # also instantiates one graph per pool buffer
+        for i in range(npool):                 # set-up, not warm-up: instantiates one CUDA graph per pool buffer
             step(i)
         sync_all()
+        # size the number of timed blocks from a short probe so that >= min_timed_s are timed whatever --steps is
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(pipe.fwd_stream)
+        for i in range(warmup):                # the W warm-up steps
+            step(i)
+        p1.record(pipe.post_stream)
+        sync_all()
+        est_ms = max(p0.elapsed_time(p1) / warmup, 1e-3)
+        blocks = int(min(200, max(1, -(-args.min_timed_s * 1e3 // (est_ms * args.steps)))))
+        tb = torch.tensor([blocks], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)   # every rank times the same number of blocks
+        blocks = int(tb.item())
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(pipe.fwd_stream)
-        for i in range(args.steps):
-            step(i)
-        e1.record(pipe.post_stream)
-        sync_all()
-        ms_total = e0.elapsed_time(e1)
+        block_ms = []
+        for b in range(blocks):                # every block: EXACTLY K steps between a barrier + synchronize on both sides
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(pipe.fwd_stream)
+            for i in range(args.steps):
+                step(b * args.steps + i)
+            e1.record(pipe.post_stream)
+            sync_all()
+            block_ms.append(e0.elapsed_time(e1))
         clocks = sampler.stop() if rank == 0 else None
         counts = post.count.tolist()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor(block_ms, dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * N * args.steps / (ms_total / 1e3)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # per block: the slowest rank
+    block_ms = [float(v) for v in t.tolist()]
+    ms_total = float(sum(block_ms))
+    ms_step = ms_total / (args.steps * blocks)
+    value = world * N * args.steps * blocks / (ms_total / 1e3)
 
     # ---- end to end: pinned host frames in, host detections out, copies inside the timed region
     det = StreamingDetector(model, N, H, W, score_thr, IOU_THR, max_out=1024, device=dev)
+    e2e_steps = args.steps * blocks
     with torch.no_grad():
         for i in range(3):
             det.infer(host_pool[i % 2])
         sync_all()
         t0 = time.perf_counter()
         pending = []                           # up to depth - 1 batches stay in flight behind the one being submitted
-        for i in range(args.steps):
+        for i in range(e2e_steps):
             pending.append(det.submit(host_pool[i % 2]))
             if len(pending) >= det.depth:
                 det.collect(pending.pop(0))
@@ -337,15 +430,21 @@ def main():
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * args.steps / float(te.item())
+    e2e_value = world * N * e2e_steps / float(te.item())
     # how long the host->device copy of one batch takes on its own (diagnostic: is e2e bound by the PCIe link?)
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record()
-    for i in range(10):
-        det.slots[i % 2]['x'].copy_(host_pool[i % 2], non_blocking=True)
-    c1.record()
     torch.cuda.synchronize()
-    h2d_ms = c0.elapsed_time(c1) / 10
+    t0 = time.perf_counter()
+    for i in range(10):
+        det.stage_input(i % 2, host_pool[i % 2])      # on the detector's copy streams
+    torch.cuda.synchronize()
+    h2d_ms = (time.perf_counter() - t0) * 1e3 / 10
+    h2d_all = torch.tensor([det.h2d_bytes / (h2d_ms * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(h2d_all) for _ in range(world)]
+        dist.all_gather(gathered, h2d_all)
+        h2d_per_rank = [round(float(v.item()), 1) for v in gathered]
+    else:
+        h2d_per_rank = [round(float(h2d_all.item()), 1)]
 
     if rank != 0:
         if world > 1:
@@ -360,7 +459,7 @@ def main():
     reps = 5
     with torch.no_grad():
         for rep in range(reps + 1):
-            nat.check(nat.lib().lfd_plan_profile(plan.handle, nat.ptr(pool[rep % POOL]), nat.INPUT_U8_NHWC, nat.ptr(plan.workspace),
+            nat.check(nat.lib().lfd_plan_profile(plan.handle, nat.ptr(pool[rep % npool]), nat.INPUT_U8_NHWC, nat.ptr(plan.workspace),
                                                  nat.ptr(plan.cls_out), nat.ptr(plan.reg_out), buf, nat.stream_ptr()))
             if rep:
                 acc += np.frombuffer(buf, dtype=np.float32)
@@ -382,14 +481,14 @@ def main():
     conv_ms = float(sum(r['ms'] for r in table if r['row']['kind'] == 'conv'))
     net_bound_ms = float(sum(r['t_bound_ms'] for r in table))
     total_bytes, total_flops = sum(r['bytes'] for r in table), sum(r['flops'] for r in table)
-    kname = '%s %dx%d/s%d %d->%d @%dx%d' % (top['row']['kind'], top['row']['ksize'], top['row']['ksize'], top['row']['stride'],
-                                         top['row']['Cin'], top['row']['Cout'], top['row']['Ho'], top['row']['Wo'])
+    kname = op_name(top['row'])
     roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
-                    traffic=NCU_TRAFFIC.get((wl['cfg'], kname)),
+                    traffic=ncu_traffic(args.config, dtype, kname),
                     peak_source=pk['source'],
                     kernel=kname,
                     kernel_ms=top['ms'], kernel_share_of_step=top['ms'] / sum_ms, algorithmic_bytes=top['bytes'], algorithmic_flops=top['flops'],
                     net=dict(layerwise_bound_ms=net_bound_ms, forward_ms_eager_sum=sum_ms, frac_of_layerwise_bound=net_bound_ms / sum_ms,
+                             frac_of_layerwise_bound_in_graph=net_bound_ms / ms_step,
                              conv_share=conv_ms / sum_ms, algorithmic_gb=total_bytes / 1e9, algorithmic_gflop=total_flops / 1e9,
                              hbm_view=total_bytes / (ms_step * 1e-3) / 1e9 / pk['hbm_gbs'],
                              tensor_view=total_flops / (ms_step * 1e-3) / 1e12 / pk['bf16_tflops']))
@@ -403,21 +502,23 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, ms_cpu, done = cpu_leg(wl, sd, 50, 1, 1, budget_s=20.0)
-        cpu = dict(value=ips, unit='images/s', cores=torch.get_num_threads(), kind='port',
-                   sample='1 frame %dx%d per step, %d steps (forward fp32 + decode + NMS on the host)' % (W, H, done))
-    line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(warmup, POOL), ms_per_step=ms_step,
-                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic',
-                config=dict(workload=wl['name'], input='uint8 BGR NHWC frames, normalisation fused into the stem kernel',
-                            weights='synthetic (tests/synth.py)', score_thr='%.4f (calibrated: %.2f%% of (point, class) scores pass)' % (score_thr, 100 * pass_fraction),
-                            iou_thr=IOU_THR, detections_last_step=counts[:N], parallelism='batch-sharded replicas x%d, no collective' % world,
-                            l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
-                               % (POOL, POOL * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),
-                            cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl,
-                            pipelining='post-process of batch i overlaps the forward of batch i+1 (two streams, two output slots)'),
-                clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps,
-                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes,
-                         h2d_copy_alone_ms=h2d_ms, h2d_gbps=det.h2d_bytes / (h2d_ms * 1e-3) / 1e9,
+        r = cpu_leg(wl, sd, 50, 1, 1, budget_s=20.0)
+        cpu = dict(value=r['ips'], unit='images/s', cores=r['cores'], kind='port',
+                   sample='1 frame %dx%d per step, %d steps (forward fp32 + decode + NMS [%s] on the host)' % (W, H, r['done'], r['nms']))
+    line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms_step,
+                higher_is_better=True, scaling='weak', vs_baseline=None, dtype=dtype, data='synthetic',
+                config=config,
+                impl_detail=dict(score_thr=score_thr, detections_last_step=counts[:N],
+                                 timed_blocks=blocks, block_ms=[round(v, 4) for v in block_ms[:16]], timed_s=ms_total / 1e3,
+                                 setup_steps=npool,
+                                 l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
+                                    % (npool, npool * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),
+                                 cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl, launches_per_step=plan.num_launches + 2,
+                                 pipelining='post-process of batch i overlaps the forward of batch i+1 (two streams, two output slots)'),
+                clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps * blocks,
+                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes, steps=e2e_steps,
+                         h2d_copy_alone_ms=h2d_ms, h2d_gbps=det.h2d_bytes / (h2d_ms * 1e-3) / 1e9, h2d_gbps_per_rank=h2d_per_rank,
+                         copy_streams=len(det.copy_streams), host_numa_node=numa_node,
                          note='pinned host uint8 frames -> device -> detections -> pinned host; copy / forward / post-process pipelined on three streams'),
                 roofline=roofline)
     if cpu is not None:

@@ -10,8 +10,8 @@ from collections import OrderedDict
 
 import torch
 
-from .hooks import CheckpointHook, LoggerHook, LrSchedulerHook, OptimizerHook, SpeedHook, get_priority
-from .parallel import shard_batch, world
+from .hooks import CheckpointHook, EvaluationHook, LoggerHook, LrSchedulerHook, OptimizerHook, SpeedHook, get_priority
+from .parallel import broadcast_module_state, shard_batch, world
 from .utils import AverageMeter, get_root_logger, load_checkpoint, save_checkpoint
 
 _RESUME_BLACKLIST = ('timestamp', 'work_dir', 'log_path', 'training_epochs', 'gpu_list', 'display_interval', 'save_interval',
@@ -36,6 +36,10 @@ class Executor(object):
         gpu_list = cfg.get('gpu_list') or [0]
         self.device = torch.device('cuda', gpu_list[rank % len(gpu_list)]) if torch.cuda.is_available() else torch.device('cpu')
         cfg['model'] = cfg['model'].to(self.device)
+        # every replica starts from rank 0's parameters AND buffers (freshly initialised, loaded or resumed): with seed=None or
+        # diverged RNG state the ranks would otherwise train different models (the reference's DataParallel re-broadcasts
+        # module 0 every iteration, executor.py:39)
+        broadcast_module_state(cfg['model'])
         if cfg.get('resume_path') is not None:
             self.resume_optimizer()
             self.resume_lr_scheduler()
@@ -52,12 +56,15 @@ class Executor(object):
         self._hooks.insert(0, hook)
 
     def _register_all_hooks(self):
+        """Same hooks, priorities and registration order as the reference (executor.py:67-99): equal priorities run in
+        registration order, i.e. lr scheduler -> optimizer -> evaluation, then speed, logger, checkpoint."""
         cfg = self.config_dict
-        self._register_hook(LrSchedulerHook(**cfg['warmup_setting']) if 'warmup_setting' in cfg else LrSchedulerHook(), 'NORMAL')
-        self._register_hook(OptimizerHook(cfg.get('optimizer_grad_clip_cfg'), cfg['training_epochs']), 'HIGH')
-        self._register_hook(SpeedHook(), 'LOW')
-        self._register_hook(LoggerHook(), 'VERY_LOW')
         self._register_hook(CheckpointHook(), 'LOWEST')
+        self._register_hook(LoggerHook(), 'VERY_LOW')
+        self._register_hook(LrSchedulerHook(**cfg['warmup_setting']) if 'warmup_setting' in cfg else LrSchedulerHook(), 'NORMAL')
+        self._register_hook(OptimizerHook(cfg.get('optimizer_grad_clip_cfg'), cfg['training_epochs']), 'NORMAL')
+        self._register_hook(SpeedHook(), 'LOW')
+        self._register_hook(EvaluationHook(), 'NORMAL')
 
     def _call_hooks(self, fn_name):
         for hook in self._hooks:
@@ -69,6 +76,8 @@ class Executor(object):
         return {k: v for k, v in self.config_dict.items() if type(v) in types}
 
     def save(self):
+        """Rank 0 writes the checkpoint.  BatchNorm running statistics are per replica (no SyncBN, like the reference's
+        DataParallel, where only replica 0's buffers persist): rank 0's are the ones saved."""
         cfg = self.config_dict
         save_checkpoint(cfg['model'], os.path.join(cfg['work_dir'], 'epoch_' + str(cfg['epoch']) + '.pth'),
                         optimizer=cfg['optimizer'], lr_scheduler=cfg['lr_scheduler'], meta=self._generate_meta())
@@ -113,8 +122,13 @@ class Executor(object):
             self._call_hooks('before_train_iter')
             image_batch, annotation_batch, meta_batch = shard_batch(data_batch)
             cfg.update(batch_size=len(annotation_batch))
-            predict_outputs = cfg['model'](self._to_device(image_batch))
-            loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
+            if len(annotation_batch) == 0:
+                # the last batch had fewer images than ranks: this rank has nothing to compute but must still take part in the
+                # collectives of the step (positive counters, loss values, gradients), with zeros
+                loss_dict = cfg['model'].empty_shard_loss()
+            else:
+                predict_outputs = cfg['model'](self._to_device(image_batch))
+                loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
             cfg.update(loss=loss_dict['loss'])
             for name, value in loss_dict['loss_values'].items():
                 cfg['train_average_meter'].update(name, value, cfg['batch_size'])

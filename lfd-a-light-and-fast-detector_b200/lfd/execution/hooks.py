@@ -43,7 +43,8 @@ class OptimizerHook(Hook):
     def after_train_iter(self, executor):
         cfg = executor.config_dict
         cfg['optimizer'].zero_grad()
-        cfg['loss'].backward()
+        if cfg['loss'] is not None:        # None: this rank's shard of the batch was empty; it still joins the all-reduce with zeros
+            cfg['loss'].backward()
         # one flat-bucket all-reduce (no-op for a single process); losses already normalised by the global number of
         # positives (LFD.get_loss) add up over ranks, otherwise the per-rank means are averaged
         allreduce_gradients(cfg['model'].parameters(), average=not getattr(cfg['model'], 'loss_globally_normalised', False))
@@ -129,6 +130,30 @@ class LoggerHook(Hook):
         cfg = executor.config_dict
         cfg['logger'].info('val epoch %d: %s' % (cfg['epoch'], ' '.join('%s %.5f' % kv for kv in cfg['val_average_meter'].averages().items())))
         cfg['val_average_meter'].reset()
+
+
+class EvaluationHook(Hook):
+    """reference lfd/execution/hooks/evaluation_hook.py: feed every validation batch's results to the evaluator, evaluate at
+    the end of the validation epoch.  One process per GPU: the per-rank result shards are all-gathered (python objects, small)
+    so that every rank's evaluator sees the whole batch in rank order."""
+
+    def after_val_iter(self, executor):
+        cfg = executor.config_dict
+        if cfg.get('evaluator') is None:
+            return
+        results, meta = cfg['eval_results']
+        rank, ws = world()
+        if ws > 1:
+            import torch.distributed as dist
+            shards = [None] * ws
+            dist.all_gather_object(shards, (results, meta))
+            results = [r for sh in shards for r in sh[0]]
+            meta = [m for sh in shards for m in sh[1]]
+        cfg['evaluator'].update((results, meta))
+
+    def after_val_epoch(self, executor):
+        if executor.config_dict.get('evaluator') is not None:
+            executor.config_dict['evaluator'].evaluate()
 
 
 class CheckpointHook(Hook):

@@ -9,7 +9,7 @@ GLOBAL number of positives like the reference does after its DataParallel gather
 import torch
 import torch.distributed as dist
 
-__all__ = ['world', 'shard_range', 'shard_batch', 'allreduce_gradients', 'allreduce_scalar']
+__all__ = ['world', 'shard_range', 'shard_batch', 'allreduce_gradients', 'allreduce_scalar', 'broadcast_module_state']
 
 
 def world():
@@ -67,3 +67,27 @@ def allreduce_gradients(parameters, average=True):
             p.grad.copy_(g)
         off += n
     return off
+
+
+def broadcast_module_state(module, src=0):
+    """Every parameter and buffer of `module` takes rank `src`'s value (one flat bucket per dtype).  No-op for one process."""
+    r, w = world()
+    if w == 1:
+        return 0
+    tensors = [p.data for p in module.parameters()] + [b.data for b in module.buffers()]
+    seen, uniq = set(), []
+    for t in tensors:                       # shared tensors (share_head_flag aliases) travel once
+        if t.data_ptr() not in seen and t.numel():
+            seen.add(t.data_ptr())
+            uniq.append(t)
+    n = 0
+    for dt in sorted(set(t.dtype for t in uniq), key=str):
+        group = [t for t in uniq if t.dtype == dt]
+        flat = torch.cat([t.reshape(-1) for t in group])
+        dist.broadcast(flat, src)
+        off = 0
+        for t in group:
+            t.copy_(flat[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        n += off
+    return n

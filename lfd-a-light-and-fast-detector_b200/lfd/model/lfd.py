@@ -180,6 +180,10 @@ class LFD(nn.Module):
     def _assign(self, sizes, gt_bboxes_list, gt_labels_list, device):
         lv, P = self._levels(sizes)
         N = len(gt_bboxes_list)
+        for l in gt_labels_list:           # the reference indexes a [P, C] target with the label and raises on a bad one
+            l = numpy.asarray(l).reshape(-1)
+            if l.size and (int(l.min()) < 0 or int(l.max()) >= self._num_classes):
+                raise IndexError('gt label out of range [0, %d): %s' % (self._num_classes, sorted(set(l.tolist()))[:8]))
         gmax = max([int(b.shape[0]) for b in gt_bboxes_list] + [1])
         boxes = torch.zeros((N, gmax, 4), dtype=torch.float32)
         labels = torch.zeros((N, gmax), dtype=torch.int32)
@@ -236,8 +240,7 @@ class LFD(nn.Module):
         # group before the loss kernels use them; per-rank losses / gradients then ADD up to the global-batch values and the
         # gradient all-reduce must sum, not average (`loss_globally_normalised`, read by OptimizerHook).
         self.loss_globally_normalised = False
-        if self.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
+        if self._data_parallel():
             torch.distributed.all_reduce(counters, op=torch.distributed.ReduceOp.SUM)
             self.loss_globally_normalised = True
         N, P = cls_pred.shape[0], cls_pred.shape[1]
@@ -264,8 +267,29 @@ class LFD(nn.Module):
             loss = _DetectionLossFn.apply(cls_pred, reg_pred, total, grad_cls, grad_reg)
         else:
             loss = total
-        vals = torch.stack([total, cls_loss, reg_loss]).tolist()   # one D2H sync instead of the reference's three
+        vals = torch.stack([total, cls_loss, reg_loss])
+        if self.loss_globally_normalised:   # logged values = the GLOBAL batch's losses (per-rank sums over the global positive count add up)
+            torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.SUM)
+        vals = vals.tolist()                # one D2H sync instead of the reference's three
         return dict(loss=loss, loss_values=dict(loss=vals[0], classification_loss=vals[1], regression_loss=vals[2]))
+
+    def _data_parallel(self):
+        return self.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1
+
+    def empty_shard_loss(self):
+        """A rank whose shard of the batch is empty: joins the two collectives of get_loss (positive counters, logged loss values)
+        with zeros and returns loss=None (OptimizerHook then reduces zero gradients)."""
+        device = self._device()
+        self.loss_globally_normalised = False
+        vals = torch.zeros(3, dtype=torch.float32, device=device)
+        if self._data_parallel():
+            counters = torch.zeros((2,), dtype=torch.int32, device=device)
+            torch.distributed.all_reduce(counters, op=torch.distributed.ReduceOp.SUM)
+            self.loss_globally_normalised = True
+            torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.SUM)
+        vals = vals.tolist()
+        return dict(loss=None, loss_values=dict(loss=vals[0], classification_loss=vals[1], regression_loss=vals[2]))
 
     # ------------------------------------------------------------------ post-process
     def _post_cfg(self, N, sizes, score_thr, iou_thr, class_agnostic):

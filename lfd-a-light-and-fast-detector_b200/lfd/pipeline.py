@@ -12,6 +12,30 @@ import torch
 from . import _native as nat
 
 
+def bind_host_to_gpu_numa_node(device):
+    """Restrict this process to the CPU cores of the NUMA node the GPU hangs off (sysfs), so that host buffers pinned afterwards
+    are first-touched on that node and the H2D DMA does not cross the inter-socket link.  One process per GPU (the layout of
+    bench.py / the Executor), so the affinity is per GPU.  Returns the node (None when the topology cannot be read)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bdf = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ForwardPostPipeline(object):
     """Software pipeline over batches on two streams: forward(i+1) starts as soon as forward(i) is done, while the (small,
     latency-bound) score / decode / NMS kernels of batch i run next to it.  The forward writes alternating output slots; a
@@ -51,7 +75,7 @@ class ForwardPostPipeline(object):
 
 class StreamingDetector(object):
 
-    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None, depth=3):
+    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None, depth=3, copy_streams=2):
         self.model = model
         self.depth = max(2, int(depth))     # batches in flight: copy of i+2 | forward of i+1 | post-process + read-back of i
         self.device = device if device is not None else next(model.parameters()).device
@@ -60,7 +84,10 @@ class StreamingDetector(object):
         self.max_out = min(int(max_out), int(model.max_detections_per_image))
         dev = self.device
         with torch.cuda.device(dev):
-            self.copy_stream = torch.cuda.Stream(device=dev)
+            # the batch goes up in `copy_streams` chunks on as many streams: two DMA engines in flight fill the PCIe link better
+            # than one 22 MB copy (measured in bench.py: e2e.h2d_gbps)
+            self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(int(copy_streams), batch)))]
+            self.copy_stream = self.copy_streams[0]
         self.plan = model.inference_plan(batch, height, width, dev)
         for i, hw in enumerate(self.plan.level_sizes):
             model._head_indexes_to_feature_map_sizes[i] = hw
@@ -74,7 +101,7 @@ class StreamingDetector(object):
                 out_dets=torch.empty((batch, self.max_out, 5), dtype=torch.float32).pin_memory(),
                 out_labels=torch.empty((batch, self.max_out), dtype=torch.int32).pin_memory(),
                 out_count=torch.empty((batch + 1,), dtype=torch.int32).pin_memory(),
-                h2d=torch.cuda.Event(), done=torch.cuda.Event(), busy=False))
+                h2d=torch.cuda.Event(), h2d_aux=[torch.cuda.Event() for _ in self.copy_streams[1:]], done=torch.cuda.Event(), busy=False))
         self.step = 0
         self.h2d_bytes = batch * height * width * 3
         self.d2h_bytes = batch * self.max_out * (5 * 4 + 4) + (batch + 1) * 4
@@ -84,9 +111,8 @@ class StreamingDetector(object):
         s = self.slots[self.step % self.depth]
         if s['busy']:
             s['done'].synchronize()
-        with torch.cuda.stream(self.copy_stream):
-            s['x'].copy_(frames_u8, non_blocking=True)
-            s['h2d'].record(self.copy_stream)
+        self.stage_input(self.step % self.depth, frames_u8)
+
         def read_back(results):          # runs with the post-process stream current
             dets, labels, _, count = results
             s['out_dets'].copy_(dets[:, :self.max_out], non_blocking=True)
@@ -98,6 +124,21 @@ class StreamingDetector(object):
         s['busy'] = True
         self.step += 1
         return (self.step - 1) % self.depth
+
+    def stage_input(self, slot, frames_u8):
+        """Host -> device copy of one batch into slot `slot`, split over the copy streams; s['h2d'] fires when all of it landed."""
+        s = self.slots[slot]
+        k = len(self.copy_streams)
+        bounds = [(self.N * i) // k for i in range(k + 1)]
+        for i in range(1, k):
+            with torch.cuda.stream(self.copy_streams[i]):
+                s['x'][bounds[i]:bounds[i + 1]].copy_(frames_u8[bounds[i]:bounds[i + 1]], non_blocking=True)
+                s['h2d_aux'][i - 1].record(self.copy_streams[i])
+        with torch.cuda.stream(self.copy_stream):
+            s['x'][bounds[0]:bounds[1]].copy_(frames_u8[bounds[0]:bounds[1]], non_blocking=True)
+            for ev in s['h2d_aux']:
+                self.copy_stream.wait_event(ev)
+            s['h2d'].record(self.copy_stream)
 
     def collect(self, slot):
         """Blocks until the slot's results are on the host.  -> (dets [N,max_out,5], labels [N,max_out], counts [N])."""

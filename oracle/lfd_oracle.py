@@ -538,7 +538,7 @@ def nms(dets, thr):
     return np.asarray(keep, np.int64)
 
 
-def multiclass_nms(boxes, scores, score_thr, iou_thr, class_agnostic=False, max_num=-1):
+def multiclass_nms(boxes, scores, score_thr, iou_thr, class_agnostic=False, max_num=-1, nms_fn=None):
     """nms.py:161-220 + batched_nms :119-158.  boxes [K,4], scores [K,C] (bg column already dropped).
 
     Returns (dets [k,5], labels [k], src [k]) with src = flat index point*C + class of each kept row.
@@ -559,7 +559,7 @@ def multiclass_nms(boxes, scores, score_thr, iou_thr, class_agnostic=False, max_
     else:
         off = lab.astype(np.float32) * (b.max() + np.float32(1))
         bn = (b + off[:, None]).astype(np.float32)
-    keep = nms(np.concatenate([bn, s[:, None]], 1), iou_thr)
+    keep = (nms_fn or nms)(np.concatenate([bn, s[:, None]], 1), iou_thr)   # nms_fn: e.g. the reference's compiled nms_ext.nms
     out = np.concatenate([bn[keep], s[keep, None]], 1)
     if not class_agnostic:
         out[:, :4] = out[:, :4] - off[keep][:, None]
@@ -592,7 +592,7 @@ def decode_image(cfg, cls_i, reg_i, sizes, height, width, resize_scale=1.0):
     return torch.cat(sc_all), boxes
 
 
-def get_results(cfg, cls, reg, sizes, meta_batch, score_thr, iou_thr, class_agnostic=False):
+def get_results(cfg, cls, reg, sizes, meta_batch, score_thr, iou_thr, class_agnostic=False, nms_fn=None):
     """lfd.py:397-432: per image rows [label, score, x, y, w, h] with w = x2 - x1 + 1.
 
     Also returns, per image, the flat source indices (point*C + class) of the kept rows.
@@ -601,7 +601,7 @@ def get_results(cfg, cls, reg, sizes, meta_batch, score_thr, iou_thr, class_agno
     for i in range(cls.shape[0]):
         m = meta_batch[i]
         sc, bx = decode_image(cfg, cls[i], reg[i], sizes, m['resized_height'], m['resized_width'], m['resize_scale'])
-        dets, labels, src = multiclass_nms(bx.numpy(), sc.numpy(), score_thr, iou_thr, class_agnostic)
+        dets, labels, src = multiclass_nms(bx.numpy(), sc.numpy(), score_thr, iou_thr, class_agnostic, nms_fn=nms_fn)
         rows = []
         for d, lab in zip(dets, labels):
             rows.append([int(lab), float(d[4]), float(d[0]), float(d[1]),

@@ -62,3 +62,14 @@ def rel_err(a, b):
 
 def rows_to_array(rows):
     return np.asarray(rows, np.float64).reshape(-1, 6)
+
+
+def assert_same_detections(got_src, want_src, want_scores, what, score_tol=2e-3):
+    """Kept (point, class) indices of the CUDA pipeline vs the oracle pipeline, end to end: the kept SET must be identical;
+    the order (score descending) must be identical except for swaps between detections whose ORACLE scores differ by less
+    than `score_tol` -- two pipelines that agree to 1e-3 on the logits cannot agree on the order of two scores closer than that."""
+    got_src, want_src = list(got_src), list(want_src)
+    assert sorted(got_src) == sorted(want_src), (what, len(got_src), len(want_src), sorted(set(got_src) ^ set(want_src))[:10])
+    score = dict(zip(want_src, [float(v) for v in want_scores]))
+    for a, b in zip(got_src[:-1], got_src[1:]):
+        assert score[a] >= score[b] - score_tol, (what, 'order', a, b, score[a], score[b])

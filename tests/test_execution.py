@@ -135,3 +135,72 @@ def test_gloo_world2_optimizer_hook_sums_globally_normalised_losses():
     for flag, expect in ((True, 3.0), (False, 1.5)):       # 1 + 2 summed / averaged
         assert torch.equal(r0[flag], r1[flag])
         assert torch.allclose(r0[flag], torch.full_like(r0[flag], expect))
+
+
+def test_hooks_are_registered_like_the_reference():
+    """executor.py:67-99 of the reference: checkpoint LOWEST, logger VERY_LOW, lr scheduler / optimizer / evaluation NORMAL (in that
+    registration order), speed LOW."""
+    from lfd.execution.executor import Executor
+    ex = Executor.__new__(Executor)
+    ex.config_dict = dict(training_epochs=3)
+    ex._hooks = []
+    ex._register_all_hooks()
+    assert [type(h).__name__ for h in ex._hooks] == ['LrSchedulerHook', 'OptimizerHook', 'EvaluationHook', 'SpeedHook', 'LoggerHook', 'CheckpointHook']
+
+
+def _worker_sync(rank, world_size, port, out):
+    """broadcast_module_state, the empty-shard step and the EvaluationHook gather on two gloo ranks."""
+    from lfd.execution.hooks import EvaluationHook, OptimizerHook
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    torch.manual_seed(100 + rank)                       # ranks start from DIFFERENT parameters and buffers
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1), torch.nn.BatchNorm2d(4))
+    net[1].running_mean.add_(float(rank))
+    before = [t.clone() for t in list(net.parameters()) + list(net.buffers())]
+    n = parallel.broadcast_module_state(net)
+    state = [t.clone() for t in list(net.parameters()) + list(net.buffers())]
+    # empty shard on rank 1: loss None, zero gradients join the SUM all-reduce
+    opt = torch.optim.SGD(net.parameters(), lr=1.0)
+    net.loss_globally_normalised = True
+    loss = net[0](torch.ones(1, 3, 2, 2)).sum() if rank == 0 else None
+
+    class Ex(object):
+        config_dict = dict(model=net, optimizer=opt, loss=loss, epoch=0)
+    w0 = net[0].weight.detach().clone()
+    OptimizerHook(None, 10).after_train_iter(Ex())
+    step = (w0 - net[0].weight.detach()).clone()
+
+    class Ev(object):
+        def __init__(self):
+            self.seen, self.done = [], 0
+
+        def update(self, results):
+            self.seen.append(results)
+
+        def evaluate(self):
+            self.done += 1
+    ev = Ev()
+
+    class Ex2(object):
+        config_dict = dict(evaluator=ev, eval_results=([[[0, 0.5 + rank, 1, 2, 3, 4]]], [dict(image_id=10 + rank)]))
+    hook = EvaluationHook()
+    hook.after_val_iter(Ex2())
+    hook.after_val_epoch(Ex2())
+    torch.save(dict(n=n, before=before, state=state, step=step, seen=ev.seen, done=ev.done), out % rank)
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_broadcast_empty_shard_and_evaluation_gather():
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 's%d.pt')
+        port = 33500 + os.getpid() % 2000
+        mp.spawn(_worker_sync, args=(2, port, out), nprocs=2, join=True)
+        r0, r1 = torch.load(out % 0, weights_only=False), torch.load(out % 1, weights_only=False)
+    assert r0['n'] == r1['n'] > 0
+    assert not all(torch.equal(a, b) for a, b in zip(r0['before'], r1['before']))
+    for a, b, c in zip(r0['state'], r1['state'], r0['before']):
+        assert torch.equal(a, b) and torch.equal(a, c)        # everybody holds rank 0's values
+    assert torch.equal(r0['step'], r1['step']) and float(r0['step'].abs().sum()) > 0   # rank 0's gradient, summed with zeros
+    for r in (r0, r1):
+        (results, meta), = r['seen']
+        assert [m['image_id'] for m in meta] == [10, 11] and [res[0][1] for res in results] == [0.5, 1.5] and r['done'] == 1

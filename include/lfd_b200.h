@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LFD_B200_ABI_VERSION 3
+#define LFD_B200_ABI_VERSION 4
 #define LFD_MAX_LEVELS 8
 #define LFD_MAX_BRANCHES 8
 
@@ -195,6 +195,102 @@ int lfd_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, 
                                    float* losses, lfd_stream stream);
 int lfd_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets, const float* d_losses, int M, int C,
                                     float gamma, float alpha, float* d_logits, lfd_stream stream);
+
+/* ------------------------------------------------------------------------------------------ training step
+ * What the reference gets from autograd over its conv / BatchNorm2d / GroupNorm / ReLU modules in train mode
+ * (lfd/model/backbone/lfd_resnet.py:96-154,354-473, neck/simple_neck.py:35-74, head/lfd_head.py:85-185), i.e. the body of
+ * Executor.train's `model(x)` ... `loss.backward()` (lfd/execution/executor.py:185-214), and from
+ * clip_grad_norm_ + torch.optim.SGD.step (lfd/execution/hooks/optimizer_hook.py:21-36).
+ *
+ * A training plan is an ordered list of lfd_top ops over ONE workspace (bf16 NHWC activations, their bf16 gradients, fp64
+ * statistics, packed bf16 weight operands, fp32 weight-gradient staging); parameters, their gradients and the BatchNorm
+ * running statistics are the caller's fp32 device tensors, referenced by absolute pointers that stay fixed for the plan's
+ * lifetime.  off[] are byte offsets into the workspace (-1 = unused), ptr[] absolute device pointers:
+ *
+ *   kind             off[0]   off[1]  off[2]  off[3]   off[4]     off[5]   off[6]  off[7]   ptr[0..3]
+ *   PACK             -        -       -       -        -          -        -       -        table (lfd_pack_desc[n_desc], device)
+ *   STEM0 / CONV     in       out     res     gnstats  packed w   -        -       -        -          (as lfd_op; STEM0 reads the run-time input;
+ *                                                                                                        CONV is also the data-gradient conv: in = dz
+ *                                                                                                        (zero-inserted for stride 2), packed w = PACK_CONV_DGRAD,
+ *                                                                                                        res = out accumulates into an existing gradient)
+ *   BN_STATS         z        -       -       sums     -          -        -       -        -
+ *   BN_APPLY         z        y       res     sums     -          -        -       -        gamma, beta, running_mean, running_var
+ *   GN_APPLY         in       out     -       gnstats  -          -        -       -        gamma, beta
+ *   HEAD_FINAL       raw      -       -       gnstats  staging    -        -       -        gamma, beta, cls out, reg out
+ *   HEAD_FINAL_BWD   raw      dact    -       gnstats  staging    dstage   dscale  -        gamma, beta, grad cls, grad reg
+ *   NORM_BWD_REDUCE  dy       y       z       fsums    bsums      -        -       -        gamma, beta, -, -, running_mean, running_var (frozen)
+ *   NORM_BWD_APPLY   dy       y       z       fsums    bsums      dz       dz_up   dres     gamma, beta, dgamma, dbeta, running_mean, running_var (frozen)
+ *   WGRAD            x        dz      -       -        -          dstage   -       -        -
+ *   WGRAD_STEM       -        dz      -       -        -          dstage   -       -        -          (x = the run-time input image)
+ *   UNPACK           -        -       -       -        -          -        -       -        table (lfd_unpack_desc[n_desc], device)
+ *   ZERO             begin    bytes   -       -        -          -        -       -        -          (cudaMemsetAsync of a workspace region)
+ *
+ * head staging (fp32): w[n_out][C] (bf16-rounded values), scale[n_out], shift[n_out] = bias * scale, bias[n_out];
+ * head dstage (fp32): dW[n_out][C], dbias[n_out]; dscale (fp32): the level's Scale gradient [1].  wgrad dstage (fp32): [ksize^2][Cin][Cout].
+ * BatchNorm statistics are taken over the STORED bf16 conv output; GroupNorm ones come from the conv epilogue as in inference. */
+enum { LFD_TOP_PACK = 0, LFD_TOP_STEM0 = 1, LFD_TOP_CONV = 2, LFD_TOP_BN_STATS = 3, LFD_TOP_BN_APPLY = 4, LFD_TOP_GN_APPLY = 5,
+       LFD_TOP_HEAD_FINAL = 6, LFD_TOP_HEAD_FINAL_BWD = 7, LFD_TOP_NORM_BWD_REDUCE = 8, LFD_TOP_NORM_BWD_APPLY = 9, LFD_TOP_WGRAD = 10,
+       LFD_TOP_WGRAD_STEM = 11, LFD_TOP_UNPACK = 12, LFD_TOP_ZERO = 13 };
+enum { LFD_WGRAD_UMMA = 0, LFD_WGRAD_SIMT = 1 }; /* SIMT = cross-check kernel, validation only */
+
+typedef struct lfd_top {
+    int32_t kind;
+    int32_t N, H, W, Cin, Ho, Wo, Cout, ksize, stride;
+    int32_t relu, groups, cc, n_cls, n_reg, point_off, P, cls_stride;
+    int32_t accumulate;   /* NORM_BWD_APPLY: dres += g instead of dres = g */
+    int32_t upH, upW;     /* NORM_BWD_APPLY with dz_up: size of the zero-inserted gradient map (the stride-2 conv's input size) */
+    int32_t n_desc, max_n;/* PACK / UNPACK: table entries, largest element count of an entry */
+    int32_t impl;         /* WGRAD: LFD_WGRAD_UMMA | LFD_WGRAD_SIMT; CONV: LFD_CONV_UMMA | LFD_CONV_SIMT */
+    int32_t frozen;       /* BN_APPLY / NORM_BWD_* (BatchNorm): the module is in eval mode -- normalise with the running statistics
+                             (ptr[2..3] of BN_APPLY, ptr[4..5] of NORM_BWD_*), do not update them, no batch-statistics terms in dz */
+    int32_t pad_;
+    float eps, momentum;
+    int64_t off[8];
+    const void* ptr[6];
+} lfd_top;
+
+/* entries of the PACK / UNPACK tables (device memory, absolute pointers) */
+enum { LFD_PACK_CONV_FWD = 0, LFD_PACK_CONV_DGRAD = 1, LFD_PACK_STEM = 2, LFD_PACK_ROUND_F32 = 3, LFD_PACK_SCALE_SHIFT = 4 };
+typedef struct lfd_pack_desc {
+    int32_t kind;
+    int32_t Cout, Cin, k, cc; /* conv: OIHW dims of the fp32 parameter, cc = channel chunk of the packed operand (lfd_conv_query) */
+    int32_t n;                /* destination elements */
+    const float* src;         /* the parameter; SCALE_SHIFT: the bias [n] (or NULL) */
+    const float* src2;        /* SCALE_SHIFT: the level's scalar Scale parameter (or NULL = 1) */
+    void* dst;                /* CONV_FWD: bf16 [Cin/cc][k*k][cc/8][Cout][8]; CONV_DGRAD: the transposed conv's operand
+                                 bf16 [Cout/cc][k*k][cc/8][Cin][8] with flipped taps; STEM: bf16 [kh][2][Cout][8];
+                                 ROUND_F32: fp32 copy holding bf16-rounded values; SCALE_SHIFT: scale[n] */
+    void* dst2;               /* SCALE_SHIFT: shift[n] = bias * scale */
+    void* dst3;               /* SCALE_SHIFT: bias[n] */
+} lfd_pack_desc;
+enum { LFD_UNPACK_CONV = 0, LFD_UNPACK_ADD = 1 };
+typedef struct lfd_unpack_desc {
+    int32_t kind;
+    int32_t Cout, Cin, kk;    /* UNPACK_CONV: staging [kk][Cin][Cout] -> gradient [Cout][Cin][kk] (+=) */
+    int32_t n;                /* elements */
+    int32_t pad_;
+    const float* src;
+    float* dst;               /* dst[i] += ... */
+} lfd_unpack_desc;
+
+typedef struct lfd_train_plan lfd_train_plan;
+int lfd_train_plan_create(const lfd_top* ops, int n_ops, int64_t workspace_bytes, lfd_train_plan** out);
+int lfd_train_plan_destroy(lfd_train_plan* plan);
+int lfd_train_plan_num_ops(const lfd_train_plan* plan);
+/* Enqueues every op in order on `stream`.  use_graph != 0: captured into a CUDA graph on first use per (input, workspace). */
+int lfd_train_plan_run(lfd_train_plan* plan, const void* input, int input_format, void* workspace, int use_graph, lfd_stream stream);
+/* one eager pass with a CUDA event pair around every op (synchronises): ms_per_op float[lfd_train_plan_num_ops()] (host) */
+int lfd_train_plan_profile(lfd_train_plan* plan, const void* input, int input_format, void* workspace, float* ms_per_op, lfd_stream stream);
+/* run a single op (tests) */
+int lfd_run_top(const lfd_top* op, const void* input, int input_format, void* workspace, lfd_stream stream);
+
+/* sqnorm double[1] (device) = sum of grads^2 (zeroed inside) -- the total_norm^2 of clip_grad_norm_(norm_type=2) */
+int lfd_grad_sqnorm(const float* grads, int64_t n, double* sqnorm, lfd_stream stream);
+/* torch.optim.SGD.step over flat fp32 buffers, preceded by the clip: g *= grad_scale; if max_norm > 0:
+ * g *= min(1, max_norm / (grad_scale * sqrt(*sqnorm) + 1e-6)) (written back, like clip_grad_norm_); g += weight_decay * p;
+ * buf = momentum * buf + (1 - dampening) * g; p -= lr * (nesterov ? g + momentum * buf : buf).  momentum_buf may be NULL. */
+int lfd_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, float lr, float momentum, float dampening,
+                 float weight_decay, int nesterov, float max_norm, float grad_scale, const double* sqnorm, lfd_stream stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 #include "../../include/lfd_b200.h"
 #include "conv_common.cuh"
 #include "kernels.cuh"
+#include "train.cuh"
 
 using namespace lfd;
 
@@ -26,6 +27,8 @@ static int fail(int code, const char* fmt, ...) {
         cudaError_t _e = (expr);                                                               \
         if (_e != cudaSuccess) return fail(LFD_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
+
+static inline cudaStream_t st_of(lfd_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static int sm_count() {   // of the CURRENT device (cached per device ordinal)
     static int cached[kMaxDevices] = {};
@@ -576,5 +579,304 @@ extern "C" int lfd_sigmoid_focal_loss_backward(const float* logits, const int64_
     if (M < 0 || C < 1 || (M > 0 && (!logits || !targets || !d_losses || !d_logits))) return fail(LFD_ERR_INVALID, "lfd_sigmoid_focal_loss_backward: bad arguments");
     if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "sigmoid focal loss: no CUDA device");
     CUDA_TRY(focal_backward_launch(logits, reinterpret_cast<const long long*>(targets), d_losses, M, C, gamma, alpha, d_logits, reinterpret_cast<cudaStream_t>(stream)));
+    return LFD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ training plan
+struct PlannedTop {
+    lfd_top op;
+    PlannedOp conv;   // STEM0 / CONV: the tcgen05 configuration (same kernels as the inference plan)
+};
+
+struct lfd_train_plan {
+    std::vector<PlannedTop> ops;
+    int64_t workspace_bytes;
+    struct GraphEntry { cudaGraphExec_t exec; const void* input; void* ws; int fmt; };
+    std::vector<GraphEntry> graphs;
+};
+
+static lfd_op conv_op_of(const lfd_top& t) {
+    lfd_op o;
+    memset(&o, 0, sizeof(o));
+    o.kind = t.kind == LFD_TOP_STEM0 ? LFD_OP_STEM0 : LFD_OP_CONV;
+    o.N = t.N; o.H = t.H; o.W = t.W; o.Cin = t.Cin; o.Ho = t.Ho; o.Wo = t.Wo; o.Cout = t.Cout;
+    o.ksize = t.ksize; o.stride = t.stride; o.relu = t.relu; o.gn_groups = t.groups; o.cc = t.cc;
+    o.in_off = t.off[0]; o.out_off = t.off[1]; o.res_off = t.off[2]; o.stats_off = t.off[3];
+    o.ds_out_off = -1;
+    o.dtype = LFD_DTYPE_BF16;
+    return o;
+}
+
+static int plan_top(const lfd_top& t, int64_t ws_bytes, PlannedTop* out) {
+    out->op = t;
+    for (int i = 0; i < 8; ++i)
+        if (t.off[i] >= ws_bytes && !(t.kind == LFD_TOP_ZERO && i == 1)) return fail(LFD_ERR_INVALID, "training op kind %d: off[%d] = %lld outside the workspace", t.kind, i, (long long)t.off[i]);
+    switch (t.kind) {
+        case LFD_TOP_STEM0:
+        case LFD_TOP_CONV: {
+            if (t.off[1] < 0 || t.off[4] < 0 || (t.kind == LFD_TOP_CONV && t.off[0] < 0)) return fail(LFD_ERR_INVALID, "training conv: missing in / out / packed-weight offset");
+            lfd_op o = conv_op_of(t);
+            o.weight = reinterpret_cast<const void*>(1);   // placeholder: resolved against the workspace at launch
+            return plan_op(o, t.impl, &out->conv);
+        }
+        case LFD_TOP_WGRAD: {
+            WgradGeom g = {t.N, t.H, t.W, t.Cin, t.Ho, t.Wo, t.Cout, t.ksize, t.stride};
+            if (t.impl == LFD_WGRAD_UMMA && !wgrad_umma_supported(g))
+                return fail(LFD_ERR_UNSUPPORTED, "wgrad %dx%d s%d Cin=%d Cout=%d unsupported by the tcgen05 kernel", t.ksize, t.ksize, t.stride, t.Cin, t.Cout);
+            break;
+        }
+        case LFD_TOP_PACK: case LFD_TOP_UNPACK:
+            if (!t.ptr[0] || t.n_desc < 0 || t.max_n < 0) return fail(LFD_ERR_INVALID, "pack / unpack: missing table");
+            break;
+        case LFD_TOP_BN_STATS: case LFD_TOP_BN_APPLY: case LFD_TOP_GN_APPLY: case LFD_TOP_HEAD_FINAL: case LFD_TOP_HEAD_FINAL_BWD:
+        case LFD_TOP_NORM_BWD_REDUCE: case LFD_TOP_NORM_BWD_APPLY: case LFD_TOP_WGRAD_STEM: case LFD_TOP_ZERO:
+            break;
+        default:
+            return fail(LFD_ERR_INVALID, "unknown training op kind %d", t.kind);
+    }
+    return LFD_OK;
+}
+
+template <typename T>
+static T* at(uint8_t* ws, int64_t off) { return off >= 0 ? reinterpret_cast<T*>(ws + off) : nullptr; }
+
+static int launch_top(const PlannedTop& pt, const void* input, int fmt, uint8_t* ws, cudaStream_t st) {
+    const lfd_top& t = pt.op;
+    const int sms = sm_count();
+    switch (t.kind) {
+        case LFD_TOP_PACK:
+            CUDA_TRY(pack_launch(reinterpret_cast<const PackDesc*>(t.ptr[0]), t.n_desc, t.max_n, st));
+            break;
+        case LFD_TOP_UNPACK:
+            CUDA_TRY(unpack_launch(reinterpret_cast<const UnpackDesc*>(t.ptr[0]), t.n_desc, t.max_n, st));
+            break;
+        case LFD_TOP_ZERO:
+            CUDA_TRY(cudaMemsetAsync(ws + t.off[0], 0, (size_t)t.off[1], st));
+            break;
+        case LFD_TOP_STEM0:
+        case LFD_TOP_CONV: {
+            PlannedOp po = pt.conv;
+            po.op.weight = ws + t.off[4];
+            return launch_op(po, 0, input, fmt, ws, nullptr, nullptr, 0, 0, t.impl, st);
+        }
+        case LFD_TOP_BN_STATS: {
+            BnStatsParams p;
+            p.z = at<const __nv_bfloat16>(ws, t.off[0]); p.sums = at<double>(ws, t.off[3]);
+            p.M = (long long)t.N * t.H * t.W; p.C = t.Cout;
+            CUDA_TRY(bn_stats_launch(p, sms, st));
+            break;
+        }
+        case LFD_TOP_BN_APPLY: {
+            BnApplyParams p;
+            p.z = at<const __nv_bfloat16>(ws, t.off[0]); p.y = at<__nv_bfloat16>(ws, t.off[1]); p.res = at<const __nv_bfloat16>(ws, t.off[2]);
+            p.sums = at<const double>(ws, t.off[3]);
+            p.gamma = reinterpret_cast<const float*>(t.ptr[0]); p.beta = reinterpret_cast<const float*>(t.ptr[1]);
+            p.running_mean = reinterpret_cast<float*>(const_cast<void*>(t.ptr[2])); p.running_var = reinterpret_cast<float*>(const_cast<void*>(t.ptr[3]));
+            p.M = (long long)t.N * t.H * t.W; p.C = t.Cout; p.relu = t.relu; p.eps = t.eps; p.momentum = t.momentum; p.frozen = t.frozen;
+            if (!p.gamma || !p.beta || (t.frozen && (!p.running_mean || !p.running_var))) return fail(LFD_ERR_INVALID, "bn_apply: gamma / beta / running statistics missing");
+            CUDA_TRY(bn_apply_launch(p, sms, st));
+            break;
+        }
+        case LFD_TOP_GN_APPLY: {
+            GnApplyParams p;
+            p.in = at<const __nv_bfloat16>(ws, t.off[0]); p.out = at<__nv_bfloat16>(ws, t.off[1]); p.stats = at<const double>(ws, t.off[3]);
+            p.gamma = reinterpret_cast<const float*>(t.ptr[0]); p.beta = reinterpret_cast<const float*>(t.ptr[1]);
+            p.N = t.N; p.HW = t.H * t.W; p.C = t.Cout; p.groups = t.groups; p.eps = t.eps; p.f16 = 0; p.tl = nullptr;
+            CUDA_TRY(gn_apply_launch(p, sms, st));
+            break;
+        }
+        case LFD_TOP_HEAD_FINAL: {
+            HeadFinalParams p;
+            const int no = t.n_cls + t.n_reg;
+            const float* stg = at<const float>(ws, t.off[4]);
+            p.in = at<const __nv_bfloat16>(ws, t.off[0]); p.stats = at<const double>(ws, t.off[3]);
+            p.gamma = reinterpret_cast<const float*>(t.ptr[0]); p.beta = reinterpret_cast<const float*>(t.ptr[1]);
+            p.w = stg; p.scale = stg + (size_t)no * t.Cout; p.shift = p.scale + no;
+            p.cls = t.n_cls ? reinterpret_cast<float*>(const_cast<void*>(t.ptr[2])) : nullptr;
+            p.reg = t.n_reg ? reinterpret_cast<float*>(const_cast<void*>(t.ptr[3])) : nullptr;
+            p.N = t.N; p.HW = t.H * t.W; p.C = t.Cout; p.groups = t.groups; p.n_out = no; p.n_cls = t.n_cls;
+            p.P = t.P; p.point_off = t.point_off; p.cls_stride = t.cls_stride; p.eps = t.eps; p.f16 = 0; p.tl = nullptr;
+            if ((t.n_cls && !p.cls) || (t.n_reg && !p.reg)) return fail(LFD_ERR_INVALID, "head_final: output pointers missing");
+            CUDA_TRY(head_final_launch(p, st));
+            break;
+        }
+        case LFD_TOP_HEAD_FINAL_BWD: {
+            HeadFinalBwdParams p;
+            p.raw = at<const __nv_bfloat16>(ws, t.off[0]); p.dact = at<__nv_bfloat16>(ws, t.off[1]); p.stats = at<const double>(ws, t.off[3]);
+            p.w = at<const float>(ws, t.off[4]); p.dstage = at<float>(ws, t.off[5]); p.dscale = at<float>(ws, t.off[6]);
+            p.gamma = reinterpret_cast<const float*>(t.ptr[0]); p.beta = reinterpret_cast<const float*>(t.ptr[1]);
+            p.gcls = reinterpret_cast<const float*>(t.ptr[2]); p.greg = reinterpret_cast<const float*>(t.ptr[3]);
+            p.N = t.N; p.HW = t.H * t.W; p.C = t.Cout; p.groups = t.groups; p.n_out = t.n_cls + t.n_reg; p.n_cls = t.n_cls;
+            p.P = t.P; p.point_off = t.point_off; p.cls_stride = t.cls_stride; p.eps = t.eps;
+            if ((t.n_cls && !p.gcls) || (t.n_reg && !p.greg) || !p.dact || !p.dstage) return fail(LFD_ERR_INVALID, "head_final_bwd: missing pointer");
+            CUDA_TRY(head_final_bwd_launch(p, sms, st));
+            break;
+        }
+        case LFD_TOP_NORM_BWD_REDUCE:
+        case LFD_TOP_NORM_BWD_APPLY: {
+            NormBwdParams p;
+            p.dy = at<const __nv_bfloat16>(ws, t.off[0]); p.y = at<const __nv_bfloat16>(ws, t.off[1]); p.z = at<const __nv_bfloat16>(ws, t.off[2]);
+            p.fsums = at<const double>(ws, t.off[3]); p.bsums = at<double>(ws, t.off[4]);
+            p.dz = at<__nv_bfloat16>(ws, t.off[5]); p.dz_up = at<__nv_bfloat16>(ws, t.off[6]); p.dres = at<__nv_bfloat16>(ws, t.off[7]);
+            p.gamma = reinterpret_cast<const float*>(t.ptr[0]); p.beta = reinterpret_cast<const float*>(t.ptr[1]);
+            p.dgamma = reinterpret_cast<float*>(const_cast<void*>(t.ptr[2])); p.dbeta = reinterpret_cast<float*>(const_cast<void*>(t.ptr[3]));
+            p.N = t.N; p.H = t.H; p.W = t.W; p.C = t.Cout; p.groups = t.groups; p.relu = t.relu; p.upH = t.upH; p.upW = t.upW;
+            p.dres_accumulate = t.accumulate; p.eps = t.eps; p.frozen = t.frozen;
+            p.running_mean = reinterpret_cast<const float*>(t.ptr[4]); p.running_var = reinterpret_cast<const float*>(t.ptr[5]);
+            if (t.frozen && (t.groups || !p.running_mean || !p.running_var)) return fail(LFD_ERR_INVALID, "norm backward: frozen BatchNorm needs its running statistics");
+            if (!p.dy || !p.z || (!p.fsums && !t.frozen) || !p.bsums || !p.gamma || (t.groups && !p.beta) || (!t.groups && t.relu && !p.y))
+                return fail(LFD_ERR_INVALID, "norm backward: missing tensor");
+            if (t.kind == LFD_TOP_NORM_BWD_REDUCE) CUDA_TRY(norm_bwd_reduce_launch(p, sms, st));
+            else {
+                if (!p.dz) return fail(LFD_ERR_INVALID, "norm backward apply: dz missing");
+                CUDA_TRY(norm_bwd_apply_launch(p, sms, st));
+            }
+            break;
+        }
+        case LFD_TOP_WGRAD: {
+            WgradGeom g = {t.N, t.H, t.W, t.Cin, t.Ho, t.Wo, t.Cout, t.ksize, t.stride};
+            const __nv_bfloat16* x = at<const __nv_bfloat16>(ws, t.off[0]);
+            const __nv_bfloat16* dz = at<const __nv_bfloat16>(ws, t.off[1]);
+            float* ds = at<float>(ws, t.off[5]);
+            if (!x || !dz || !ds) return fail(LFD_ERR_INVALID, "wgrad: missing tensor");
+            if (t.impl == LFD_WGRAD_SIMT) CUDA_TRY(wgrad_simt_launch(g, x, dz, ds, st));
+            else CUDA_TRY(wgrad_umma_launch(g, x, dz, ds, sms, st));
+            break;
+        }
+        case LFD_TOP_WGRAD_STEM: {
+            WgradGeom g = {t.N, t.H, t.W, t.Cin, t.Ho, t.Wo, t.Cout, t.ksize, t.stride};
+            if (!input || t.off[1] < 0 || t.off[5] < 0) return fail(LFD_ERR_INVALID, "wgrad_stem: missing tensor");
+            CUDA_TRY(wgrad_stem_launch(g, input, fmt, at<const __nv_bfloat16>(ws, t.off[1]), at<float>(ws, t.off[5]), sms, st));
+            break;
+        }
+        default:
+            return fail(LFD_ERR_INVALID, "unknown training op kind %d", t.kind);
+    }
+    return LFD_OK;
+}
+
+extern "C" int lfd_train_plan_create(const lfd_top* ops, int n_ops, int64_t workspace_bytes, lfd_train_plan** out) {
+    if (!ops || n_ops <= 0 || !out || workspace_bytes <= 0) return fail(LFD_ERR_INVALID, "lfd_train_plan_create: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_train_plan_create: no CUDA device (there is no CPU fallback)");
+    lfd_train_plan* pl = new lfd_train_plan();
+    pl->workspace_bytes = workspace_bytes;
+    for (int i = 0; i < n_ops; ++i) {
+        PlannedTop pt;
+        int rc = plan_top(ops[i], workspace_bytes, &pt);
+        if (rc) { delete pl; return rc; }
+        pl->ops.push_back(pt);
+    }
+    *out = pl;
+    return LFD_OK;
+}
+
+extern "C" int lfd_train_plan_destroy(lfd_train_plan* plan) {
+    if (!plan) return LFD_OK;
+    for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    delete plan;
+    return LFD_OK;
+}
+
+extern "C" int lfd_train_plan_num_ops(const lfd_train_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+
+static int train_enqueue(lfd_train_plan* pl, const void* input, int fmt, uint8_t* ws, cudaStream_t st) {
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+        int rc = launch_top(pl->ops[i], input, fmt, ws, st);
+        if (rc) return rc;
+    }
+    return LFD_OK;
+}
+
+extern "C" int lfd_train_plan_run(lfd_train_plan* pl, const void* input, int input_format, void* workspace, int use_graph, lfd_stream stream) {
+    if (!pl || !workspace) return fail(LFD_ERR_INVALID, "lfd_train_plan_run: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    if (!use_graph) return train_enqueue(pl, input, input_format, ws, st);
+    for (auto& g : pl->graphs)
+        if (g.input == input && g.ws == workspace && g.fmt == input_format) {
+            CUDA_TRY(cudaGraphLaunch(g.exec, st));
+            return LFD_OK;
+        }
+    int rc = train_enqueue(pl, input, input_format, ws, st);   // eager first pass (function attributes, launch errors)
+    if (rc) return rc;
+    if (pl->graphs.size() >= 8) {
+        cudaGraphExecDestroy(pl->graphs.front().exec);
+        pl->graphs.erase(pl->graphs.begin());
+    }
+    // The first eager pass already produced this call's results; the graph is captured for the FOLLOWING calls.  Capture does
+    // not execute anything, so the state (statistics, staging) is untouched.
+    cudaStream_t cap;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) { cudaStreamDestroy(cap); return fail(LFD_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); }
+    rc = train_enqueue(pl, input, input_format, ws, cap);
+    ce = cudaStreamEndCapture(cap, &graph);
+    if (rc || ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cap);
+        return rc ? rc : fail(LFD_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+    }
+    lfd_train_plan::GraphEntry e;
+    e.exec = nullptr; e.input = input; e.ws = workspace; e.fmt = input_format;
+    ce = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    if (ce != cudaSuccess) return fail(LFD_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+    pl->graphs.push_back(e);
+    return LFD_OK;
+}
+
+extern "C" int lfd_train_plan_profile(lfd_train_plan* pl, const void* input, int input_format, void* workspace, float* ms_per_op, lfd_stream stream) {
+    if (!pl || !workspace || !ms_per_op) return fail(LFD_ERR_INVALID, "lfd_train_plan_profile: null argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const size_t n = pl->ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    int rc = LFD_OK;
+    CUDA_TRY(cudaEventRecord(ev[0], st));
+    for (size_t i = 0; i < n && !rc; ++i) {
+        rc = launch_top(pl->ops[i], input, input_format, ws, st);
+        cudaEventRecord(ev[i + 1], st);
+    }
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (!rc && ce == cudaSuccess)
+        for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(LFD_ERR_CUDA, "lfd_train_plan_profile: %s", cudaGetErrorString(ce));
+    return LFD_OK;
+}
+
+extern "C" int lfd_run_top(const lfd_top* op, const void* input, int input_format, void* workspace, lfd_stream stream) {
+    if (!op || !workspace) return fail(LFD_ERR_INVALID, "lfd_run_top: null argument");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_run_top: no CUDA device (there is no CPU fallback)");
+    PlannedTop pt;
+    int rc = plan_top(*op, INT64_MAX, &pt);
+    if (rc) return rc;
+    return launch_top(pt, input, input_format, reinterpret_cast<uint8_t*>(workspace), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lfd_grad_sqnorm(const float* grads, int64_t n, double* sqnorm, lfd_stream stream) {
+    if (!grads || !sqnorm || n <= 0) return fail(LFD_ERR_INVALID, "lfd_grad_sqnorm: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_grad_sqnorm: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(sqnorm, 0, 8, st));
+    CUDA_TRY(sqnorm_launch(grads, n, sqnorm, sm_count(), st));
+    return LFD_OK;
+}
+
+extern "C" int lfd_sgd_step(float* params, float* grads, float* momentum_buf, int64_t n, float lr, float momentum, float dampening,
+                            float weight_decay, int nesterov, float max_norm, float grad_scale, const double* sqnorm, lfd_stream stream) {
+    if (!params || !grads || n <= 0 || (max_norm > 0.f && !sqnorm)) return fail(LFD_ERR_INVALID, "lfd_sgd_step: bad arguments");
+    if (nesterov && (momentum <= 0.f || dampening != 0.f || !momentum_buf)) return fail(LFD_ERR_INVALID, "lfd_sgd_step: nesterov needs momentum > 0 and zero dampening");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_sgd_step: no CUDA device (there is no CPU fallback)");
+    SgdParams p;
+    p.p = params; p.g = grads; p.m = (momentum != 0.f) ? momentum_buf : nullptr; p.n = n;
+    p.lr = lr; p.momentum = momentum; p.dampening = dampening; p.weight_decay = weight_decay; p.nesterov = nesterov;
+    p.max_norm = max_norm; p.sqnorm = sqnorm; p.grad_scale = grad_scale;
+    if (momentum != 0.f && !momentum_buf) return fail(LFD_ERR_INVALID, "lfd_sgd_step: momentum buffer missing");
+    CUDA_TRY(sgd_launch(p, sm_count(), st_of(stream)));
     return LFD_OK;
 }

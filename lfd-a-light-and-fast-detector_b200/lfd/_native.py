@@ -58,6 +58,35 @@ class Levels(C.Structure):
                 ('glo', C.c_float * MAX_LEVELS), ('ghi', C.c_float * MAX_LEVELS)]
 
 
+# training plan ops (include/lfd_b200.h, lfd_top)
+(TOP_PACK, TOP_STEM0, TOP_CONV, TOP_BN_STATS, TOP_BN_APPLY, TOP_GN_APPLY, TOP_HEAD_FINAL, TOP_HEAD_FINAL_BWD, TOP_NORM_BWD_REDUCE,
+ TOP_NORM_BWD_APPLY, TOP_WGRAD, TOP_WGRAD_STEM, TOP_UNPACK, TOP_ZERO) = range(14)
+WGRAD_UMMA, WGRAD_SIMT = 0, 1
+PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_STEM, PACK_ROUND_F32, PACK_SCALE_SHIFT = range(5)
+UNPACK_CONV, UNPACK_ADD = 0, 1
+
+
+class Top(C.Structure):
+    _fields_ = [('kind', C.c_int32),
+                ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32), ('Ho', C.c_int32), ('Wo', C.c_int32),
+                ('Cout', C.c_int32), ('ksize', C.c_int32), ('stride', C.c_int32),
+                ('relu', C.c_int32), ('groups', C.c_int32), ('cc', C.c_int32), ('n_cls', C.c_int32), ('n_reg', C.c_int32),
+                ('point_off', C.c_int32), ('P', C.c_int32), ('cls_stride', C.c_int32),
+                ('accumulate', C.c_int32), ('upH', C.c_int32), ('upW', C.c_int32), ('n_desc', C.c_int32), ('max_n', C.c_int32),
+                ('impl', C.c_int32), ('frozen', C.c_int32), ('pad_', C.c_int32), ('eps', C.c_float), ('momentum', C.c_float),
+                ('off', C.c_int64 * 8), ('ptr', C.c_void_p * 6)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('Cout', C.c_int32), ('Cin', C.c_int32), ('k', C.c_int32), ('cc', C.c_int32), ('n', C.c_int32),
+                ('src', C.c_void_p), ('src2', C.c_void_p), ('dst', C.c_void_p), ('dst2', C.c_void_p), ('dst3', C.c_void_p)]
+
+
+class UnpackDesc(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('Cout', C.c_int32), ('Cin', C.c_int32), ('kk', C.c_int32), ('n', C.c_int32), ('pad_', C.c_int32),
+                ('src', C.c_void_p), ('dst', C.c_void_p)]
+
+
 # every symbol include/lfd_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 SYMBOLS = {
@@ -81,6 +110,14 @@ SYMBOLS = {
     'lfd_detection_loss': (_i, [C.POINTER(Levels), _i, _i, _i, _i, _i, _f, _f, _f, _f, _f] + [_vp] * 9),
     'lfd_sigmoid_focal_loss_forward': (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     'lfd_sigmoid_focal_loss_backward': (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
+    'lfd_train_plan_create': (_i, [C.POINTER(Top), _i, _i64, C.POINTER(_vp)]),
+    'lfd_train_plan_destroy': (_i, [_vp]),
+    'lfd_train_plan_num_ops': (_i, [_vp]),
+    'lfd_train_plan_run': (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    'lfd_train_plan_profile': (_i, [_vp, _vp, _i, _vp, C.POINTER(C.c_float), _vp]),
+    'lfd_run_top': (_i, [C.POINTER(Top), _vp, _i, _vp, _vp]),
+    'lfd_grad_sqnorm': (_i, [_vp, _i64, _vp, _vp]),
+    'lfd_sgd_step': (_i, [_vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _f, _vp, _vp]),
 }
 
 _lib = None
@@ -110,7 +147,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.lfd_abi_version() != 3:
+    if L.lfd_abi_version() != 4:
         raise LfdError('liblfd_b200.so ABI version mismatch')
     _lib = L
     return L

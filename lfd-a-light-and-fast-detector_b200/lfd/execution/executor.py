@@ -40,6 +40,11 @@ class Executor(object):
         # diverged RNG state the ranks would otherwise train different models (the reference's DataParallel re-broadcasts
         # module 0 every iteration, executor.py:39)
         broadcast_module_state(cfg['model'])
+        # the reference's torch.optim.SGD + clip_grad_norm_ (optimizer_hook.py:21-36) run as the fused native optimizer over
+        # the model's flat parameter buffer; param_groups stay shared with the original optimizer (lr schedulers keep working)
+        if self.device.type == 'cuda' and type(cfg.get('optimizer')) is torch.optim.SGD and hasattr(cfg['model'], 'train_plan_for'):
+            from .optim import FusedSGD
+            cfg['optimizer'] = FusedSGD.from_torch(cfg['optimizer'], cfg['model'])
         if cfg.get('resume_path') is not None:
             self.resume_optimizer()
             self.resume_lr_scheduler()

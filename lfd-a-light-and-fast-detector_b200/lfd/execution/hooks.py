@@ -4,8 +4,10 @@ clipping (optimizer_hook.py:26-36) -- with the data-parallel gradient all-reduce
 lr warm-up + scheduler stepping (lr_scheduler_hook.py:55-100), speed, logging and checkpoint hooks."""
 import time
 
+import torch
 from torch.nn.utils import clip_grad
 
+from .optim import FusedSGD
 from .parallel import allreduce_gradients, world
 
 PRIORITIES = dict(HIGHEST=0, VERY_HIGH=10, HIGH=30, NORMAL=50, LOW=70, VERY_LOW=90, LOWEST=100)
@@ -42,21 +44,36 @@ class OptimizerHook(Hook):
 
     def after_train_iter(self, executor):
         cfg = executor.config_dict
-        cfg['optimizer'].zero_grad()
+        model, opt = cfg['model'], cfg['optimizer']
+        opt.zero_grad()
         if cfg['loss'] is not None:        # None: this rank's shard of the batch was empty; it still joins the all-reduce with zeros
             cfg['loss'].backward()
         # one flat-bucket all-reduce (no-op for a single process); losses already normalised by the global number of
         # positives (LFD.get_loss) add up over ranks, otherwise the per-rank means are averaged
-        allreduce_gradients(cfg['model'].parameters(), average=not getattr(cfg['model'], 'loss_globally_normalised', False))
-        if self._grad_clip_cfg is not None:
-            if cfg['epoch'] < self._grad_clip_duration:
-                params = [p for p in cfg['model'].parameters() if p.requires_grad and p.grad is not None]
-                cfg['grad_norm'] = clip_grad.clip_grad_norm_(params, **self._grad_clip_cfg) if params else 0
-            else:
-                cfg['grad_norm'] = 0
-        cfg['optimizer'].step()
-        if hasattr(cfg['model'], 'invalidate_plans'):
-            cfg['model'].invalidate_plans()
+        average = not getattr(model, 'loss_globally_normalised', False)
+        clip = self._grad_clip_cfg is not None and cfg['epoch'] < self._grad_clip_duration
+        if isinstance(opt, FusedSGD):
+            # native path: the parameters / gradients are views into flat buffers (lfd/_train.py) -- the bucket IS the gradient
+            # storage, the averaging factor, the clip and the SGD update are one fused pass (lfd_grad_sqnorm + lfd_sgd_step)
+            flat = opt._sync()
+            _, w = world()
+            if w > 1:
+                torch.distributed.all_reduce(flat.grad, op=torch.distributed.ReduceOp.SUM)
+            if clip and (self._grad_clip_cfg.get('norm_type', 2) not in (2, 2.0)):
+                raise NotImplementedError('FusedSGD clips with the 2-norm (every shipped config)')
+            norm = opt.step(max_norm=float(self._grad_clip_cfg['max_norm']) if clip else 0.0, grad_scale=(1.0 / w) if (average and w > 1) else 1.0)
+            cfg['grad_norm'] = norm if norm is not None else 0
+        else:
+            allreduce_gradients(model.parameters(), average=average)
+            if self._grad_clip_cfg is not None:
+                if clip:
+                    params = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
+                    cfg['grad_norm'] = clip_grad.clip_grad_norm_(params, **self._grad_clip_cfg) if params else 0
+                else:
+                    cfg['grad_norm'] = 0
+            opt.step()
+        if hasattr(model, 'invalidate_plans'):
+            model.invalidate_plans()
 
 
 class LrSchedulerHook(Hook):
@@ -116,13 +133,17 @@ class SpeedHook(Hook):
         executor.config_dict['speed'] = executor.config_dict['batch_size'] * world()[1] / dt
 
 
+def _fmt_norm(v):
+    return '%.4f' % float(v) if torch.is_tensor(v) else v
+
+
 class LoggerHook(Hook):
     def after_train_iter(self, executor):
         cfg = executor.config_dict
         if cfg['train_iter'] % max(cfg.get('display_interval', 100), 1) == 0:
             avg = cfg['train_average_meter'].averages()
             cfg['logger'].info('epoch %d iter %d lr %.6f speed %.1f img/s grad_norm %s %s' % (
-                cfg['epoch'], cfg['train_iter'], executor.get_current_lr(), cfg.get('speed', 0.0), cfg.get('grad_norm', '-'),
+                cfg['epoch'], cfg['train_iter'], executor.get_current_lr(), cfg.get('speed', 0.0), _fmt_norm(cfg.get('grad_norm', '-')),
                 ' '.join('%s %.5f' % kv for kv in avg.items())))
             cfg['train_average_meter'].reset()
 

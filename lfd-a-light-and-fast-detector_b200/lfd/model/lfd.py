@@ -81,6 +81,7 @@ class LFD(nn.Module):
         # native state (not part of the state_dict)
         self._plans = {}
         self._post_plans = {}
+        self._train_plans = {}
         self._plan_fingerprint = None
         self.conv_impl = nat.CONV_UMMA
         self.act_dtype = 'bf16'                # 16-bit storage type of the inference plan: 'bf16' or 'fp16' (lfd/_engine.py)
@@ -94,6 +95,16 @@ class LFD(nn.Module):
     # ------------------------------------------------------------------ forward
     def _fingerprint(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def train_plan_for(self, n, h, w, device):
+        """The native training plan (forward + backward op lists) for one input shape (built on first use)."""
+        from .._train import TrainPlan, flat_parameters
+        flat_parameters(self)
+        key = (n, h, w, str(device))
+        if key not in self._train_plans:
+            self._train_plans[key] = TrainPlan(self, n, h, w, device)
+            self._train_plans[key].use_graph = bool(getattr(self, 'use_cuda_graph_training', False))
+        return self._train_plans[key]
 
     def invalidate_plans(self):
         self._plans = {}
@@ -114,11 +125,12 @@ class LFD(nn.Module):
         if not x.is_cuda:
             raise RuntimeError('lfd_b200 has no CPU path: move the model and the input to a CUDA (B200) device')
         if self.training:
-            # the conv-stack backward is not hand-written yet: ATen / cuDNN evaluate the same module graph (lfd/_train.py)
-            if x.dtype != torch.float32:
-                raise TypeError('training-mode forward takes the float32 NCHW batch of the reference data pipeline')
+            # native training step (lfd/_train.py): forward with BatchNorm batch statistics, every intermediate kept for the backward,
+            # which loss.backward() triggers through one autograd node
+            if x.dtype not in (torch.float32, torch.uint8):
+                raise TypeError('training-mode forward takes the float32 NCHW batch of the reference data pipeline (or uint8 NHWC frames)')
             from .._train import train_forward
-            return train_forward(self, x)
+            return train_forward(self, x.contiguous())
         if x.dtype == torch.uint8:
             n, h, w = x.shape[0], x.shape[1], x.shape[2]
         else:

@@ -13,7 +13,7 @@ import pytest
 import torch
 
 import synth
-from helpers import rel_err, synth_model, assert_same_detections
+from helpers import assert_same_detections_up_to_margins, rel_err, synth_model, assert_same_detections
 from oracle import lfd_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -114,13 +114,22 @@ def test_one_720p_frame_against_the_oracle():
     assert ec[1] < 1e-3 and ec[0] < 5e-3 and er[1] < 2e-3 and er[0] < 1e-2, (ec, er)
     meta = [dict(resized_height=720, resized_width=1280, resize_scale=1.0)]
     model.max_detections_per_image = 32768
-    for (thr, iou) in ((0.5, 0.3), (0.01, 0.4)):       # WIDERFACE_train/predict.py:22, evaluation.py:60-61
+    osc, obx = orc.decode_image(orc.CONFIGS['WIDERFACE_S'], ocls[0], oreg[0], sizes, 720, 1280, 1.0)
+    osc, obx = osc.reshape(-1).numpy(), obx.numpy()
+    q999 = float(np.quantile(osc, 0.999))             # a threshold that keeps ~0.1 % of the points whatever the synthetic bias is
+    # WIDERFACE_train/predict.py:22 (0.5 / 0.3), evaluation.py:60-61 (0.01 / 0.4: ~10^4 detections per frame)
+    for (thr, iou) in ((0.5, 0.3), (q999, 0.3), (0.01, 0.4)):
         dets, labels, src, count, overflow = model.detect((cls, reg), [720], [1280], [1.0], thr, iou)
         assert int(overflow.item()) == 0
         orows, osrc = orc.get_results(orc.CONFIGS['WIDERFACE_S'], ocls, oreg, sizes, meta, thr, iou)
         k = int(count[0].item())
-        assert_same_detections(src[0, :k].cpu().tolist(), osrc[0].tolist(), [r[1] for r in orows[0]], ('720p', thr, iou))
-        print('   thr %.2f / iou %.1f: %d detections, identical kept set' % (thr, iou, k))
+        got = src[0, :k].cpu().tolist()
+        # the CUDA post-process on the CUDA outputs is EXACTLY the oracle's post-process on the same outputs ...
+        _, same_src = orc.get_results(orc.CONFIGS['WIDERFACE_S'], cls.cpu(), reg.cpu(), sizes, meta, thr, iou)
+        assert got == same_src[0].tolist(), ('720p', thr, iou, 'post-process on identical inputs')
+        # ... and end to end (two pipelines that agree to 1e-3) the kept sets agree up to provably borderline decisions
+        nd = assert_same_detections_up_to_margins(got, osrc[0].tolist(), osc, obx, thr, iou, ('720p', thr, iou))
+        print('   thr %.3f / iou %.1f: %d detections, %d borderline decisions differ end to end' % (thr, iou, k, nd))
 
 
 def test_fp16_activation_range_is_safe():

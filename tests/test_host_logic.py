@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.lfd_abi_version() == 3
+    assert lib.lfd_abi_version() == 4
 
 
 def test_conv_query_is_host_only_and_rejects_unsupported():

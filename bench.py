@@ -184,11 +184,318 @@ def init_nccl(dev):
         os.close(saved)
 
 
-TRAIN_WORKLOADS = {}
+TRAIN_WORKLOADS = {
+    # BASELINE.json configs[2]: WIDERFACE-L training, bf16, 640x640 synthetic crops, data parallel (16 crops per GPU = the reference's
+    # batch_size 64 on 4 GPUs, WIDERFACE_train/WIDERFACE_LFD_L.py:58,168); SGD(0.9, 1e-4) + clip_grad_norm_(10) as :218-226
+    'WIDERFACE_L_train': dict(cfg='WIDERFACE_L', N=16, H=640, W=640, dtype='bf16', name='WIDERFACE-L training 640x640 batch=16 per GPU'),
+}
+_TOP_NAMES = ['pack', 'stem0', 'conv', 'bn_stats', 'bn_apply', 'gn_apply', 'head_final', 'head_final_bwd', 'norm_bwd_reduce', 'norm_bwd_apply',
+              'wgrad', 'wgrad_stem', 'unpack', 'zero']
+
+
+def train_op_algorithmic(op, N):
+    """(bytes, flops) one training-plan launch must move / compute (bf16 activations, fp32 weight-gradient staging)."""
+    kind = _TOP_NAMES[op['kind']]
+    g = lambda k, d=0: op.get(k, d) or d
+    px_in, px_out = N * g('H') * g('W'), N * g('Ho', g('H')) * g('Wo', g('W'))
+    cin, cout, k = g('Cin'), g('Cout'), g('ksize', 1)
+    if kind in ('conv', 'stem0'):
+        res = 1 if op['off'].get(2) is not None else 0
+        in_b = px_in * 3 if kind == 'stem0' else px_in * cin * 2
+        return in_b + px_out * cout * 2 * (1 + res) + k * k * cin * cout * 2, 2.0 * px_out * cout * cin * k * k
+    if kind in ('wgrad', 'wgrad_stem'):
+        in_b = px_in * 3 if kind == 'wgrad_stem' else px_in * cin * 2
+        return in_b + px_out * cout * 2 + k * k * cin * cout * 4, 2.0 * px_out * cout * cin * k * k
+    if kind == 'bn_stats':
+        return px_in * cout * 2, 0.0
+    if kind in ('bn_apply', 'gn_apply'):
+        return px_in * cout * 2 * (2 + (1 if op['off'].get(2) is not None else 0)), 0.0
+    if kind == 'norm_bwd_reduce':
+        return px_in * cout * 2 * (2 + (1 if op['off'].get(1) is not None else 0)), 0.0
+    if kind == 'norm_bwd_apply':
+        return px_in * cout * 2 * (3 + (1 if op['off'].get(1) is not None else 0) + (1 if op['off'].get(7) is not None else 0)), 0.0
+    if kind == 'head_final':
+        no = g('n_cls') + g('n_reg')
+        return px_in * 128 * 2 + px_in * no * 4, 2.0 * px_in * no * 128
+    if kind == 'head_final_bwd':
+        no = g('n_cls') + g('n_reg')
+        return px_in * 128 * 2 * 2 + px_in * no * 4, 3 * 2.0 * px_in * no * 128
+    return 0, 0.0
+
+
+def train_op_name(op):
+    kind = _TOP_NAMES[op['kind']]
+    if kind in ('conv', 'stem0', 'wgrad', 'wgrad_stem'):
+        return '%s %dx%d/s%d %d->%d @%dx%d' % (kind, op['ksize'], op['ksize'], op['stride'], op['Cin'], op['Cout'], op['Ho'], op['Wo'])
+    if 'H' in op:
+        return '%s C=%d @%dx%d' % (kind, op.get('Cout', 0), op['H'], op['W'])
+    return kind
+
+
+def train_config(wl, world):
+    return dict(workload=wl['name'], model=wl['cfg'], frames_per_step_per_gpu=wl['N'], height=wl['H'], width=wl['W'], dtype=wl['dtype'],
+                input='synthetic uint8 BGR crops + synthetic ground truth (0..30 boxes per crop, sides log-uniform in [4, 320], one negative crop '
+                      'per batch; tests/synth.py weights; no network for datasets / checkpoints)',
+                step='forward (train mode, BatchNorm batch statistics) + label assignment + focal / IoU loss + backward (dgrad, wgrad, norm '
+                     'backward) + gradient all-reduce + clip_grad_norm_(10) + SGD(momentum 0.9, weight decay 1e-4) step',
+                parallelism='data parallel x%d: per-rank shards, global positive-count normalisation, ONE flat-buffer NCCL all-reduce' % world)
+
+
+def cpu_train_leg(wl, steps, warmup, frames, budget_s=25.0):
+    """The reference's CPU training step for this workload: the same module graph in fp32 by ATen + autograd (tests/aten_train_reference.py:
+    the reference's arithmetic, lfd/model/lfd.py:511-542), the oracle's label assignment + losses (lfd.py:109-395), clip_grad_norm_ + torch SGD
+    (optimizer_hook.py:21-36), all host threads."""
+    import synth
+    from aten_train_reference import train_forward as aten_forward
+    from helpers import build_model as product_model
+    from oracle import lfd_oracle as orc
+    cfg = orc.CONFIGS[wl['cfg']]
+    model = product_model(wl['cfg'])
+    model.train()
+    x = synth.synth_input(frames, wl['H'], wl['W'])
+    ann = synth.synth_annotations(frames, wl['H'], wl['W'], cfg['lfd']['num_classes'], seed=7, max_boxes=30)
+    opt = torch.optim.SGD(model.parameters(), lr=0.001, momentum=0.9, weight_decay=1e-4)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+
+    def step():
+        cls, reg = aten_forward(model, x)
+        sizes = [model._head_indexes_to_feature_map_sizes[i] for i in range(len(model._head_indexes_to_feature_map_sizes))]
+        out = orc.get_loss(cfg, cls, reg, sizes, ann)
+        opt.zero_grad()
+        out['loss'].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10, norm_type=2)
+        opt.step()
+    for _ in range(warmup):
+        step()
+    t0, done = time.time(), 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.time() - t0 > budget_s and done >= 1:
+            break
+    dt = time.time() - t0
+    return dict(ips=frames * done / dt, ms=dt / done * 1e3, done=done, cores=torch.get_num_threads())
 
 
 def train_main(args):
-    raise SystemExit('no training workload registered')
+    wl = TRAIN_WORKLOADS[args.config]
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    warmup = max(args.warmup, 3)
+    metric = 'images/sec %s %s' % (wl['name'], wl['dtype'])
+    config = train_config(wl, max(world, args.gpus))
+    N, H, W = wl['N'], wl['H'], wl['W']
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        frames = 2
+        r = cpu_train_leg(wl, args.steps, 1, frames, budget_s=150.0)
+        line = dict(metric=metric, value=r['ips'], unit='images/s', n_gpus=args.gpus, steps=r['done'], warmup=1, ms_per_step=r['ms'], higher_is_better=True,
+                    scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference', config=config,
+                    impl_detail=dict(note='CPU training step of the reference: ATen fp32 forward + autograd over the same module graph (/root/reference does not '
+                                          'exist on the GPU box), oracle label assignment + losses, clip_grad_norm_ + torch SGD', frames_per_step=frames,
+                                     steps_requested=args.steps, steps_timed=r['done'], time_budget_s=150.0),
+                    cpu_baseline=dict(value=r['ips'], unit='images/s', cores=r['cores'], kind='port', sample='%d crops per step, %d steps' % (frames, r['done'])),
+                    e2e=dict(value=r['ips'], unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback for the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    import torch.distributed as dist
+    if world > 1:
+        init_nccl(dev)
+    import synth
+    from helpers import build_model as product_model
+    from lfd.execution.hooks import OptimizerHook
+    from lfd.execution.optim import FusedSGD
+    from lfd.pipeline import bind_host_to_gpu_numa_node
+    numa_node = bind_host_to_gpu_numa_node(dev)
+    model, _ = build_model(wl['cfg'])
+    model.to(dev).train()
+    model.use_cuda_graph_training = not args.no_graph
+    if world > 1:
+        from lfd.execution.parallel import broadcast_module_state
+        broadcast_module_state(model)
+    opt = FusedSGD.from_torch(torch.optim.SGD(model.parameters(), lr=0.001, momentum=0.9, weight_decay=1e-4), model)
+    hook = OptimizerHook(dict(max_norm=10, norm_type=2), 10)
+
+    class _Exec(object):
+        config_dict = dict(model=model, optimizer=opt, epoch=0)
+    g = torch.Generator().manual_seed(2000 + rank)
+    npool = 4        # 4 x 19.7 MB of frames; the ~13 GB activation / gradient workspace is rewritten every step (>> L2)
+    pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(npool)]
+    host_pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    anns = [synth.synth_annotations(N, H, W, 1, seed=100 * rank + i, max_boxes=30) for i in range(npool)]
+    times = dict(assign=0.0)
+
+    def step(i, x=None):
+        out = model(pool[i % npool] if x is None else x)
+        ld = model.get_loss(out, anns[i % npool])
+        _Exec.config_dict['loss'] = ld['loss']
+        hook.after_train_iter(_Exec)
+        return ld['loss_values']
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(warmup, 3)):           # W warm-up steps (the first ones also capture the forward / backward CUDA graphs)
+        lv = step(i)
+    sync_all()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    step(0)
+    p1.record()
+    sync_all()
+    est_ms = max(p0.elapsed_time(p1), 1e-3)
+    blocks = int(min(50, max(1, -(-args.min_timed_s * 1e3 // (est_ms * args.steps)))))
+    tb = torch.tensor([blocks], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    blocks = int(tb.item())
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    block_ms, losses = [], []
+    for b in range(blocks):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            lv = step(b * args.steps + i)
+        e1.record()
+        sync_all()
+        block_ms.append(e0.elapsed_time(e1))
+        losses.append(lv['loss'])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor(block_ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    block_ms = [float(v) for v in t.tolist()]
+    ms_total = float(sum(block_ms))
+    ms_step = ms_total / (args.steps * blocks)
+    value = world * N * args.steps * blocks / (ms_total / 1e3)
+
+    # ---- end to end: pinned host uint8 crops in (H2D inside the timed region), loss values out (the reference's three .item() reads)
+    e2e_steps = args.steps * blocks
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty((N, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    sync_all()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(copy_stream):
+        stage[0].copy_(host_pool[0], non_blocking=True)
+    ev = [torch.cuda.Event(), torch.cuda.Event()]
+    ev[0].record(copy_stream)
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:                 # prefetch the next batch while this one trains
+            with torch.cuda.stream(copy_stream):
+                stage[(i + 1) % 2].copy_(host_pool[(i + 1) % 2], non_blocking=True)
+            ev[(i + 1) % 2].record(copy_stream)
+        torch.cuda.current_stream().wait_event(ev[i % 2])
+        step(i, x=stage[i % 2])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(te.item())
+    ann_bytes = int(sum(a[0].nbytes + a[1].nbytes for a in anns[0]))
+
+    # ---- all-reduce of the flat gradient buffer alone (what the collective costs inside the step)
+    flat = model._flat_parameters
+    ar_us = None
+    if world > 1:
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(flat.grad)
+        a1.record()
+        sync_all()
+        ar = torch.tensor([a0.elapsed_time(a1) / 20 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        ar_us = float(ar.item())
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return 0
+
+    # ---- label assignment: native kernel vs the reference's CPU annotation_to_target (oracle restatement), one batch
+    from oracle import lfd_oracle as orc
+    sizes = model._sizes()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        model._assign(sizes, [a[0] for a in anns[0]], [a[1] for a in anns[0]], dev)
+    torch.cuda.synchronize()
+    assign_ms = (time.perf_counter() - t0) * 1e3 / 10
+    t0 = time.perf_counter()
+    orc.assign_targets(orc.CONFIGS[wl['cfg']], sizes, [a[0] for a in anns[0][:2]], [a[1] for a in anns[0][:2]])
+    assign_cpu_ms = (time.perf_counter() - t0) * 1e3 / 2 * N
+
+    # ---- live per-op roofline of the forward and backward plans (eager passes with an event pair around every launch)
+    pk = peaks()
+    plan = list(model._train_plans.values())[0]
+    table = []
+    for which, ops in (('fwd', plan.fwd_ops), ('bwd', plan.bwd_ops)):
+        acc = np.zeros(len(ops))
+        for rep in range(4):
+            ms = plan.profile(which)
+            if rep:
+                acc += np.asarray(ms)
+        for op, ms in zip(ops, acc / 3):
+            b, f = train_op_algorithmic(op, N)
+            table.append(dict(op=op, which=which, ms=float(ms), bytes=b, flops=f, t_bound_ms=max(b / (pk['hbm_gbs'] * 1e9), f / (pk['bf16_tflops'] * 1e12)) * 1e3))
+    top = sorted(table, key=lambda r: -r['ms'])[0]
+    hbm_bound = top['bytes'] / (pk['hbm_gbs'] * 1e9) >= top['flops'] / (pk['bf16_tflops'] * 1e12)
+    if hbm_bound:
+        achieved, peak, unit = top['bytes'] / (top['ms'] * 1e-3) / 1e9, pk['hbm_gbs'], 'GB/s'
+    else:
+        achieved, peak, unit = top['flops'] / (top['ms'] * 1e-3) / 1e12, pk['bf16_tflops'], 'TFLOP/s'
+    sum_ms = float(sum(r['ms'] for r in table))
+    by_kind = {}
+    for r in table:
+        kname = ('dgrad' if (r['which'] == 'bwd' and _TOP_NAMES[r['op']['kind']] == 'conv') else _TOP_NAMES[r['op']['kind']])
+        e = by_kind.setdefault(kname, dict(ms=0.0, bound_ms=0.0, launches=0))
+        e['ms'] += r['ms']; e['bound_ms'] += r['t_bound_ms']; e['launches'] += 1
+    net_bound_ms = float(sum(r['t_bound_ms'] for r in table))
+    roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak, traffic=None,
+                    peak_source=pk['source'], kernel='%s (%s)' % (train_op_name(top['op']), top['which']), kernel_ms=top['ms'],
+                    kernel_share_of_step=top['ms'] / sum_ms, algorithmic_bytes=top['bytes'], algorithmic_flops=top['flops'],
+                    net=dict(layerwise_bound_ms=net_bound_ms, plan_ms_eager_sum=sum_ms, frac_of_layerwise_bound=net_bound_ms / sum_ms,
+                             frac_of_layerwise_bound_in_step=net_bound_ms / ms_step,
+                             by_kind={k: dict(ms=round(v['ms'], 4), bound_ms=round(v['bound_ms'], 4), launches=v['launches']) for k, v in sorted(by_kind.items())}))
+    if args.profile_ops:
+        for r in table:
+            sys.stderr.write('%s %-44s %8.3f ms  bound %7.3f ms  %5.1f%%\n' % (r['which'], train_op_name(r['op']), r['ms'], r['t_bound_ms'], 100 * r['t_bound_ms'] / max(r['ms'], 1e-9)))
+        sys.stderr.write('sum of plan ops %.3f ms; step %.3f ms\n' % (sum_ms, ms_step))
+    launches = len(plan.fwd_ops) + len(plan.bwd_ops) + 5 + 2      # + assign, 2 loss kernels, 2 memsets; + sqnorm, sgd
+    line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=warmup, ms_per_step=ms_step, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype=wl['dtype'], data='synthetic', config=config,
+                impl_detail=dict(timed_blocks=blocks, block_ms=[round(v, 3) for v in block_ms[:16]], timed_s=ms_total / 1e3, loss_first_last=[losses[0], losses[-1]],
+                                 cuda_graph=bool(model.use_cuda_graph_training), launches_per_step=launches,
+                                 workspace_gb=plan.workspace_bytes / 1e9, parameters=int(flat.numel),
+                                 l2='the %.1f GB activation / gradient workspace is rewritten every step; inputs rotate over %d batches' % (plan.workspace_bytes / 1e9, npool),
+                                 label_assign_ms=assign_ms, label_assign_reference_cpu_ms=assign_cpu_ms,
+                                 label_assign_note='native lfd_assign_targets incl. the H2D copy of the boxes vs the oracle restatement of '
+                                                   'annotation_to_target (lfd.py:109-259) on the host, same batch',
+                                 allreduce_us=ar_us, allreduce_bytes=int(flat.numel * 4)),
+                clocks=clocks, gpu_launches=launches * args.steps * blocks,
+                e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=N * H * W * 3 + ann_bytes, d2h_bytes_per_step=12, steps=e2e_steps,
+                         host_numa_node=numa_node, note='pinned host uint8 crops -> device (prefetched on a copy stream) -> training step -> loss values on the host'),
+                roofline=roofline)
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_train_leg(wl, 3, 1, 2, budget_s=20.0)
+        line['cpu_baseline'] = dict(value=r['ips'], unit='images/s', cores=r['cores'], kind='port',
+                                    sample='2 crops 640x640 per step, %d steps (ATen fp32 forward + autograd + oracle losses + clip + SGD on the host)' % r['done'])
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+    return 0
 
 
 def build_model(cfg_name):

@@ -129,9 +129,6 @@ class TrainPlan(object):
     # ------------------------------------------------------------------ checks
     @staticmethod
     def _check_supported(model):
-        bb = model._backbone
-        if bb._frozen_stages > 0 or bb._norm_eval:
-            raise NotImplementedError('native training implements the shipped configuration (frozen_stages=-1, norm_eval=False)')
         for m in model.modules():
             if isinstance(m, nn.BatchNorm2d):
                 if not (m.affine and m.track_running_stats and m.momentum is not None):
@@ -197,12 +194,15 @@ class TrainPlan(object):
             cc = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s)['cc']
             wp = self._wpack(conv, nat.PACK_CONV_FWD, cc)
             self._fwd.append(dict(kind=nat.TOP_CONV, cc=cc, off={0: x, 1: z, 4: wp}, **geo))
-        bn_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, eps=float(norm.eps))
-        self._fwd.append(dict(kind=nat.TOP_BN_STATS, off={0: z, 3: sums}, **bn_geo))
+        frozen = int(not norm.training)       # a BatchNorm2d in eval mode inside a training step (norm_eval / frozen stages): running statistics
+        bn_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, eps=float(norm.eps), frozen=frozen)
+        if not frozen:
+            self._fwd.append(dict(kind=nat.TOP_BN_STATS, off={0: z, 3: sums}, **bn_geo))
         self._fwd.append(dict(kind=nat.TOP_BN_APPLY, relu=int(relu), momentum=float(norm.momentum), off={0: z, 1: y, 2: res, 3: sums},
                               ptr={0: norm.weight, 1: norm.bias, 2: norm.running_mean, 3: norm.running_var}, **bn_geo))
-        self._layers.append(dict(type='bn', name=name, conv=conv, norm=norm, relu=relu, x=x, z=z, y=y, res=res, sums=sums, geo=geo))
-        self._bn_modules.append(norm)
+        self._layers.append(dict(type='bn', name=name, conv=conv, norm=norm, relu=relu, x=x, z=z, y=y, res=res, sums=sums, geo=geo, frozen=frozen))
+        if not frozen:
+            self._bn_modules.append(norm)
         return y, ho, wo
 
     def _conv_gn(self, name, conv, norm, x, h, w, last):
@@ -390,12 +390,14 @@ class TrainPlan(object):
                     dres = self._grad_of(L['res'], ho, wo, cout)
                     acc = int(dres in self._grad_written)
                     self._grad_written.add(dres)
-                n_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, groups=0, relu=int(L['relu']), eps=float(L['norm'].eps))
+                n_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, groups=0, relu=int(L['relu']), eps=float(L['norm'].eps), frozen=L['frozen'])
                 offs = {0: dy, 1: L['y'] if L['relu'] else None, 2: L['z'], 3: L['sums'], 4: bs}
-                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias}, **n_geo))
+                rstats = {4: L['norm'].running_mean, 5: L['norm'].running_var}
+                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias, 4: rstats[4], 5: rstats[5]}, **n_geo))
                 offs.update({5: dz, 6: dz_up, 7: dres})
                 self._bwd.append(dict(kind=nat.TOP_NORM_BWD_APPLY, accumulate=acc, upH=geo['H'] if need_up else 0, upW=geo['W'] if need_up else 0, off=offs,
-                                      ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: ('grad', L['norm'].weight), 3: ('grad', L['norm'].bias)}, **n_geo))
+                                      ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: ('grad', L['norm'].weight), 3: ('grad', L['norm'].bias), 4: rstats[4], 5: rstats[5]},
+                                      **n_geo))
                 self._emit_conv_backward(L, dz, dz_up)
 
     def _layout(self):

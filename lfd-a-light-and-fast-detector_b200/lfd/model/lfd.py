@@ -100,7 +100,8 @@ class LFD(nn.Module):
         """The native training plan (forward + backward op lists) for one input shape (built on first use)."""
         from .._train import TrainPlan, flat_parameters
         flat_parameters(self)
-        key = (n, h, w, str(device))
+        # BatchNorm modules in eval mode (norm_eval, frozen stages) normalise with their running statistics: part of the plan
+        key = (n, h, w, str(device), tuple(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)))
         if key not in self._train_plans:
             self._train_plans[key] = TrainPlan(self, n, h, w, device)
             self._train_plans[key].use_graph = bool(getattr(self, 'use_cuda_graph_training', False))

@@ -84,26 +84,30 @@ def _iou_one_to_many(b, bs):
     return inter / np.maximum(a + aa - inter, 1e-12)
 
 
-def assert_same_detections_up_to_margins(got_src, want_src, scores, boxes, thr, iou_thr, what, score_tol=3e-3, iou_tol=2e-2, max_frac=2e-3):
-    """End-to-end kept sets of two pipelines whose logits agree to ~1e-3, at a threshold that keeps THOUSANDS of detections
-    (the evaluation setting 0.01 / 0.4): the sets must be identical except for provably borderline decisions.  Every index in
-    the symmetric difference must (a) have an oracle score within `score_tol` of the score threshold, or (b) have an IoU within
-    `iou_tol` of the NMS threshold against some kept box, or (c) overlap (IoU > iou_thr - iou_tol) another differing index
-    (a borderline flip cascading through the greedy sweep); and there may be at most max(2, max_frac * kept) of them.
-    scores / boxes: the ORACLE's per-candidate scores [P*C] and decoded boxes [P*C, 4] (single-class use: P)."""
+def assert_same_detections_up_to_margins(got_src, want_src, scores, boxes, thr, iou_thr, what, num_classes=1, score_tol=3e-3, iou_tol=2e-2,
+                                         max_frac=2e-2):
+    """End-to-end kept sets of two pipelines whose logits agree to ~1e-3 (CUDA forward + CUDA post-process vs oracle forward +
+    oracle post-process): the sets must be identical except for provably borderline decisions.  Every index in the symmetric
+    difference must (a) have an oracle score within `score_tol` of the score threshold, or (b) have an IoU within `iou_tol` of
+    the NMS threshold against some kept box of its class, or (c) overlap (IoU > iou_thr - iou_tol) another differing index of its
+    class (a borderline flip cascading through the greedy sweep); and there may be at most max(2, max_frac * kept) of them.
+    (The CUDA post-process on the CUDA outputs is separately required to be EXACTLY the oracle post-process on those outputs.)
+    scores: the ORACLE's scores flattened [P*C]; boxes: its decoded boxes [P, 4]; indices are point * C + class."""
     got, want = set(got_src), set(want_src)
     diff = sorted(got ^ want)
     assert len(diff) <= max(2, int(max_frac * len(want))), (what, 'too many differing detections', len(diff), len(want))
     if not diff:
         return 0
+    C = int(num_classes)
+    boxes, scores = np.asarray(boxes), np.asarray(scores).reshape(-1)
     union = np.asarray(sorted(got | want))
-    ub = np.asarray(boxes)[union]
     dset = set(diff)
     for d in diff:
         if abs(float(scores[d]) - thr) < score_tol:
             continue
-        ious = _iou_one_to_many(np.asarray(boxes)[d], ub)
+        same = union[(union % C) == (d % C)]
+        ious = _iou_one_to_many(boxes[d // C], boxes[same // C])
         near = np.abs(ious - iou_thr) < iou_tol
-        cascade = [int(u) for u, v in zip(union, ious) if int(u) in dset and int(u) != d and v > iou_thr - iou_tol]
+        cascade = [int(u) for u, v in zip(same, ious) if int(u) in dset and int(u) != d and v > iou_thr - iou_tol]
         assert bool(near.any()) or cascade, (what, 'detection differs without a borderline decision', d, float(scores[d]))
     return len(diff)

@@ -3,8 +3,11 @@
 a sharded batch must leave every rank with the parameters a single process obtains on the full batch.
 
 BatchNorm uses per-replica statistics in the reference (plain DataParallel), which makes 2 x (n/2) differ from 1 x n by
-construction; the comparison therefore runs with the norm layers on their running statistics, so that what is compared is
-exactly the data-parallel arithmetic: global positive count, per-rank loss sums, SUM all-reduce of the flat bucket."""
+construction; the comparison therefore runs with the BatchNorm layers on their running statistics (eval mode inside the training
+step, the `norm_eval` arithmetic), so that what is compared is exactly the data-parallel arithmetic of the NATIVE training step:
+global positive count, per-rank loss sums, SUM all-reduce of the flat gradient buffer, fused clip + SGD.  Activations and their
+gradients are bf16, so '2 x half batch' and '1 x full batch' agree to bf16 accumulation-order noise, not bit for bit.
+"""
 import os
 import sys
 
@@ -16,6 +19,7 @@ import torch.distributed as dist  # noqa: E402
 import synth  # noqa: E402
 from helpers import synth_model  # noqa: E402
 from lfd.execution.hooks import OptimizerHook  # noqa: E402
+from lfd.execution.optim import FusedSGD  # noqa: E402
 from lfd.execution.parallel import shard_batch  # noqa: E402
 
 
@@ -25,7 +29,7 @@ class _Exec(object):
 
 
 def run(model, batches, sharded):
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt = FusedSGD.from_torch(torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4), model)
     hook = OptimizerHook(dict(max_norm=10, norm_type=2, duration=5), 10)
     cfg = dict(model=model, optimizer=opt, epoch=0)
     losses = []
@@ -43,11 +47,6 @@ def run(model, batches, sharded):
 def main():
     rank = int(os.environ['RANK'])
     torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
-    # batch 4 and 2 x batch 2 pick different cuDNN algorithms; with TF32 products their results differ at the 1e-3 level and
-    # three momentum steps amplify that -- the comparison is about the data-parallel arithmetic, so run the convs in true fp32
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.deterministic = True
     n, h, w = 4, 192, 192
     batches = [(synth.synth_input(n, h, w, seed=10 + i), synth.synth_annotations(n, h, w, 1, seed=20 + i)) for i in range(3)]
 
@@ -73,7 +72,7 @@ def main():
     for (name, a), (_, b) in zip(ref.named_parameters(), ddp.named_parameters()):
         d = float((a.detach() - b.detach()).abs().max() / a.detach().abs().max().clamp(min=1e-12))
         worst = max(worst, d)
-    ok = worst < 1e-3 and all(abs(float(t[i]) - ref_losses[i]) < 1e-3 * abs(ref_losses[i]) for i in range(len(ref_losses)))
+    ok = worst < 5e-3 and all(abs(float(t[i]) - ref_losses[i]) < 2e-3 * abs(ref_losses[i]) for i in range(len(ref_losses)))
     # every rank holds the same parameters
     flat = torch.cat([p.detach().reshape(-1) for p in ddp.parameters()])
     other = flat.clone()

@@ -1,10 +1,10 @@
 # -*- coding: utf-8 -*-
-"""Training step through the drop-in API on the GPU.
+"""The native training step through the drop-in API on the GPU.
 
-What is native here: label assignment, the losses and their gradients w.r.t. the network outputs, the flat-bucket gradient
-all-reduce.  The conv-stack forward / backward in training mode is ATen / cuDNN (lfd/_train.py, library code) -- these tests
-tie that module-graph walk to the native layer plan and check that the train loop of lfd.execution actually trains.
-"""
+Everything in the step is hand-written CUDA: forward in train mode (BatchNorm batch statistics), label assignment, losses, the
+backward of the whole conv stack (tcgen05 dgrad / wgrad, norm backward), the flat-bucket gradient all-reduce, clip + SGD.
+The checker is tests/aten_train_reference.py: the SAME module graph evaluated by ATen in fp32 and differentiated by autograd --
+the reference's arithmetic (lfd/model/lfd.py:511-542 through autograd)."""
 import os
 import subprocess
 import sys
@@ -14,6 +14,7 @@ import pytest
 import torch
 
 import synth
+from aten_train_reference import train_forward as aten_train_forward
 from helpers import rel_err, synth_model
 
 pytestmark = pytest.mark.gpu
@@ -22,66 +23,309 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _freeze_norms(model):
     for m in model.modules():
-        if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.GroupNorm)):
+        if isinstance(m, torch.nn.BatchNorm2d):
             m.eval()
 
 
-@pytest.mark.parametrize('cfg', ['WIDERFACE_XS', 'TT100K_S'])
-def test_train_graph_walk_matches_native_plan(cfg):
-    """With the BatchNorm layers on running statistics the ATen walk computes the same function as the native (bf16) plan:
-    same wiring, taps, shared towers, scales and output layout; the difference is the bounded bf16 drift of DESIGN.md gate C."""
-    model, _ = synth_model(cfg)
-    model.cuda()
+def _pair(cfg, cls_bias=-2.0):
+    a, _ = synth_model(cfg, cls_bias=cls_bias)
+    b, _ = synth_model(cfg, cls_bias=cls_bias)
+    return a.cuda().train(), b.cuda().train()
+
+
+@pytest.mark.parametrize('cfg,frozen', [('WIDERFACE_XS', False), ('WIDERFACE_L', False), ('TT100K_S', False), ('WIDERFACE_S', True)])
+def test_native_train_forward_matches_aten(cfg, frozen):
+    """Train-mode forward (batch statistics; `frozen`: BatchNorm modules in eval mode, as with norm_eval): native bf16 plan vs ATen fp32
+    on the same weights -- outputs inside the bf16 drift of DESIGN.md gate C, identical wiring / layout, running statistics updated
+    like nn.BatchNorm2d does."""
+    model, ref = _pair(cfg)
+    if frozen:
+        _freeze_norms(model)
+        _freeze_norms(ref)
     x = synth.synth_input(2, 184, 248).cuda()
-    model.eval()
+    emu, _ = synth_model(cfg, cls_bias=-2.0)
+    emu.cuda().train()
+    if frozen:
+        _freeze_norms(emu)
     with torch.no_grad():
         cls_n, reg_n = model(x)
-    sizes_eval = dict(model._head_indexes_to_feature_map_sizes)
-    model.train()
-    _freeze_norms(model)
-    with torch.no_grad():
-        cls_t, reg_t = model(x)
+        cls_n, reg_n = cls_n.clone(), reg_n.clone()
+        cls_t, reg_t = aten_train_forward(ref, x)
+        cls_e, reg_e = aten_train_forward(emu, x, emulate_bf16=True)
     assert cls_t.shape == cls_n.shape and reg_t.shape == reg_n.shape
-    assert dict(model._head_indexes_to_feature_map_sizes) == sizes_eval
-    for a, b in ((cls_n, cls_t), (reg_n, reg_t)):
-        _, rms = rel_err(a, b)
-        assert rms < 2.5e-2, rms
+    assert dict(model._head_indexes_to_feature_map_sizes) == dict(ref._head_indexes_to_feature_map_sizes)
+    # against the same graph with the native rounding points (bf16-emulated) and against plain fp32: train mode stores z AND y per
+    # layer as bf16 and re-normalises every layer to unit variance, so the drift is about twice the inference plan's
+    for a, b, c in ((cls_n, cls_e, cls_t), (reg_n, reg_e, reg_t)):
+        assert rel_err(a, b)[1] < 3e-2, ('vs bf16-emulated', rel_err(a, b))
+        assert rel_err(a, c)[1] < 6e-2, ('vs fp32', rel_err(a, c))
+        assert rel_err(a, c)[1] < 2.5 * max(rel_err(b, c)[1], 1e-2), ('drift vs the emulation\'s own drift', rel_err(a, c), rel_err(b, c))
+    worst = 0.0
+    for (name, ba), (_, bb_) in zip(model.named_buffers(), ref.named_buffers()):
+        if ba.dtype.is_floating_point:
+            worst = max(worst, float((ba - bb_).abs().max() / bb_.abs().max().clamp(min=1e-6)))
+        else:
+            assert torch.equal(ba, bb_), name          # num_batches_tracked
+    assert worst < 2e-2, worst
+
+
+def _teacher_forced_backward_check(cfg, n, h, w):
+    """Gate A/B of the backward: every layer of the native backward plan, fed the tensors the native path itself stored
+    (teacher forced: x, z, y and the incoming gradient dy come from the workspace), must reproduce torch autograd of THAT layer --
+    dz (normalisation + ReLU (+residual) backward), its share of dx (data gradient), its weight gradient, the norm-parameter
+    gradients, and for the head the final-conv / Scale gradients.  ReLU masks are the native ones, so the comparison is free of the
+    mask-flip chaos that dominates any end-to-end gradient comparison of two 16-bit pipelines (see the e2e test below)."""
+    import torch.nn.functional as F
+    model, _ = synth_model(cfg, cls_bias=-2.0)
+    model.cuda().train()
+    x_img = synth.synth_input(n, h, w).cuda()
+    ann = synth.synth_annotations(n, h, w, model._num_classes, seed=3)
+    out = model(x_img)
+    ld = model.get_loss(out, ann)
+    ld['loss'].backward()
+    torch.cuda.synchronize()
+    plan = list(model._train_plans.values())[0]
+    flat = model._flat_parameters
+    bf = lambda t: t.to(torch.bfloat16).float()
+
+    def nhwc(name, hh, ww, c):               # native tensor -> fp32 NCHW
+        return plan.tensor(name, hh, ww, c).float().permute(0, 3, 1, 2).contiguous()
+
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-20))
+
+    exp_grad, exp_param, shapes, worst = {}, {}, {}, {}
+
+    def note(kind, name, e, tol):
+        worst[kind] = max(worst.get(kind, (0.0, ''))[0], e), name if e >= worst.get(kind, (0.0, ''))[0] else worst[kind][1]
+        assert e < tol, (cfg, kind, name, e)
+
+    def add_param(p, g):
+        exp_param[id(p)] = exp_param.get(id(p), 0) + g
+
+    def conv_backward(L, dz_native):
+        conv, geo = L['conv'], L['geo']
+        k, s = geo['ksize'], geo['stride']
+        if L['x'] is None:
+            xin = bf(x_img)
+        else:
+            xin = nhwc(L['x'], geo['H'], geo['W'], geo['Cin'])
+        add_param(conv.weight, torch.nn.grad.conv2d_weight(xin, conv.weight.shape, dz_native, stride=s, padding=k // 2))
+        if L['x'] is not None:
+            dx = torch.nn.grad.conv2d_input(xin.shape, bf(conv.weight.detach()), dz_native, stride=s, padding=k // 2)
+            exp_grad[L['x']] = exp_grad.get(L['x'], 0) + dx
+            shapes[L['x']] = (geo['H'], geo['W'], geo['Cin'])
+        # forward of this layer, teacher forced: z = conv(x) on the bf16 operands
+        zname = L['z'] if L['type'] == 'bn' else L['raw']
+        z_exp = F.conv2d(xin, bf(conv.weight.detach()), None, stride=s, padding=k // 2)
+        z_nat = nhwc(zname, geo['Ho'], geo['Wo'], geo['Cout'])
+        note('forward conv', L['name'], float((z_nat - z_exp).abs().max() / z_exp.abs().max().clamp(min=1e-20)), 2.0 ** -7)
+
+    for L in reversed(plan._layers):
+        geo = L['geo']
+        if L['type'] == 'final':
+            hh, ww = geo['H'], geo['W']
+            raw = nhwc(L['raw'], hh, ww, 128)
+            norm = L['norm']
+            t = bf(F.relu(F.group_norm(raw, 16, norm.weight.detach(), norm.bias.detach(), norm.eps))).requires_grad_(True)
+            # the convs / Scale of this level, from the staging the native kernel read (bf16-rounded weights)
+            no = geo['n_cls'] + geo['n_reg']
+            off = plan._off[L['stage']]
+            stg = plan.workspace[off:off + (no * 128 + 3 * no) * 4].view(torch.float32)
+            Wm = stg[:no * 128].view(no, 128).clone().requires_grad_(True)
+            sc = stg[no * 128:no * 128 + no].clone()
+            bias = stg[no * 128 + 2 * no:no * 128 + 3 * no].clone().requires_grad_(True)
+            scale_leaf = torch.ones((), device='cuda', requires_grad=True)
+            pre = torch.einsum('nchw,oc->nohw', t, Wm) + bias[None, :, None, None]
+            mult = torch.cat([sc[:geo['n_cls']], scale_leaf * sc[geo['n_cls']:]])      # d/d(Scale) goes through the regression rows
+            o = pre * mult[None, :, None, None]
+            po, HW = geo['point_off'], hh * ww
+            up = torch.cat([plan.gcls[:, po:po + HW, :geo['n_cls']], plan.greg[:, po:po + HW, :geo['n_reg']]], -1)
+            o.backward(up.permute(0, 2, 1).reshape(n, no, hh, ww))
+            dact = nhwc('d_' + L['raw'] + '_act', hh, ww, 128)
+            note('head dact', L['name'], rel(dact, t.grad), 1e-2)
+            L['_exp'] = (Wm.grad, bias.grad, scale_leaf.grad, sc)
+            continue
+        if L['type'] == 'gn':
+            hh, ww, c = geo['H'], geo['W'], geo['Cout']
+            raw = nhwc(L['raw'], hh, ww, c).requires_grad_(True)
+            norm = L['norm']
+            g, b = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
+            dact = nhwc('d_' + (L['act'] if L['act'] is not None else L['raw'] + '_act'), hh, ww, c)
+            F.relu(F.group_norm(raw, 16, g, b, norm.eps)).backward(dact)
+            draw = nhwc('d_' + L['raw'], hh, ww, c)
+            note('gn dz', L['name'], rel(draw, raw.grad), 1.2e-2)
+            add_param(norm.weight, g.grad)
+            add_param(norm.bias, b.grad)
+            conv_backward(L, draw)
+            continue
+        ho, wo, c = geo['Ho'], geo['Wo'], geo['Cout']
+        norm = L['norm']
+        z = nhwc(L['z'], ho, wo, c).requires_grad_(True)
+        g, b = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
+        yt = F.batch_norm(z, None, None, g, b, training=True, eps=norm.eps)
+        res = None
+        if L['res'] is not None:
+            res = nhwc(L['res'], ho, wo, c).requires_grad_(True)
+            yt = yt + res
+        if L['relu']:
+            yt = F.relu(yt)
+        y_nat = nhwc(L['y'], ho, wo, c)
+        note('forward bn', L['name'], float((y_nat - yt.detach()).abs().max() / yt.detach().abs().max()), 2.0 ** -7)
+        yt.backward(nhwc('d_' + L['y'], ho, wo, c))
+        dz = nhwc('d_' + L['z'], ho, wo, c)
+        note('bn dz', L['name'], rel(dz, z.grad), 1.2e-2)
+        add_param(norm.weight, g.grad)
+        add_param(norm.bias, b.grad)
+        if res is not None:
+            exp_grad[L['res']] = exp_grad.get(L['res'], 0) + res.grad
+            shapes[L['res']] = (ho, wo, c)
+        conv_backward(L, dz)
+    # accumulated data gradients: every consumer's contribution, each computed from the NATIVE dz of that consumer
+    for name, gexp in exp_grad.items():
+        hh, ww, c = shapes[name]
+        note('dx', name, rel(nhwc('d_' + name, hh, ww, c), gexp), 1.5e-2)
+    # head final convs / Scale (the rows of a shared head add up over the levels)
+    head = model._head
+    for L in plan._layers:
+        if L['type'] != 'final':
+            continue
+        Wg, bg, sg, sc = L.pop('_exp')
+        lvl = int(''.join(ch for ch in L['name'].split('fin')[0] if ch.isdigit()))
+        cls_tower, reg_tower, fin_cls, fin_reg = head.level_paths(lvl)
+        ncls = L['geo']['n_cls']
+        if ncls:
+            add_param(fin_cls.weight, Wg[:ncls].reshape(fin_cls.weight.shape))
+            add_param(fin_cls.bias, bg[:ncls])
+        if L['geo']['n_reg']:
+            add_param(fin_reg.weight, Wg[ncls:].reshape(fin_reg.weight.shape))
+            add_param(fin_reg.bias, bg[ncls:])
+            if head.uses_scale:
+                add_param(head._scales[lvl]._scale, sg / float(sc[ncls]))      # d/dScale = d/d(scale_leaf) / Scale
+    for name, p in model.named_parameters():
+        if id(p) not in exp_param:
+            continue
+        e = rel(p.grad, exp_param[id(p)].reshape(p.shape))
+        if float(exp_param[id(p)].norm()) > 1e-12:
+            note('parameter gradient', name, e, 5e-3 if p.dim() != 0 else 2e-2)
+    print('%s teacher-forced backward: %s' % (cfg, {k: '%.1e (%s)' % v for k, v in worst.items()}))
+
+
+@pytest.mark.parametrize('cfg,shape', [('WIDERFACE_XS', (2, 160, 192)), ('WIDERFACE_L', (2, 128, 160)), ('TT100K_S', (2, 160, 160)), ('TT100K_L', (1, 128, 128))])
+def test_native_backward_teacher_forced(cfg, shape):
+    _teacher_forced_backward_check(cfg, *shape)
+
+
+@pytest.mark.parametrize('cfg', ['WIDERFACE_XS', 'WIDERFACE_L'])
+def test_native_parameter_gradients_end_to_end(cfg):
+    """loss.backward() through the native backward plan vs autograd over the ATen evaluation, END TO END.  Two 16-bit pipelines whose
+    activations agree to ~1 % flip about that fraction of the ReLU masks, and every flipped element carries a full-size gradient error:
+    the gradients of deep layers decorrelate at the 30-50 % level -- for ANY pair of bf16 pipelines: the ATen graph with the native
+    rounding points (emulated) differs from ATen fp32 by as much as the native path does.  What is asserted end to end is therefore
+    (a) losses agree, (b) the native gradients are as close to the fp32 ones as the emulation is (within 1.5x), (c) the layers next to
+    the loss (final head convs) agree tightly.  The tight, per-layer statement is test_native_backward_teacher_forced."""
+    models = [synth_model(cfg, cls_bias=-2.0)[0].cuda().train() for _ in range(3)]
+    n, h, w = 4, 192, 256
+    x = synth.synth_input(n, h, w).cuda()
+    ann = synth.synth_annotations(n, h, w, models[0]._num_classes, seed=3)
+    lv = []
+    for i, m in enumerate(models):
+        out = m(x) if i == 0 else aten_train_forward(m, x, emulate_bf16=(i == 2))
+        ld = m.get_loss(out, ann)
+        if i:
+            for p in m.parameters():
+                p.grad = None
+        ld['loss'].backward()
+        lv.append(ld['loss_values']['loss'])
+    assert abs(lv[0] - lv[1]) < 2e-2 * abs(lv[1]) and abs(lv[0] - lv[2]) < 2e-2 * abs(lv[2]), lv
+    sq = [0.0, 0.0, 0.0]      # |native - fp32|^2, |emulated - fp32|^2, |fp32|^2 over all parameters
+    for (name, p), (_, q), (_, r) in zip(*[m.named_parameters() for m in models]):
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        g, t, e = p.grad.double(), q.grad.double(), r.grad.double()
+        sq[0] += float(((g - t) ** 2).sum()); sq[1] += float(((e - t) ** 2).sum()); sq[2] += float((t ** 2).sum())
+        if 'classification_path' in name and name.endswith('weight'):
+            assert float((g - t).norm() / t.norm()) < 5e-2, name
+    nat, emu = (sq[0] / sq[2]) ** 0.5, (sq[1] / sq[2]) ** 0.5
+    print('%s: whole-model gradient error vs fp32: native %.2f, bf16-emulated ATen %.2f' % (cfg, nat, emu))
+    assert nat < 1.5 * emu + 0.05, (nat, emu)
 
 
 def test_train_loop_reduces_the_loss():
-    """Executor-style iterations on a fixed batch: forward (train mode, batch statistics), native get_loss, backward,
-    gradient clipping, SGD step -- all parameters receive finite gradients and the loss goes down."""
+    """Executor-style iterations on a fixed batch with the hook's native path: forward (train mode), native get_loss, backward,
+    fused clip + SGD over the flat buffers -- every parameter receives a finite gradient and the loss goes down."""
+    from lfd.execution.hooks import OptimizerHook
+    from lfd.execution.optim import FusedSGD
     model, _ = synth_model('WIDERFACE_XS', cls_bias=-2.0)
     model.cuda().train()
     n, h, w = 4, 256, 256
     x = synth.synth_input(n, h, w).cuda()
     ann = synth.synth_annotations(n, h, w, 1, seed=3)
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt = FusedSGD.from_torch(torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4), model)
+    hook = OptimizerHook(dict(max_norm=10, norm_type=2, duration=5), 10)
+
+    class _Exec(object):
+        config_dict = dict(model=model, optimizer=opt, epoch=0)
     losses = []
     for it in range(8):
         out = model(x)
         ld = model.get_loss(out, ann)
-        opt.zero_grad()
-        ld['loss'].backward()
+        _Exec.config_dict['loss'] = ld['loss']
+        hook.after_train_iter(_Exec)
         if it == 0:
             for name, p in model.named_parameters():
                 assert p.grad is not None and torch.isfinite(p.grad).all(), name
-        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10, norm_type=2)
-        opt.step()
+            assert float(_Exec.config_dict['grad_norm']) > 0
         losses.append(ld['loss_values']['loss'])
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < 0.8 * losses[0], losses
-    # the eval path picks the updated weights up (the plan cache is keyed by a parameter fingerprint)
+    # the eval path picks the updated weights up
     model.eval()
     with torch.no_grad():
         cls, reg = model(x)
     assert torch.isfinite(cls).all() and torch.isfinite(reg).all()
 
 
+def test_fused_sgd_state_dict_round_trip():
+    from lfd.execution.optim import FusedSGD
+    model, _ = synth_model('WIDERFACE_XS')
+    model.cuda().train()
+    topt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt = FusedSGD.from_torch(topt, model)
+    opt.zero_grad()
+    for p in model.parameters():
+        p.grad.normal_()
+    opt.step()
+    sd = opt.state_dict()
+    assert len(sd['state']) == len(list(model.parameters())) and sd['param_groups'][0]['lr'] == 0.01
+    topt2 = torch.optim.SGD(model.parameters(), lr=0.5, momentum=0.9)
+    topt2.load_state_dict(sd)          # the reference's optimizer reads it
+    opt2 = FusedSGD.from_torch(topt2, model)
+    opt2.load_state_dict(sd)
+    opt2._sync()
+    assert opt2.param_groups[0]['lr'] == 0.01 and torch.equal(opt2._mom, opt._mom)
+
+
+def test_cuda_graph_training_step_matches_eager():
+    model, ref = _pair('WIDERFACE_XS')
+    ref.use_cuda_graph_training = True
+    n, h, w = 2, 128, 160
+    x = synth.synth_input(n, h, w).cuda()
+    ann = synth.synth_annotations(n, h, w, 1, seed=5)
+    grads = []
+    for m in (model, ref):
+        for it in range(3):          # the third pass of `ref` replays the captured graphs
+            out = m(x)
+            ld = m.get_loss(out, ann)
+            m._flat_parameters.grad.zero_()
+            ld['loss'].backward()
+        grads.append(m._flat_parameters.grad.clone())
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-3 * float(grads[0].abs().max())
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (NCCL)')
 def test_ddp_two_ranks_match_one_rank_on_the_full_batch():
     """tests/run_train_ddp.py: 2 ranks (NCCL), each on half of the batch, global positive-count normalisation + SUM
-    all-reduce of one flat gradient bucket == 1 rank on the whole batch."""
+    all-reduce of the flat gradient buffer == 1 rank on the whole batch."""
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
            '--master-port', '29517', os.path.join(ROOT, 'tests', 'run_train_ddp.py')]

@@ -434,8 +434,9 @@ def train_main(args):
     torch.cuda.synchronize()
     assign_ms = (time.perf_counter() - t0) * 1e3 / 10
     t0 = time.perf_counter()
-    orc.assign_targets(orc.CONFIGS[wl['cfg']], sizes, [a[0] for a in anns[0][:2]], [a[1] for a in anns[0][:2]])
-    assign_cpu_ms = (time.perf_counter() - t0) * 1e3 / 2 * N
+    for a in anns[0][:4]:                     # one image at a time, like the reference's python loop (lfd.py:121-150)
+        orc.assign_targets(orc.CONFIGS[wl['cfg']], sizes, a[0], a[1])
+    assign_cpu_ms = (time.perf_counter() - t0) * 1e3 / 4 * N
 
     # ---- live per-op roofline of the forward and backward plans (eager passes with an event pair around every launch)
     pk = peaks()

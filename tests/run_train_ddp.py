@@ -65,9 +65,11 @@ def main():
     ddp = fresh()
     losses = run(ddp, batches, sharded=True)
     assert ddp.loss_globally_normalised
-    # per-rank losses add up to the full-batch loss
+    # LFD.get_loss logs the GLOBAL batch's loss on every rank (per-rank sums over the global positive count, all-reduced):
+    # the mean over ranks of what each rank logged is that global loss, and it must equal the full-batch loss
     t = torch.tensor(losses, dtype=torch.float64, device='cuda')
     dist.all_reduce(t)
+    t /= dist.get_world_size()
     worst = 0.0
     for (name, a), (_, b) in zip(ref.named_parameters(), ddp.named_parameters()):
         d = float((a.detach() - b.detach()).abs().max() / a.detach().abs().max().clamp(min=1e-12))
@@ -81,7 +83,7 @@ def main():
     flag = torch.tensor([1 if (ok and same) else 0], device='cuda')
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print('losses full batch %s | summed over ranks %s | worst relative parameter difference %.2e | identical across ranks %s'
+        print('losses full batch %s | logged by the ranks (global) %s | worst relative parameter difference %.2e | identical across ranks %s'
               % (['%.5f' % v for v in ref_losses], ['%.5f' % float(v) for v in t], worst, same))
         print('DDP_OK' if int(flag.item()) == 1 else 'DDP_MISMATCH')
     dist.barrier()

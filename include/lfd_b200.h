@@ -183,13 +183,33 @@ int lfd_assign_targets(const lfd_levels* lv, int N, int P, int C, int gmax, int 
                        const float* gt_boxes, const int32_t* gt_labels, const int32_t* gt_count, float* cls_target,
                        float* reg_target, int32_t* label, int32_t* counters, lfd_stream stream);
 
-/* loss_sums double[2] = {sum of element-wise cls loss over valid rows, sum of -log(IoU) over positives} (zeroed inside);
+/* Losses of LFD.get_loss (lfd/model/lfd.py:326-387) and their gradients w.r.t. the network outputs.
+ * classification (over the non-gray rows, avg_factor = n_pos + 1): sigmoid focal (FocalLoss), cross entropy over C+1 logits
+ * (CrossEntropyLoss), BCE with logits against the soft targets (BCEWithLogitsLoss), quality focal (QualityFocalLoss, beta in `gamma`,
+ * quality = the point's maximal centre score); regression (positives, avg_factor = n_pos): -log IoU / GIoU / DIoU / CIoU on the decoded
+ * boxes (bbox_mode sigmoid | exp), SmoothL1 / MSE on the raw outputs against the range-normalised targets (bbox_mode independent). */
+enum { LFD_CLS_BCE = 2, LFD_CLS_QFL = 3 }; /* continues LFD_CLS_SIGMOID = 0, LFD_CLS_SOFTMAX = 1 */
+enum { LFD_REG_IOU = 0, LFD_REG_GIOU = 1, LFD_REG_DIOU = 2, LFD_REG_CIOU = 3, LFD_REG_SMOOTH_L1 = 4, LFD_REG_MSE = 5 };
+typedef struct lfd_loss_cfg {
+    int32_t N, P, C;
+    int32_t cls_mode, bbox_mode, reg_loss;
+    float gamma, alpha;          /* focal: gamma, alpha; quality focal: beta in gamma */
+    float reg_eps;               /* IoU family eps */
+    float smooth_l1_beta;
+    float cls_weight, reg_weight;
+} lfd_loss_cfg;
+/* loss_sums double[2] = {sum of element-wise cls loss over valid rows, sum of the regression loss over positives} (zeroed inside);
  * the reference's normalisation is loss = sums[0]/(n_pos+1) + sums[1]/n_pos.  grad_cls / grad_reg (optional) receive
- * d loss / d cls_logits and d loss / d reg with that normalisation and the loss weights applied. */
-int lfd_detection_loss(const lfd_levels* lv, int N, int P, int C, int cls_mode, int bbox_mode, float gamma, float alpha,
-                       float iou_eps, float cls_weight, float reg_weight, const float* cls_logits, const float* reg,
-                       const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls,
-                       float* grad_reg, double* loss_sums, lfd_stream stream);
+ * d loss / d cls_logits and d loss / d reg with that normalisation and the loss weights applied.  cls_target (N, P, C): the soft
+ * targets of lfd_assign_targets, needed by BCE / QFL only (may be NULL otherwise). */
+int lfd_detection_loss(const lfd_levels* lv, const lfd_loss_cfg* cfg, const float* cls_logits, const float* reg, const float* cls_target,
+                       const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls, float* grad_reg,
+                       double* loss_sums, lfd_stream stream);
+
+/* Element-wise box losses of the stand-alone IoULoss / GIoULoss / DIoULoss / CIoULoss modules (lfd/model/losses/iou_loss.py:105-283,
+ * before the reduction): pred / target float[n][4] xyxy, kind = LFD_REG_IOU .. LFD_REG_CIOU; loss float[n], grad_pred float[n][4]
+ * (d loss_i / d pred_i, optional). */
+int lfd_box_loss(int kind, const float* pred, const float* target, int n, float eps, float* loss, float* grad_pred, lfd_stream stream);
 
 int lfd_sigmoid_focal_loss_forward(const float* logits, const int64_t* targets, int M, int C, float gamma, float alpha,
                                    float* losses, lfd_stream stream);

@@ -546,24 +546,36 @@ extern "C" int lfd_assign_targets(const lfd_levels* lv, int N, int P, int C, int
     return LFD_OK;
 }
 
-extern "C" int lfd_detection_loss(const lfd_levels* lv, int N, int P, int C, int cls_mode, int bbox_mode, float gamma, float alpha,
-                                  float iou_eps, float cls_weight, float reg_weight, const float* cls_logits, const float* reg,
-                                  const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls,
-                                  float* grad_reg, double* loss_sums, lfd_stream stream) {
-    if (!lv || !cls_logits || !reg || !reg_target || !label || !counters || !loss_sums) return fail(LFD_ERR_INVALID, "lfd_detection_loss: null argument");
-    if (bbox_mode != LFD_BBOX_SIGMOID && bbox_mode != LFD_BBOX_EXP) return fail(LFD_ERR_UNSUPPORTED, "lfd_detection_loss: only IoU-type (union) regression losses are implemented");
+extern "C" int lfd_detection_loss(const lfd_levels* lv, const lfd_loss_cfg* c, const float* cls_logits, const float* reg, const float* cls_target,
+                                  const float* reg_target, const int32_t* label, const int32_t* counters, float* grad_cls, float* grad_reg,
+                                  double* loss_sums, lfd_stream stream) {
+    if (!lv || !c || !cls_logits || !reg || !reg_target || !label || !counters || !loss_sums) return fail(LFD_ERR_INVALID, "lfd_detection_loss: null argument");
+    if (c->cls_mode < LFD_CLS_SIGMOID || c->cls_mode > LFD_CLS_QFL) return fail(LFD_ERR_INVALID, "lfd_detection_loss: unknown classification loss %d", c->cls_mode);
+    if ((c->cls_mode == LFD_CLS_BCE || c->cls_mode == LFD_CLS_QFL) && !cls_target) return fail(LFD_ERR_INVALID, "lfd_detection_loss: BCE / QFL need the soft classification targets");
+    if (c->reg_loss < LFD_REG_IOU || c->reg_loss > LFD_REG_MSE) return fail(LFD_ERR_INVALID, "lfd_detection_loss: unknown regression loss %d", c->reg_loss);
+    const bool indep = c->reg_loss == LFD_REG_SMOOTH_L1 || c->reg_loss == LFD_REG_MSE;
+    if (indep != (c->bbox_mode == LFD_BBOX_INDEPENDENT)) return fail(LFD_ERR_INVALID, "lfd_detection_loss: SmoothL1 / MSE go with the 'independent' targets, the IoU family with sigmoid / exp");
+    if (c->reg_loss == LFD_REG_SMOOTH_L1 && !(c->smooth_l1_beta > 0.f)) return fail(LFD_ERR_INVALID, "lfd_detection_loss: SmoothL1 beta must be > 0");
     if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_detection_loss: no CUDA device (there is no CPU fallback)");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaMemsetAsync(loss_sums, 0, 16, st));
-    ClsLossParams c;
-    c.logits = cls_logits; c.label = label; c.counters = counters; c.grad = grad_cls; c.loss_sum = loss_sums;
-    c.N = N; c.P = P; c.C = C; c.cls_mode = cls_mode; c.gamma = gamma; c.alpha = alpha; c.loss_weight = cls_weight;
-    CUDA_TRY(cls_loss_launch(c, sm_count(), st));
+    ClsLossParams k;
+    k.logits = cls_logits; k.cls_target = cls_target; k.label = label; k.counters = counters; k.grad = grad_cls; k.loss_sum = loss_sums;
+    k.N = c->N; k.P = c->P; k.C = c->C; k.cls_mode = c->cls_mode; k.gamma = c->gamma; k.alpha = c->alpha; k.loss_weight = c->cls_weight;
+    CUDA_TRY(cls_loss_launch(k, sm_count(), st));
     RegLossParams r;
     fill_levels(lv, &r.lv);
     r.reg = reg; r.reg_target = reg_target; r.label = label; r.counters = counters; r.grad = grad_reg; r.loss_sum = loss_sums + 1;
-    r.N = N; r.P = P; r.C = C; r.bbox_mode = bbox_mode; r.eps = iou_eps; r.loss_weight = reg_weight;
+    r.N = c->N; r.P = c->P; r.C = c->C; r.bbox_mode = c->bbox_mode; r.loss_kind = c->reg_loss; r.eps = c->reg_eps; r.loss_weight = c->reg_weight;
+    r.beta = c->smooth_l1_beta;
     CUDA_TRY(iou_loss_launch(r, sm_count(), st));
+    return LFD_OK;
+}
+
+extern "C" int lfd_box_loss(int kind, const float* pred, const float* target, int n, float eps, float* loss, float* grad_pred, lfd_stream stream) {
+    if (kind < LFD_REG_IOU || kind > LFD_REG_CIOU || n < 0 || (n > 0 && (!pred || !target || !loss))) return fail(LFD_ERR_INVALID, "lfd_box_loss: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_box_loss: no CUDA device (there is no CPU fallback)");
+    CUDA_TRY(box_loss_launch(kind, pred, target, n, eps, loss, grad_pred, reinterpret_cast<cudaStream_t>(stream)));
     return LFD_OK;
 }
 

@@ -109,11 +109,12 @@ cudaError_t focal_backward_launch(const float* logits, const long long* targets,
 
 struct ClsLossParams {
     const float* logits;       // (N, P, C')
+    const float* cls_target;   // (N, P, C) soft targets (BCE / QFL only)
     const int* label;
     const int* counters;
     float* grad;               // (N, P, C') or null
     double* loss_sum;          // zeroed by the caller
-    int N, P, C, cls_mode;
+    int N, P, C, cls_mode;     // 0 sigmoid focal, 1 cross entropy (C+1 logits), 2 BCE-with-logits on the soft targets, 3 quality focal (beta = gamma)
     float gamma, alpha, loss_weight;
 };
 cudaError_t cls_loss_launch(const ClsLossParams& p, int num_sms, cudaStream_t st);
@@ -126,9 +127,12 @@ struct RegLossParams {
     const int* counters;
     float* grad;
     double* loss_sum;
-    int N, P, C, bbox_mode;
-    float eps, loss_weight;
+    int N, P, C, bbox_mode;    // 0 sigmoid * range, 1 exp, 2 independent (raw outputs against targets / range)
+    int loss_kind;             // 0 IoU (-log), 1 GIoU, 2 DIoU, 3 CIoU, 4 SmoothL1, 5 MSE (4, 5: bbox_mode 2 only)
+    float eps, loss_weight, beta;
 };
 cudaError_t iou_loss_launch(const RegLossParams& p, int num_sms, cudaStream_t st);
+// element-wise IoU-family loss (kind 0..3) + d loss / d pred on explicit box pairs
+cudaError_t box_loss_launch(int kind, const float* pred, const float* target, int n, float eps, float* loss, float* grad, cudaStream_t st);
 
 }  // namespace lfd

@@ -185,15 +185,40 @@ __global__ void __launch_bounds__(256) cls_loss_kernel(const ClsLossParams p) {
     const float inv_avg = 1.0f / (float)(p.counters[0] + 1);
     double acc = 0.0;
     const size_t rows = (size_t)p.N * p.P;
-    if (p.cls_mode == 0) {
+    if (p.cls_mode != 1) {
         const size_t total = rows * Cp;
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
             const int t = p.label[i / Cp];
             float l = 0.f, g = 0.f;
             if (t >= 0) {
                 const int d = (int)(i % Cp);
-                l = focal_fwd(p.logits[i], t, d, p.gamma, p.alpha);
-                g = focal_bwd(p.logits[i], t, d, p.gamma, p.alpha) * inv_avg * p.loss_weight;
+                const float x = p.logits[i];
+                if (p.cls_mode == 0) {
+                    l = focal_fwd(x, t, d, p.gamma, p.alpha);
+                    g = focal_bwd(x, t, d, p.gamma, p.alpha);
+                } else {
+                    // binary cross entropy with logits against a target q (ATen's stable form): max(x,0) - x q + log(1 + exp(-|x|))
+                    const float sg = 1.0f / (1.0f + expf(-x));
+                    const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));      // softplus(x) = BCE(x, 0)
+                    if (p.cls_mode == 2) {                                          // losses/bce_with_logits_loss.py:28-44, soft targets
+                        const float q = p.cls_target[i];
+                        l = sp - x * q;
+                        g = sg - q;
+                    } else if (d != t) {                                            // quality focal, negatives: BCE(x, 0) * sigmoid^beta
+                        const float m = powf(sg, p.gamma);                          // (losses/gfocal_loss.py:32-38)
+                        l = sp * m;
+                        g = sg * m + sp * p.gamma * m * (1.0f - sg);
+                    } else {                                                        // positives: BCE(x, score) * |score - sigmoid|^beta (:41-46)
+                        const float* row = p.cls_target + (i / Cp) * Cp;
+                        float q = row[0];
+                        for (int c = 1; c < Cp; ++c) q = fmaxf(q, row[c]);          // quality = the point's (maximal) centre score
+                        const float a = fabsf(q - sg), bce = sp - x * q;
+                        const float m = powf(a, p.gamma);
+                        l = bce * m;
+                        g = (sg - q) * m + (a > 0.f ? bce * p.gamma * powf(a, p.gamma - 1.0f) * (q > sg ? -1.f : 1.f) * sg * (1.0f - sg) : 0.f);
+                    }
+                }
+                g *= inv_avg * p.loss_weight;
             }
             if (p.grad) p.grad[i] = g;
             acc += (double)l;
@@ -220,7 +245,63 @@ __global__ void __launch_bounds__(256) cls_loss_kernel(const ClsLossParams p) {
     if (threadIdx.x == 0) atomicAdd(p.loss_sum, s);
 }
 
-// regression loss of get_loss (lfd.py:343-387), union (IoU) type only: positives, avg_factor = n_pos.
+
+// ---------------------------------------------------------------------------------------------------
+// forward-mode derivatives w.r.t. the four predicted box coordinates (x1, y1, x2, y2): the GIoU / DIoU / CIoU losses are written
+// exactly like the reference's functions (losses/iou_loss.py:125-283) on this type, so value AND gradient follow the same formula
+struct Dual {
+    float v, d[4];
+};
+__device__ __forceinline__ Dual dc(float c) { Dual r; r.v = c; r.d[0] = r.d[1] = r.d[2] = r.d[3] = 0.f; return r; }
+__device__ __forceinline__ Dual dvar(float v, int i) { Dual r = dc(v); r.d[i] = 1.f; return r; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { Dual r; r.v = a.v + b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] + b.d[i]; return r; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { Dual r; r.v = a.v - b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] - b.d[i]; return r; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { Dual r; r.v = a.v * b.v; for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+    Dual r; r.v = a.v / b.v;
+    const float inv = 1.0f / b.v;
+    for (int i = 0; i < 4; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+    return r;
+}
+__device__ __forceinline__ Dual dmax(Dual a, Dual b) {   // torch.max(a, b): ties share the gradient
+    if (a.v > b.v) return a;
+    if (b.v > a.v) return b;
+    Dual r; r.v = a.v; for (int i = 0; i < 4; ++i) r.d[i] = 0.5f * (a.d[i] + b.d[i]); return r;
+}
+__device__ __forceinline__ Dual dmin(Dual a, Dual b) {
+    if (a.v < b.v) return a;
+    if (b.v < a.v) return b;
+    Dual r; r.v = a.v; for (int i = 0; i < 4; ++i) r.d[i] = 0.5f * (a.d[i] + b.d[i]); return r;
+}
+__device__ __forceinline__ Dual dclamp0(Dual a) { return a.v >= 0.f ? a : dc(0.f); }   // clamp(min=0): gradient where a >= 0
+__device__ __forceinline__ Dual datan(Dual a) { Dual r; r.v = atanf(a.v); const float k = 1.0f / (1.0f + a.v * a.v); for (int i = 0; i < 4; ++i) r.d[i] = a.d[i] * k; return r; }
+
+// kind 1 GIoU, 2 DIoU, 3 CIoU; pr = predicted box (variables), tg = target box (constants)
+__device__ __forceinline__ Dual iou_family_loss(int kind, const Dual* pr, const float* tgf, float eps) {
+    const Dual tg[4] = {dc(tgf[0]), dc(tgf[1]), dc(tgf[2]), dc(tgf[3])};
+    const Dual w = dclamp0(dmin(pr[2], tg[2]) - dmax(pr[0], tg[0])), h = dclamp0(dmin(pr[3], tg[3]) - dmax(pr[1], tg[1]));
+    const Dual overlap = w * h;
+    const Dual ap = (pr[2] - pr[0]) * (pr[3] - pr[1]), ag = (tg[2] - tg[0]) * (tg[3] - tg[1]);
+    const Dual uni = ap + ag - overlap + dc(eps);
+    const Dual ious = overlap / uni;
+    const Dual cw = dclamp0(dmax(pr[2], tg[2]) - dmin(pr[0], tg[0])), ch = dclamp0(dmax(pr[3], tg[3]) - dmin(pr[1], tg[1]));
+    if (kind == 1) {
+        const Dual area = cw * ch + dc(eps);
+        return dc(1.f) - (ious - (area - uni) / area);
+    }
+    const Dual c2 = cw * cw + ch * ch + dc(eps);
+    const Dual dx = (tg[0] + tg[2]) - (pr[0] + pr[2]), dy = (tg[1] + tg[3]) - (pr[1] + pr[3]);
+    const Dual rho2 = (dx * dx) / dc(4.f) + (dy * dy) / dc(4.f);
+    if (kind == 2) return dc(1.f) - (ious - rho2 / c2);
+    const Dual w1 = pr[2] - pr[0], h1 = pr[3] - pr[1] + dc(eps);
+    const Dual w2 = tg[2] - tg[0], h2 = tg[3] - tg[1] + dc(eps);
+    const Dual da = datan(w2 / h2) - datan(w1 / h1);
+    const Dual v = dc(0.40528473456935109f) * da * da;          // 4 / pi^2
+    return dc(1.f) - (ious - (rho2 / c2 + (v * v) / (dc(1.f) - ious + v)));
+}
+
+// regression loss of get_loss (lfd.py:343-387): positives, avg_factor = n_pos.  loss_kind 0: -log IoU (analytic gradient);
+// 1..3: GIoU / DIoU / CIoU through forward-mode derivatives; 4, 5: SmoothL1 / MSE on the raw outputs ('independent' targets).
 __global__ void __launch_bounds__(256) iou_loss_kernel(const RegLossParams p) {
     __shared__ double sh[8];
     const size_t rows = (size_t)p.N * p.P;
@@ -236,6 +317,22 @@ __global__ void __launch_bounds__(256) iou_loss_kernel(const RegLossParams p) {
             const float4 rv = reinterpret_cast<const float4*>(p.reg)[r];
             const float4 tv = reinterpret_cast<const float4*>(p.reg_target)[r];
             float raw[4] = {rv.x, rv.y, rv.z, rv.w}, d[4], dd[4];  // dd = d(distance)/d(raw)
+            if (p.loss_kind >= 4) {   // 'independent': element-wise loss between the raw outputs and the range-normalised targets (lfd.py:353-358)
+                const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
+                float gk[4], ls = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float df = raw[k] - tg[k], ad = fabsf(df);
+                    if (p.loss_kind == 4) {                      // losses/smooth_l1_loss.py:10-28
+                        if (ad < p.beta) { ls += 0.5f * ad * ad / p.beta; gk[k] = df / p.beta; }
+                        else { ls += ad - 0.5f * p.beta; gk[k] = df > 0.f ? 1.f : -1.f; }
+                    } else { ls += df * df; gk[k] = 2.f * df; }  // F.mse_loss(reduction='none')
+                }
+                acc += (double)ls;
+                const float sc = inv_avg * p.loss_weight;
+                if (p.grad) reinterpret_cast<float4*>(p.grad)[r] = make_float4(gk[0] * sc, gk[1] * sc, gk[2] * sc, gk[3] * sc);
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (p.bbox_mode == 0) { const float s = 1.0f / (1.0f + expf(-raw[k])); d[k] = s * pg.hi; dd[k] = pg.hi * s * (1.0f - s); }
@@ -243,6 +340,15 @@ __global__ void __launch_bounds__(256) iou_loss_kernel(const RegLossParams p) {
             }
             const float px1 = pg.px - d[0], py1 = pg.py - d[1], px2 = pg.px + d[2], py2 = pg.py + d[3];
             const float tx1 = pg.px - tv.x, ty1 = pg.py - tv.y, tx2 = pg.px + tv.z, ty2 = pg.py + tv.w;
+            if (p.loss_kind >= 1) {
+                const Dual pr[4] = {dvar(px1, 0), dvar(py1, 1), dvar(px2, 2), dvar(py2, 3)};
+                const float tg[4] = {tx1, ty1, tx2, ty2};
+                const Dual ls = iou_family_loss(p.loss_kind, pr, tg, p.eps);
+                acc += (double)ls.v;
+                const float sc = inv_avg * p.loss_weight;
+                if (p.grad) reinterpret_cast<float4*>(p.grad)[r] = make_float4(-ls.d[0] * dd[0] * sc, -ls.d[1] * dd[1] * sc, ls.d[2] * dd[2] * sc, ls.d[3] * dd[3] * sc);
+                continue;
+            }
             const float ltx = fmaxf(px1, tx1), lty = fmaxf(py1, ty1), rbx = fminf(px2, tx2), rby = fminf(py2, ty2);
             const float rw = rbx - ltx, rh = rby - lty;
             const float w = fmaxf(rw, 0.f), h = fmaxf(rh, 0.f);
@@ -273,6 +379,40 @@ __global__ void __launch_bounds__(256) iou_loss_kernel(const RegLossParams p) {
     }
     const double s = block_sum(acc, sh);
     if (threadIdx.x == 0) atomicAdd(p.loss_sum, s);
+}
+
+// element-wise box losses on explicit (pred, target) xyxy pairs: the stand-alone IoULoss / GIoULoss / DIoULoss / CIoULoss modules
+// (losses/iou_loss.py:105-283 before the reduction).  kind 0: -log(max(IoU, eps)) with IoU = overlap / max(union, 1e-6).
+__global__ void __launch_bounds__(256) box_loss_kernel(int kind, const float* __restrict__ pred, const float* __restrict__ target, int n, float eps,
+                                                       float* __restrict__ loss, float* __restrict__ grad) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 pv = reinterpret_cast<const float4*>(pred)[i], tv = reinterpret_cast<const float4*>(target)[i];
+        const Dual pr[4] = {dvar(pv.x, 0), dvar(pv.y, 1), dvar(pv.z, 2), dvar(pv.w, 3)};
+        const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
+        Dual ls;
+        if (kind == 0) {
+            const Dual t4[4] = {dc(tg[0]), dc(tg[1]), dc(tg[2]), dc(tg[3])};
+            const Dual w = dclamp0(dmin(pr[2], t4[2]) - dmax(pr[0], t4[0])), h = dclamp0(dmin(pr[3], t4[3]) - dmax(pr[1], t4[1]));
+            const Dual ov = w * h;
+            Dual un = (pr[2] - pr[0]) * (pr[3] - pr[1]) + (t4[2] - t4[0]) * (t4[3] - t4[1]) - ov;
+            if (un.v < 1e-6f) un = dc(1e-6f);
+            Dual iou = ov / un;
+            if (iou.v < eps) iou = dc(eps);
+            ls = dc(-logf(iou.v));
+            for (int k = 0; k < 4; ++k) ls.d[k] = -iou.d[k] / iou.v;
+        } else {
+            ls = iou_family_loss(kind, pr, tg, eps);
+        }
+        loss[i] = ls.v;
+        if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(ls.d[0], ls.d[1], ls.d[2], ls.d[3]);
+    }
+}
+cudaError_t box_loss_launch(int kind, const float* pred, const float* target, int n, float eps, float* loss, float* grad, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int grid = (n + 255) / 256;
+    if (grid > 4096) grid = 4096;
+    box_loss_kernel<<<grid, 256, 0, st>>>(kind, pred, target, n, eps, loss, grad);
+    return cudaGetLastError();
 }
 
 cudaError_t assign_targets_launch(const AssignParams& p, cudaStream_t st) {

@@ -17,7 +17,8 @@ OP_STEM0, OP_CONV, OP_GN_APPLY, OP_HEAD_FINAL = 0, 1, 2, 3
 INPUT_F32_NCHW, INPUT_U8_NHWC = 0, 1
 CONV_UMMA, CONV_SIMT = 0, 1
 DTYPE_BF16, DTYPE_FP16 = 0, 1
-CLS_SIGMOID, CLS_SOFTMAX = 0, 1
+CLS_SIGMOID, CLS_SOFTMAX, CLS_BCE, CLS_QFL = 0, 1, 2, 3
+REG_IOU, REG_GIOU, REG_DIOU, REG_CIOU, REG_SMOOTH_L1, REG_MSE = range(6)
 BBOX_SIGMOID, BBOX_EXP, BBOX_INDEPENDENT = 0, 1, 2
 ASSIGN_DIST, ASSIGN_LONGER, ASSIGN_SHORTER = 0, 1, 2
 
@@ -56,6 +57,12 @@ class Levels(C.Structure):
                 ('off', C.c_int32 * MAX_LEVELS), ('w', C.c_int32 * MAX_LEVELS), ('stride', C.c_int32 * MAX_LEVELS),
                 ('lo', C.c_float * MAX_LEVELS), ('hi', C.c_float * MAX_LEVELS),
                 ('glo', C.c_float * MAX_LEVELS), ('ghi', C.c_float * MAX_LEVELS)]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [('N', C.c_int32), ('P', C.c_int32), ('C', C.c_int32), ('cls_mode', C.c_int32), ('bbox_mode', C.c_int32), ('reg_loss', C.c_int32),
+                ('gamma', C.c_float), ('alpha', C.c_float), ('reg_eps', C.c_float), ('smooth_l1_beta', C.c_float),
+                ('cls_weight', C.c_float), ('reg_weight', C.c_float)]
 
 
 # training plan ops (include/lfd_b200.h, lfd_top)
@@ -107,7 +114,8 @@ SYMBOLS = {
     'lfd_nms_workspace_bytes': (C.c_size_t, [_i]),
     'lfd_nms': (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
     'lfd_assign_targets': (_i, [C.POINTER(Levels), _i, _i, _i, _i, _i, _i] + [_vp] * 8),
-    'lfd_detection_loss': (_i, [C.POINTER(Levels), _i, _i, _i, _i, _i, _f, _f, _f, _f, _f] + [_vp] * 9),
+    'lfd_detection_loss': (_i, [C.POINTER(Levels), C.POINTER(LossCfg)] + [_vp] * 10),
+    'lfd_box_loss': (_i, [_i, _vp, _vp, _i, _f, _vp, _vp, _vp]),
     'lfd_sigmoid_focal_loss_forward': (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     'lfd_sigmoid_focal_loss_backward': (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     'lfd_train_plan_create': (_i, [C.POINTER(Top), _i, _i64, C.POINTER(_vp)]),

@@ -232,13 +232,17 @@ class LFD(nn.Module):
         return cls_t, reg_t
 
     def get_loss(self, predict_outputs, annotation_batch, *args):
-        """reference :284-395 for FocalLoss | CrossEntropyLoss + IoULoss.
+        """reference :284-395: FocalLoss | CrossEntropyLoss | BCEWithLogitsLoss | QualityFocalLoss with IoULoss | GIoULoss | DIoULoss | CIoULoss
+        (union targets, sigmoid / exp decode) or SmoothL1Loss | MSELoss (independent targets).
         Returns dict(loss=Tensor (differentiable w.r.t. predict_outputs), loss_values=dict of floats)."""
         cls_pred, reg_pred = predict_outputs
         cname = type(self._classification_loss_func).__name__
         rname = type(self._regression_loss_func).__name__
-        if cname not in ('FocalLoss', 'CrossEntropyLoss') or rname != 'IoULoss':
-            raise NotImplementedError('native get_loss implements FocalLoss/CrossEntropyLoss + IoULoss (got %s + %s)' % (cname, rname))
+        cls_codes = dict(FocalLoss=nat.CLS_SIGMOID, CrossEntropyLoss=nat.CLS_SOFTMAX, BCEWithLogitsLoss=nat.CLS_BCE, QualityFocalLoss=nat.CLS_QFL)
+        reg_codes = dict(IoULoss=nat.REG_IOU, GIoULoss=nat.REG_GIOU, DIoULoss=nat.REG_DIOU, CIoULoss=nat.REG_CIOU, SmoothL1Loss=nat.REG_SMOOTH_L1,
+                         MSELoss=nat.REG_MSE)
+        if cname not in cls_codes or rname not in reg_codes:
+            raise NotImplementedError('native get_loss: unknown loss pair %s + %s' % (cname, rname))
         if self._enable_classification_weight or self._enable_regression_weight:
             raise NotImplementedError('classification / regression weighting is disabled in every shipped config and not implemented')
         device = cls_pred.device
@@ -264,14 +268,21 @@ class LFD(nn.Module):
         grad_reg = torch.empty_like(reg_c) if need_grad else None
         sums = torch.empty((2,), dtype=torch.float64, device=device)
         lf, rf = self._classification_loss_func, self._regression_loss_func
-        cls_mode = nat.CLS_SOFTMAX if cname == 'CrossEntropyLoss' else nat.CLS_SIGMOID
-        bbox_mode = nat.BBOX_SIGMOID if self._distance_to_bbox_mode == 'sigmoid' else nat.BBOX_EXP
+        lc = nat.LossCfg()
+        lc.N, lc.P, lc.C = N, P, self._num_classes
+        lc.cls_mode, lc.reg_loss = cls_codes[cname], reg_codes[rname]
+        if self._regression_loss_type == 'independent':
+            lc.bbox_mode = nat.BBOX_INDEPENDENT
+        else:
+            lc.bbox_mode = nat.BBOX_SIGMOID if self._distance_to_bbox_mode == 'sigmoid' else nat.BBOX_EXP
+        lc.gamma = float(getattr(lf, 'beta', 2.0)) if cname == 'QualityFocalLoss' else float(getattr(lf, 'gamma', 2.0))
+        lc.alpha = float(getattr(lf, 'alpha', 0.25))
+        lc.reg_eps = float(getattr(rf, 'eps', 1e-6))
+        lc.smooth_l1_beta = float(getattr(rf, 'beta', 1.0))
+        lc.cls_weight, lc.reg_weight = float(lf.loss_weight), float(rf.loss_weight)
         with torch.cuda.device(device):
-            nat.check(nat.lib().lfd_detection_loss(C.byref(lv), N, P, self._num_classes, cls_mode, bbox_mode,
-                                                   float(getattr(lf, 'gamma', 2.0)), float(getattr(lf, 'alpha', 0.25)),
-                                                   float(rf.eps), float(lf.loss_weight), float(rf.loss_weight),
-                                                   nat.ptr(cls_c), nat.ptr(reg_c), nat.ptr(reg_t), nat.ptr(label), nat.ptr(counters),
-                                                   nat.ptr(grad_cls), nat.ptr(grad_reg), nat.ptr(sums), nat.stream_ptr()))
+            nat.check(nat.lib().lfd_detection_loss(C.byref(lv), C.byref(lc), nat.ptr(cls_c), nat.ptr(reg_c), nat.ptr(cls_t), nat.ptr(reg_t), nat.ptr(label),
+                                                   nat.ptr(counters), nat.ptr(grad_cls), nat.ptr(grad_reg), nat.ptr(sums), nat.stream_ptr()))
         n_pos = counters[0].to(torch.float64)
         cls_loss = (lf.loss_weight * sums[0] / (n_pos + 1.0)).float()
         reg_loss = torch.where(n_pos > 0, rf.loss_weight * sums[1] / torch.clamp(n_pos, min=1.0), torch.zeros_like(sums[1])).float()

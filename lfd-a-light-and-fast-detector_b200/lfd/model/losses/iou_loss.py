@@ -1,15 +1,20 @@
 # -*- coding: utf-8 -*-
-"""IoULoss -- API of lfd/model/losses/iou_loss.py:11-123,286-321.  Inside LFD.get_loss the decode + IoU loss +
-gradient are one fused kernel (lfd_detection_loss); this module keeps the stand-alone call signature."""
+"""IoULoss / GIoULoss / DIoULoss / CIoULoss -- API of lfd/model/losses/iou_loss.py:105-430.  Inside LFD.get_loss the decode + box
+loss + gradient are one fused kernel (lfd_detection_loss); the stand-alone modules here evaluate the element-wise loss and its
+gradient w.r.t. the predicted boxes in liblfd_b200.so (lfd_box_loss).  CUDA only."""
 import torch
 import torch.nn as nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
-from .utils import weighted_loss
+from ... import _native as nat
+from .utils import weight_reduce_loss
 
-__all__ = ['IoULoss', 'bbox_overlaps']
+__all__ = ['IoULoss', 'GIoULoss', 'DIoULoss', 'CIoULoss', 'bbox_overlaps']
 
 
 def bbox_overlaps(bboxes1, bboxes2, mode='iou', is_aligned=False, eps=1e-6):
+    """lfd/model/losses/iou_loss.py:11-102 (plain tensor arithmetic: an API helper, not on the hot path)."""
     assert mode in ['iou', 'iof']
     rows, cols = bboxes1.size(0), bboxes2.size(0)
     if is_aligned:
@@ -24,15 +29,35 @@ def bbox_overlaps(bboxes1, bboxes2, mode='iou', is_aligned=False, eps=1e-6):
     return overlap / torch.max(union, union.new_tensor([eps]))
 
 
-@weighted_loss
-def iou_loss(pred, target, eps=1e-6):
-    return -bbox_overlaps(pred, target, is_aligned=True).clamp(min=eps).log()
+class _BoxLossFunction(Function):
+    """element-wise loss [n] of box pairs [n,4] with the gradient w.r.t. the predictions precomputed by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, pred, target, kind, eps):
+        if not pred.is_cuda:
+            raise RuntimeError('lfd_b200 box losses are CUDA only (no CPU fallback)')
+        p = pred.detach().float().contiguous()
+        t = target.detach().float().contiguous()
+        n = p.shape[0]
+        loss = torch.empty((n,), dtype=torch.float32, device=p.device)
+        grad = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            nat.check(nat.lib().lfd_box_loss(int(kind), nat.ptr(p), nat.ptr(t), n, float(eps), nat.ptr(loss), nat.ptr(grad), nat.stream_ptr()))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss):
+        (grad,) = ctx.saved_tensors
+        return grad * d_loss[:, None], None, None, None
 
 
-class IoULoss(nn.Module):
+class _BoxLoss(nn.Module):
+    KIND = nat.REG_IOU
 
     def __init__(self, eps=1e-6, reduction='mean', loss_weight=1.0):
-        super(IoULoss, self).__init__()
+        super(_BoxLoss, self).__init__()
         self.eps, self.reduction, self.loss_weight = eps, reduction, loss_weight
 
     def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
@@ -43,4 +68,21 @@ class IoULoss(nn.Module):
         if weight is not None and weight.dim() > 1:
             assert weight.shape == pred.shape
             weight = weight.mean(-1)
-        return self.loss_weight * iou_loss(pred, target, weight, eps=self.eps, reduction=reduction, avg_factor=avg_factor, **kwargs)
+        loss = _BoxLossFunction.apply(pred, target, self.KIND, self.eps)
+        return self.loss_weight * weight_reduce_loss(loss, weight, reduction, avg_factor)
+
+
+class IoULoss(_BoxLoss):       # -log(max(IoU, eps)), reference :105-123,286-321
+    KIND = nat.REG_IOU
+
+
+class GIoULoss(_BoxLoss):      # reference :125-170,324-357
+    KIND = nat.REG_GIOU
+
+
+class DIoULoss(_BoxLoss):      # reference :173-224,360-394
+    KIND = nat.REG_DIOU
+
+
+class CIoULoss(_BoxLoss):      # reference :227-283,397-430
+    KIND = nat.REG_CIOU

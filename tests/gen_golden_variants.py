@@ -92,6 +92,23 @@ def main():
                               results=dict(thr=thr, iou=iou, rows=rows))
         print('%-28s loss %s  |grad| %.3e / %.3e  detections %s' % (v['name'], ld['loss_values'], float(cls_pred.grad.norm()), float(reg_pred.grad.norm()),
                                                                      [len(r) for r in rows]))
+    # element-wise box losses of the stand-alone modules (reduction='none') on random box pairs, with autograd gradients
+    g = torch.Generator().manual_seed(77)
+    n = 300
+    c = torch.rand(n, 2, generator=g) * 200 + 20
+    wh = torch.rand(n, 2, generator=g) * 80 + 4
+    target = torch.cat([c - wh / 2, c + wh / 2], 1)
+    pred = target + torch.randn(n, 4, generator=g) * 12
+    pred[:40] = target[:40] + 300          # disjoint pairs
+    pred[40:60, 2:] = pred[40:60, :2] + wh[40:60] * 0.5
+    box = dict(pred=pred.clone(), target=target.clone())
+    for name in ('IoULoss', 'GIoULoss', 'DIoULoss', 'CIoULoss'):
+        pr = pred.clone().requires_grad_(True)
+        mod = getattr(R['losses'], name)(eps=1e-6, reduction='mean', loss_weight=1.0)
+        el = mod(pr, target, reduction_override='none')
+        el.sum().backward()
+        box[name] = dict(loss=el.detach().clone(), grad=pr.grad.clone())
+    out['box_pairs'] = box
     torch.save(out, os.path.join(HERE, 'golden', 'loss_variants.pt'))
 
 

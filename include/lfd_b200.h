@@ -73,7 +73,8 @@ enum { LFD_DTYPE_BF16 = 0, LFD_DTYPE_FP16 = 1 };
  *              gn_groups > 0: also accumulates sum / sum-of-squares of the stored output per (image, group)
  *              into double[N][gn_groups][2] at stats_off (group size must be 8).
  *   GN_APPLY   y = relu(gamma * (x - mean) * rstd + beta) from the statistics at stats_off, bf16 -> bf16.
- *   HEAD_FINAL GN_APPLY (as above, rounded to bf16) followed by the final 1x1 convs of one level: outputs
+ *   HEAD_FINAL GN_APPLY (as above, rounded to bf16; gn_groups = 0: no normalisation, the input is an already activated tensor --
+ *              heads built with norm_cfg=None) followed by the final 1x1 convs of one level: outputs
  *              [0, n_cls) -> cls[n][point_off + pixel][.] and [n_cls, n_cls + n_reg) -> reg[n][point_off + pixel][.];
  *              weight = float[n_cls + n_reg][Cin]; scale/shift = per-output scale and (scale * bias).
  */

@@ -132,6 +132,7 @@ static int check_op(const lfd_op& o) {
             break;
         case LFD_OP_GN_APPLY:
         case LFD_OP_HEAD_FINAL:
+            if (o.kind == LFD_OP_HEAD_FINAL && o.gn_groups == 0) break;   // head without norm layers: the input is already activated
             if (o.Cin != o.gn_groups * 8) return fail(LFD_ERR_UNSUPPORTED, "GroupNorm needs groups of 8 channels (C=%d groups=%d)", o.Cin, o.gn_groups);
             break;
         default:
@@ -216,7 +217,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
         case LFD_OP_HEAD_FINAL: {
             HeadFinalParams p;
             p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off);
-            p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
+            p.stats = o.gn_groups ? reinterpret_cast<const double*>(ws + o.stats_off) : nullptr; p.gamma = o.gamma; p.beta = o.beta;
             p.w = reinterpret_cast<const float*>(o.weight); p.scale = o.scale; p.shift = o.shift;
             p.cls = o.n_cls ? cls : nullptr; p.reg = o.n_reg ? reg : nullptr;
             p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.n_out = o.n_cls + o.n_reg; p.n_cls = o.n_cls;

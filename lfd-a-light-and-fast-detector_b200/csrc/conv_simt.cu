@@ -197,14 +197,15 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
     LFD_TL_BEGIN(p.tl);
     const int n = blockIdx.y;
     for (int i = threadIdx.x; i < p.n_out * p.C; i += kHfThreads) wsm[i] = p.w[i];
-    if (threadIdx.x < p.groups)
+    const bool gn = p.groups > 0;      // groups == 0: the tower has no norm layers, the input is the already activated tensor
+    if (gn && threadIdx.x < p.groups)
         gn_mean_rstd(p.stats, n, threadIdx.x, p.groups, (double)p.HW * 8.0, p.eps, &s_mean[threadIdx.x], &s_rstd[threadIdx.x]);
     __syncthreads();
     const int sl = threadIdx.x & 7;                       // channel slice: channels [16 sl, 16 sl + 16)
     float ga[16], be[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { ga[j] = p.gamma[sl * 16 + j]; be[j] = p.beta[sl * 16 + j]; }
-    const float m0 = s_mean[2 * sl], r0 = s_rstd[2 * sl], m1 = s_mean[2 * sl + 1], r1 = s_rstd[2 * sl + 1];
+    for (int j = 0; j < 16; ++j) { ga[j] = gn ? p.gamma[sl * 16 + j] : 1.f; be[j] = gn ? p.beta[sl * 16 + j] : 0.f; }
+    const float m0 = gn ? s_mean[2 * sl] : 0.f, r0 = gn ? s_rstd[2 * sl] : 1.f, m1 = gn ? s_mean[2 * sl + 1] : 0.f, r1 = gn ? s_rstd[2 * sl + 1] : 1.f;
     const int pix0 = blockIdx.x * kHfPixPerBlock + (threadIdx.x >> 3);
     float a[kHfPpt][16];
 #pragma unroll
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
 }
 
 cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
-    if (p.C != kHfMaxC || p.groups != 16) return cudaErrorInvalidValue;   // 128 channels, 16 groups of 8 (every shipped head)
+    if (p.C != kHfMaxC || (p.groups != 16 && p.groups != 0)) return cudaErrorInvalidValue;   // 128 channels; 16 groups of 8, or no norm
     const size_t smem = ((size_t)p.n_out * p.C + 64) * sizeof(float);
     static bool attr[kMaxDevices] = {};   // per-device function attribute
     int dev = 0;

@@ -263,8 +263,8 @@ class InferencePlan(object):
         taps = list(bb._out_indices)
         if len(taps) != head._num_heads:
             raise ValueError('backbone taps (%d) and head levels (%d) differ' % (len(taps), head._num_heads))
-        if not isinstance(make_norm_probe(head), nn.GroupNorm):
-            raise NotImplementedError('the B200 head kernels implement the GroupNorm towers of the shipped configs')
+        if make_norm_probe(head) is not None and not isinstance(make_norm_probe(head), nn.GroupNorm):
+            raise NotImplementedError('the B200 head kernels implement GroupNorm towers and towers without norm layers (the shipped configs)')
         # point offsets need every level size up front: strides are fixed by the stage index
         sizes, hh, ww = {}, h, w
         for si, stage in enumerate(bb.stages()):
@@ -330,12 +330,22 @@ class InferencePlan(object):
         scale_l = float(head._scales[l]._scale.detach()) if head.uses_scale else 1.0
 
         def run_tower(tower, tag):
+            """-> (last stored tensor, GN statistics slot or None, GN module or None).  With GroupNorm the last conv's normalisation + ReLU is
+            applied inside HEAD_FINAL; without norm layers (TrafficLight configs, lfd_head.py:47-49 norm_cfg=None) every tower conv is a plain
+            conv + bias + ReLU layer and HEAD_FINAL reads the activated tensor."""
             x = nk
             for ti, (tconv, tnorm) in enumerate(tower):
-                if tconv.kernel_size != (1, 1):
-                    raise NotImplementedError('head towers with conv_kernel_size=3 are outside the implemented hot path')
+                if tconv.kernel_size not in ((1, 1), (3, 3)) or tconv.stride != (1, 1):
+                    raise NotImplementedError('head towers use 1x1 or 3x3 stride-1 convs (lfd_head.py:47-49)')
+                if tnorm is None:
+                    act = 'h%d%s_act%d' % (l, tag, ti)
+                    self._emit_conv(tconv, None, True, x, act, fh, fw, cache=cache)
+                    x = act
+                    if ti == len(tower) - 1:
+                        return act, None, None
+                    continue
                 if not isinstance(tnorm, nn.GroupNorm) or tnorm.num_channels != tnorm.num_groups * 8:
-                    raise NotImplementedError('head towers need GroupNorm with 8 channels per group')
+                    raise NotImplementedError('head towers need GroupNorm with 8 channels per group (or no norm at all)')
                 raw = 'h%d%s_raw%d' % (l, tag, ti)
                 self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
                 stats_id = self._ops[-1]['stats']
@@ -357,13 +367,14 @@ class InferencePlan(object):
                 b = fc.bias.detach().float().cpu() if fc.bias is not None else torch.zeros(fc.out_channels)
                 scs.append(torch.full((fc.out_channels,), sc))
                 shs.append(b * sc)
-            self._push(dict(kind=nat.OP_HEAD_FINAL, H=fh, W=fw, Cin=ws[0].shape[1], Ho=fh, Wo=fw, Cout=n_cls + n_reg,
-                            gn_groups=tnorm.num_groups, inp=raw, stats=stats_id, n_cls=n_cls, n_reg=n_reg,
-                            point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
-                            scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
-                            gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight),
-                            beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias),
-                            modules=(tnorm, [c for c, _ in convs], [sc for _, sc in convs])))
+            op = dict(kind=nat.OP_HEAD_FINAL, H=fh, W=fw, Cin=ws[0].shape[1], Ho=fh, Wo=fw, Cout=n_cls + n_reg,
+                      gn_groups=tnorm.num_groups if tnorm is not None else 0, inp=raw, stats=stats_id, n_cls=n_cls, n_reg=n_reg,
+                      point_off=point_off, w_f32=self._add_f32(torch.cat(ws, 0)),
+                      scale=self._add_f32(torch.cat(scs)), shift=self._add_f32(torch.cat(shs)),
+                      modules=(tnorm, [c for c, _ in convs], [sc for _, sc in convs]))
+            if tnorm is not None:
+                op.update(gamma=self._cached_f32(cache, ('g', id(tnorm)), tnorm.weight), beta=self._cached_f32(cache, ('b', id(tnorm)), tnorm.bias))
+            self._push(op)
 
         if cls_tower is reg_tower:
             raw, sid, tn = run_tower(cls_tower, 'm')

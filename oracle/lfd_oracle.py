@@ -52,12 +52,13 @@ GN_EPS = 1e-5  # nn.GroupNorm default
 # ----------------------------------------------------------------------------------------------
 # model configurations (the `prepare_model()` blocks of the shipped config scripts)
 # ----------------------------------------------------------------------------------------------
-def _cfg(stem_mode, stem_channels, arch, channels, out_indices, num_classes, ranges, cls_loss, merge, assign):
+def _cfg(stem_mode, stem_channels, arch, channels, out_indices, num_classes, ranges, cls_loss, merge, assign, block_mode='faster', head_k=1,
+         head_norm=True):
     return dict(
-        backbone=dict(block_mode='faster', stem_mode=stem_mode, input_channels=3, stem_channels=stem_channels,
+        backbone=dict(block_mode=block_mode, stem_mode=stem_mode, input_channels=3, stem_channels=stem_channels,
                       body_architecture=list(arch), body_channels=list(channels), out_indices=tuple(out_indices)),
         neck=dict(num_neck_channels=128),
-        head=dict(num_classes=num_classes, num_head_channels=128, num_conv_layers=2, gn_groups=16,
+        head=dict(num_classes=num_classes, num_head_channels=128, num_conv_layers=2, gn_groups=16, conv_kernel_size=head_k, norm=head_norm,
                   share_head_flag=True, merge_path_flag=merge, classification_loss_type=cls_loss,
                   regression_loss_type='IoULoss'),
         lfd=dict(num_classes=num_classes, regression_ranges=tuple(ranges), gray_range_factors=(0.9, 1.1),
@@ -67,6 +68,7 @@ def _cfg(stem_mode, stem_channels, arch, channels, out_indices, num_classes, ran
 
 _WF_RANGES = ((4, 20), (20, 40), (40, 80), (80, 160), (160, 320))
 _TT_RANGES = ((4, 32), (32, 64), (64, 128), (128, 256))
+_TL_RANGES = ((4, 32), (32, 64), (64, 128), (128, 256), (256, 512))
 CONFIGS = {
     # WIDERFACE_train/WIDERFACE_LFD_{XS,S,M,L}.py:76-158
     'WIDERFACE_XS': _cfg('faster', 32, [4, 2, 2, 3], [64, 64, 64, 64], ((0, 3), (1, 1), (2, 1), (3, 0), (3, 2)), 1, _WF_RANGES, 'FocalLoss', True, 'dist'),
@@ -76,6 +78,14 @@ CONFIGS = {
     # TT100K_train/TT100K_LFD_{L,S}.py
     'TT100K_L': _cfg('fast', 64, [5, 3, 2, 2], [64, 64, 128, 128], ((0, 4), (1, 2), (2, 1), (3, 1)), 45, _TT_RANGES, 'CrossEntropyLoss', False, 'longer'),
     'TT100K_S': _cfg('faster', 64, [4, 2, 1, 1], [64, 64, 64, 128], ((0, 3), (1, 1), (2, 0), (3, 0)), 45, _TT_RANGES, 'CrossEntropyLoss', False, 'longer'),
+    # TrafficLight_train/TL_LFD_L.py:95-150: the head has NO norm layers (conv + bias + ReLU towers)
+    'TL_L': _cfg('fast', 64, [5, 3, 2, 2, 2], [64, 64, 128, 128, 128], ((0, 4), (1, 2), (2, 1), (3, 1), (4, 1)), 1, _TL_RANGES, 'FocalLoss', True, 'dist',
+                 head_norm=False),
+    # not shipped: small nets that exercise the remaining block / stem modes (lfd_resnet.py:21-93 FastBlock, :157-215 FastestBlock,
+    # 'fastest' stem :420-439) and conv_kernel_size=3 head towers (lfd_head.py:47-49)
+    'TEST_FAST': _cfg('fast', 64, [2, 1, 1], [64, 64, 128], ((0, 1), (1, 0), (2, 0)), 2, ((4, 32), (32, 64), (64, 128)), 'FocalLoss', True, 'dist',
+                      block_mode='fast', head_k=3),
+    'TEST_FASTEST': _cfg('fastest', 32, [2, 2], [64, 64], ((0, 1), (1, 1)), 1, ((8, 64), (64, 128)), 'FocalLoss', False, 'dist', block_mode='fastest'),
 }
 
 
@@ -209,13 +219,18 @@ class _Net(object):
 
     def tower(self, x, prefix):
         hd = self.cfg['head']
+        k = hd.get('conv_kernel_size', 1)
+        step = 3 if hd.get('norm', True) else 2          # conv, [norm], activation (lfd_head.py:85-106)
         for i in range(hd['num_conv_layers']):
-            y, b = self.conv(x, prefix + '.%d' % (3 * i), 1, 0)
-            assert b is None  # bias=False when a norm follows (lfd_head.py:98)
-            x = self.gn_relu(y, prefix + '.%d' % (3 * i + 1), hd['gn_groups'])
+            y, b = self.conv(x, prefix + '.%d' % (step * i), 1, k // 2)
+            if hd.get('norm', True):
+                assert b is None  # bias=False when a norm follows (lfd_head.py:98)
+                x = self.gn_relu(y, prefix + '.%d' % (step * i + 1), hd['gn_groups'])
+            else:                 # no norm: conv + bias + ReLU; the CUDA path adds the bias as a bf16 row on the tensor core
+                x = self.r(F.relu(y + (self.r(b) if self.emu else b)[None, :, None, None]))
             if self.trace is not None:
-                self.trace[prefix + '.%d' % (3 * i) + ':raw'] = self.r(y)
-                self.trace[prefix + '.%d' % (3 * i) + ':act'] = x
+                self.trace[prefix + '.%d' % (step * i) + ':raw'] = self.r(y)
+                self.trace[prefix + '.%d' % (step * i) + ':act'] = x
         return x
 
     def head_level(self, x, l):
@@ -228,7 +243,7 @@ class _Net(object):
         else:  # :108-135, towers live inside the cls/reg paths, final conv at index 3*nl
             cls_in = self.tower(x, p + 'classification_path')
             reg_in = self.tower(x, p + 'regression_path')
-            last = 3 * nl
+            last = (3 if hd.get('norm', True) else 2) * nl
         ck, rk = p + 'classification_path.%d' % last, p + 'regression_path.%d' % last
         cls = F.conv2d(cls_in, self.w(ck + '.weight'), self.sd[ck + '.bias'])
         reg = F.conv2d(reg_in, self.w(rk + '.weight'), self.sd[rk + '.bias'])

@@ -85,7 +85,8 @@ def build_ref_model(R, cfg):
                            activation_cfg=dict(type='ReLU', inplace=True))
     head = R['LFDHead'](num_classes=hd['num_classes'], num_heads=len(neck.num_output_strides_list), num_input_channels=128,
                         num_head_channels=128, num_conv_layers=2, activation_cfg=dict(type='ReLU', inplace=True),
-                        norm_cfg=dict(type='GroupNorm', num_groups=16), share_head_flag=hd['share_head_flag'],
+                        norm_cfg=dict(type='GroupNorm', num_groups=16) if hd.get('norm', True) else None,
+                   conv_kernel_size=hd.get('conv_kernel_size', 1), share_head_flag=hd['share_head_flag'],
                         merge_path_flag=hd['merge_path_flag'], classification_loss_type=type(cls_loss).__name__,
                         regression_loss_type=type(reg_loss).__name__)
     model = R['LFD'](backbone=backbone, neck=neck, head=head, num_classes=lc['num_classes'], regression_ranges=lc['regression_ranges'],
@@ -125,6 +126,42 @@ def sizes_for(cfg, h, w):
     return out
 
 
+def forward_case(R, name, n, h, w, cls_bias, out_dir):
+    """One forward / results / loss golden of the reference model `name` on the synthetic weights and input."""
+    cfg = orc.CONFIGS[name]
+    model = build_ref_model(R, cfg)
+    sd = synth.synth_state_dict(model.state_dict(), seed=666, cls_bias=cls_bias)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    x = synth.synth_input(n, h, w)
+    with torch.no_grad():
+        cls, reg = model(x)
+    sizes = [model.head_indexes_to_feature_map_sizes[i] for i in range(len(model.head_indexes_to_feature_map_sizes))]
+    assert sizes == sizes_for(cfg, h, w), (sizes, sizes_for(cfg, h, w))
+    meta = [dict(resized_height=h, resized_width=w, resize_scale=1.0) for _ in range(n)]
+    meta[-1]['resize_scale'] = 0.75
+    results = {}
+    probs = cls.sigmoid() if cfg['head']['classification_loss_type'] == 'FocalLoss' else cls.softmax(-1)[..., :-1]
+    is_focal = cfg['head']['classification_loss_type'] == 'FocalLoss'
+    for (thr, iou) in (((0.5, 0.3), (0.2, 0.4), (0.05, 0.4)) if is_focal else ((0.1, 0.3), (0.04, 0.4))):
+        model._classification_threshold = thr
+        model._nms_cfg = dict(type='nms', iou_thr=iou)
+        with torch.no_grad():
+            res = model.get_results((cls, reg), meta)
+        results[(thr, iou)] = [torch.tensor(r, dtype=torch.float32).reshape(-1, 6) for r in res]
+        print('  %s thr=%.3f iou=%.1f: pass=%d kept=%s' % (name, thr, iou, int((probs > thr).sum()), [len(r) for r in res]))
+    # loss + gradients w.r.t. the outputs (annotations scaled to this small crop)
+    ann = synth.synth_annotations(n, h, w, cfg['lfd']['num_classes'], seed=11, max_boxes=6)
+    cls_g, reg_g = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ld = model.get_loss((cls_g, reg_g), ann)
+    ld['loss'].backward()
+    torch.save(dict(cfg=name, N=n, H=h, W=w, cls_bias=cls_bias, seed=666, keys=[(k, tuple(v.shape)) for k, v in sd.items()],
+                    checksum=synth.state_checksum(sd), sizes=sizes, cls=cls, reg=reg, meta=meta,
+                    results=results, ann=ann, loss_values=ld['loss_values'], grad_cls=cls_g.grad.clone(), grad_reg=reg_g.grad.clone()),
+               os.path.join(out_dir, 'forward_%s.pt' % name))
+    print('forward %s: P=%d cls %s loss %s' % (name, cls.shape[1], tuple(cls.shape), ld['loss_values']))
+
+
 def main():
     R = import_reference()
     out_dir = os.path.join(HERE, 'golden')
@@ -149,38 +186,7 @@ def main():
     print('known answers: doc keep', keep.tolist(), 'random keep', len(keep_rnd))
 
     for name, (n, h, w, cls_bias) in FORWARD_CASES.items():
-        cfg = orc.CONFIGS[name]
-        model = build_ref_model(R, cfg)
-        sd = synth.synth_state_dict(model.state_dict(), seed=666, cls_bias=cls_bias)
-        model.load_state_dict(sd, strict=True)
-        model.eval()
-        x = synth.synth_input(n, h, w)
-        with torch.no_grad():
-            cls, reg = model(x)
-        sizes = [model.head_indexes_to_feature_map_sizes[i] for i in range(len(model.head_indexes_to_feature_map_sizes))]
-        assert sizes == sizes_for(cfg, h, w), (sizes, sizes_for(cfg, h, w))
-        meta = [dict(resized_height=h, resized_width=w, resize_scale=1.0) for _ in range(n)]
-        meta[-1]['resize_scale'] = 0.75
-        results = {}
-        probs = cls.sigmoid() if cfg['head']['classification_loss_type'] == 'FocalLoss' else cls.softmax(-1)[..., :-1]
-        is_focal = cfg['head']['classification_loss_type'] == 'FocalLoss'
-        for (thr, iou) in (((0.5, 0.3), (0.2, 0.4), (0.05, 0.4)) if is_focal else ((0.1, 0.3), (0.04, 0.4))):
-            model._classification_threshold = thr
-            model._nms_cfg = dict(type='nms', iou_thr=iou)
-            with torch.no_grad():
-                res = model.get_results((cls, reg), meta)
-            results[(thr, iou)] = [torch.tensor(r, dtype=torch.float32).reshape(-1, 6) for r in res]
-            print('  %s thr=%.3f iou=%.1f: pass=%d kept=%s' % (name, thr, iou, int((probs > thr).sum()), [len(r) for r in res]))
-        # loss + gradients w.r.t. the outputs (annotations scaled to this small crop)
-        ann = synth.synth_annotations(n, h, w, cfg['lfd']['num_classes'], seed=11, max_boxes=6)
-        cls_g, reg_g = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
-        ld = model.get_loss((cls_g, reg_g), ann)
-        ld['loss'].backward()
-        torch.save(dict(cfg=name, N=n, H=h, W=w, cls_bias=cls_bias, seed=666, keys=[(k, tuple(v.shape)) for k, v in sd.items()],
-                        checksum=synth.state_checksum(sd), sizes=sizes, cls=cls, reg=reg, meta=meta,
-                        results=results, ann=ann, loss_values=ld['loss_values'], grad_cls=cls_g.grad.clone(), grad_reg=reg_g.grad.clone()),
-                   os.path.join(out_dir, 'forward_%s.pt' % name))
-        print('forward %s: P=%d cls %s loss %s' % (name, cls.shape[1], tuple(cls.shape), ld['loss_values']))
+        forward_case(R, name, n, h, w, cls_bias, out_dir)
 
     for name, (h, w) in ASSIGN_CASES.items():
         cfg = orc.CONFIGS[name]

@@ -52,8 +52,16 @@ def make_loss(R, name):
     return getattr(L, name)(eps=1e-6, reduction='mean', loss_weight=1.0)
 
 
+# reference forward / results / loss goldens of the configurations outside the BASELINE list: the shipped TrafficLight model (head without
+# norm layers) and two small nets covering FastBlock / FastestBlock, the 'fastest' stem and 3x3 head towers
+EXTRA_FORWARD_CASES = {'TL_L': (1, 136, 200, -1.0), 'TEST_FAST': (2, 120, 168, -1.0), 'TEST_FASTEST': (2, 152, 200, -1.0)}
+
+
 def main():
     R = gg.import_reference()
+    torch.set_num_threads(8)
+    for name, (n, h, w, cls_bias) in EXTRA_FORWARD_CASES.items():
+        gg.forward_case(R, name, n, h, w, cls_bias, os.path.join(HERE, 'golden'))
     out = {}
     H, W, N = 256, 320, 2
     for v in VARIANTS:

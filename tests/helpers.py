@@ -36,7 +36,8 @@ def build_model(cfg_name):
                       activation_cfg=dict(type='ReLU', inplace=True))
     head = LFDHead(num_classes=hd['num_classes'], num_heads=len(neck.num_output_strides_list), num_input_channels=128,
                    num_head_channels=128, num_conv_layers=2, activation_cfg=dict(type='ReLU', inplace=True),
-                   norm_cfg=dict(type='GroupNorm', num_groups=16), share_head_flag=hd['share_head_flag'],
+                   norm_cfg=dict(type='GroupNorm', num_groups=16) if hd.get('norm', True) else None,
+                   conv_kernel_size=hd.get('conv_kernel_size', 1), share_head_flag=hd['share_head_flag'],
                    merge_path_flag=hd['merge_path_flag'], classification_loss_type=type(cls_loss).__name__,
                    regression_loss_type=type(reg_loss).__name__)
     return LFD(backbone=backbone, neck=neck, head=head, num_classes=lc['num_classes'], regression_ranges=lc['regression_ranges'],

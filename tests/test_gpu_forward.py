@@ -11,7 +11,7 @@ from lfd import _native as nat
 from oracle import lfd_oracle as orc
 
 pytestmark = pytest.mark.gpu
-FWD = ['WIDERFACE_XS', 'WIDERFACE_S', 'WIDERFACE_L', 'TT100K_L']
+FWD = ['WIDERFACE_XS', 'WIDERFACE_S', 'WIDERFACE_L', 'TT100K_L', 'TL_L', 'TEST_FAST', 'TEST_FASTEST']
 # Parity protocol (DESIGN.md "Parity"):
 #  Gate A/B  every fused layer, fed the tensors the CUDA path actually produced upstream ("teacher forced"), equals the
 #            fp32 CPU evaluation of that layer on the same bf16 operands to <= 1 bf16 ulp; the fp32 head outputs to 1e-4.

@@ -10,7 +10,7 @@ from helpers import load_golden, build_model, rel_err
 from oracle import lfd_oracle as orc
 from oracle import build_ref
 
-FWD = ['WIDERFACE_XS', 'WIDERFACE_S', 'WIDERFACE_L', 'TT100K_L']
+FWD = ['WIDERFACE_XS', 'WIDERFACE_S', 'WIDERFACE_L', 'TT100K_L', 'TL_L', 'TEST_FAST', 'TEST_FASTEST']
 
 
 @pytest.mark.parametrize('name', FWD)

@@ -242,7 +242,9 @@ int lfd_sigmoid_focal_loss_backward(const float* logits, const int64_t* targets,
  *   NORM_BWD_REDUCE  dy       y       z       fsums    bsums      -        -       -        gamma, beta, -, -, running_mean, running_var (frozen)
  *   NORM_BWD_APPLY   dy       y       z       fsums    bsums      dz       dz_up   dres     gamma, beta, dgamma, dbeta, running_mean, running_var (frozen)
  *   WGRAD            x        dz      -       -        -          dstage   -       -        -
- *   WGRAD_STEM       -        dz      -       -        -          dstage   -       -        -          (x = the run-time input image)
+ *   WGRAD_STEM       x27      dz      -       -        -          dstage   -       -        -          (x = the run-time input image; x27 >= 0: scratch
+ *                                                                                                        bf16 [N][Ho][Wo][32] for the im2col + tensor-core path, dstage then has 32 rows;
+ *                                                                                                        x27 = -1 or impl = SIMT: the SIMT kernel, 27 rows)
  *   UNPACK           -        -       -       -        -          -        -       -        table (lfd_unpack_desc[n_desc], device)
  *   ZERO             begin    bytes   -       -        -          -        -       -        -          (cudaMemsetAsync of a workspace region)
  *

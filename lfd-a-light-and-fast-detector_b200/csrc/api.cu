@@ -759,7 +759,16 @@ static int launch_top(const PlannedTop& pt, const void* input, int fmt, uint8_t*
         case LFD_TOP_WGRAD_STEM: {
             WgradGeom g = {t.N, t.H, t.W, t.Cin, t.Ho, t.Wo, t.Cout, t.ksize, t.stride};
             if (!input || t.off[1] < 0 || t.off[5] < 0) return fail(LFD_ERR_INVALID, "wgrad_stem: missing tensor");
-            CUDA_TRY(wgrad_stem_launch(g, input, fmt, at<const __nv_bfloat16>(ws, t.off[1]), at<float>(ws, t.off[5]), sms, st));
+            if (t.off[0] >= 0 && t.impl == LFD_WGRAD_UMMA) {
+                // tensor-core path: im2col into the scratch tensor X27 [N][Ho][Wo][32] at off[0], then the 1x1 wgrad (32 -> Cout) over it;
+                // the staging at off[5] must hold 32 rows of Cout floats (rows 27..31 stay zero)
+                __nv_bfloat16* x27 = at<__nv_bfloat16>(ws, t.off[0]);
+                CUDA_TRY(stem_im2col_launch(g, input, fmt, x27, sms, st));
+                WgradGeom g1 = {t.N, t.Ho, t.Wo, 32, t.Ho, t.Wo, t.Cout, 1, 1};
+                CUDA_TRY(wgrad_umma_launch(g1, x27, at<const __nv_bfloat16>(ws, t.off[1]), at<float>(ws, t.off[5]), sms, st));
+            } else {
+                CUDA_TRY(wgrad_stem_launch(g, input, fmt, at<const __nv_bfloat16>(ws, t.off[1]), at<float>(ws, t.off[5]), sms, st));
+            }
             break;
         }
         default:

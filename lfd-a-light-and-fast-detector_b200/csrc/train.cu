@@ -616,6 +616,44 @@ cudaError_t wgrad_stem_launch(const WgradGeom& g, const void* image, int input_f
     return cudaGetLastError();
 }
 
+// im2col of the 3-channel stem conv for its weight gradient: X27[n][oy][ox][q] with q = (kh*3 + kw)*3 + ci (q >= 27: zero) as bf16, the
+// image normalised + rounded like the forward does (R0).  The weight gradient of the stem conv is then the weight gradient of a 1x1 conv
+// with 32 input channels over X27, i.e. one launch of the tensor-core wgrad kernel; its staging rows [q][co] ARE the [tap][ci][co] layout.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(WgradGeom g, const void* __restrict__ image, int input_format, __nv_bfloat16* __restrict__ x27) {
+    const size_t total = (size_t)g.N * g.Ho * g.Wo * 4;          // one thread per (output pixel, 8-value chunk)
+    const size_t plane = (size_t)g.H * g.W;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int chunk = (int)(i & 3);
+        const size_t pix = i >> 2;
+        const int ox = (int)(pix % g.Wo), oy = (int)((pix / g.Wo) % g.Ho), n = (int)(pix / ((size_t)g.Wo * g.Ho));
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int q = chunk * 8 + j;
+            float f = 0.f;
+            if (q < 27) {
+                const int ci = q % 3, t = q / 3;
+                const int y = 2 * oy + t / 3 - 1, x = 2 * ox + t % 3 - 1;
+                if ((unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W) {
+                    if (input_format == 1) f = ((float)reinterpret_cast<const uint8_t*>(image)[((size_t)n * plane + (size_t)y * g.W + x) * 3 + ci] - 127.5f) * (1.0f / 127.5f);
+                    else f = reinterpret_cast<const float*>(image)[((size_t)n * 3 + ci) * plane + (size_t)y * g.W + x];
+                }
+            }
+            v[j] = f;
+        }
+        reinterpret_cast<uint4*>(x27)[i] = pack8f(v);
+    }
+}
+
+cudaError_t stem_im2col_launch(const WgradGeom& g, const void* image, int input_format, __nv_bfloat16* x27, int num_sms, cudaStream_t st) {
+    if (g.Cin != 3 || g.ksize != 3 || g.stride != 2) return cudaErrorInvalidValue;
+    const size_t total = (size_t)g.N * g.Ho * g.Wo * 4;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
+    stem_im2col_kernel<<<(int)blocks, 256, 0, st>>>(g, image, input_format, x27);
+    return cudaGetLastError();
+}
+
 // SIMT cross-check of the tensor-core wgrad: one thread per (tap, ci, co), loop over one image's pixels (grid.y = image)
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradGeom g, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                                          float* __restrict__ dstage) {

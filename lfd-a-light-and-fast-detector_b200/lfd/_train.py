@@ -164,7 +164,8 @@ class TrainPlan(object):
         """fp32 staging [k*k][Cin][Cout] of a conv's weight gradient (shared by every use of the parameter)."""
         key = id(conv.weight)
         if key not in self._gstage:
-            name = self._alloc('g%d' % len(self._gstage), conv.weight.numel() * 4)
+            # (the stem conv's staging has 32 rows: its tensor-core path pads the 27 (tap, ci) rows to a 32-channel 1x1 problem)
+            name = self._alloc('g%d' % len(self._gstage), (conv.weight.numel() if conv.in_channels != 3 else 32 * conv.out_channels) * 4)
             self._gstage[key] = name
             self._zero_bwd.append(name)
             kk = conv.kernel_size[0] ** 2
@@ -339,7 +340,8 @@ class TrainPlan(object):
         conv, geo, x = L['conv'], L['geo'], L['x']
         gs = self._gstage_of(conv)
         if x is None:
-            self._bwd.append(dict(kind=nat.TOP_WGRAD_STEM, off={1: dz, 5: gs}, **geo))
+            x27 = self._act('stem_im2col', geo['Ho'], geo['Wo'], 32)      # scratch of the im2col + tcgen05 path
+            self._bwd.append(dict(kind=nat.TOP_WGRAD_STEM, impl=nat.WGRAD_UMMA, off={0: x27, 1: dz, 5: gs}, **geo))
             return
         self._bwd.append(dict(kind=nat.TOP_WGRAD, impl=nat.WGRAD_UMMA, off={0: x, 1: dz, 5: gs}, **geo))
         # data gradient = the forward kernel on the transposed / tap-flipped weights (stride 2: on the zero-inserted dz)

@@ -1,0 +1,108 @@
+# -*- coding: utf-8 -*-
+"""lfd.execution.Executor on the GPU: the reference's train / val loop contract (lfd/execution/executor.py:13-259)
+driving the NATIVE training step and the fused optimizer, checkpoint + resume parity (an interrupted-and-resumed run ends where the
+uninterrupted one does), online evaluation through the EvaluationHook with the COCO evaluator, and the WIDER FACE SIO writer."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from helpers import synth_model
+from lfd.evaluation import COCOEvaluator, SIO_evaluation
+from lfd.execution.executor import Executor
+from lfd.execution.optim import FusedSGD
+
+pytestmark = pytest.mark.gpu
+N, H, W = 4, 160, 192
+
+
+def _loader(n_batches, seed0):
+    out = []
+    for i in range(n_batches):
+        x = synth.synth_input(N, H, W, seed=seed0 + i).numpy()
+        ann = synth.synth_annotations(N, H, W, 1, seed=seed0 + 50 + i, max_boxes=6)
+        meta = [dict(image_id=100 * i + j, resized_height=H, resized_width=W, resize_scale=1.0) for j in range(N)]
+        out.append((x, ann, meta))
+    return out
+
+
+def _config(work_dir, epochs, resume=None, evaluator=None):
+    model, _ = synth_model('WIDERFACE_XS', cls_bias=-2.0)
+    opt = torch.optim.SGD(model.parameters(), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1], gamma=0.5)
+    return dict(work_dir=work_dir, log_path=None, model=model, optimizer=opt, lr_scheduler=sched, training_epochs=epochs, gpu_list=[0],
+                train_data_loader=_loader(3, 10), val_data_loader=_loader(1, 90), evaluator=evaluator, val_interval=1, save_interval=1,
+                display_interval=1, optimizer_grad_clip_cfg=dict(max_norm=10, norm_type=2),
+                warmup_setting=dict(by_epoch=False, warmup_mode='linear', warmup_loops=2, warmup_ratio=0.1), resume_path=resume, weight_path=None)
+
+
+def test_executor_trains_natively_checkpoints_and_resumes(tmp_path):
+    a = _config(os.path.join(str(tmp_path), 'a'), 2)
+    ex = Executor(a)
+    assert isinstance(a['optimizer'], FusedSGD)                # torch.optim.SGD was re-hosted on the flat buffers
+    ex.run()
+    assert a['epoch'] == 2 and a['train_iter'] == 6
+    assert os.path.isfile(os.path.join(a['work_dir'], 'epoch_1.pth')) and os.path.isfile(os.path.join(a['work_dir'], 'epoch_2.pth'))
+    ck = torch.load(os.path.join(a['work_dir'], 'epoch_2.pth'), weights_only=False)
+    assert set(ck) >= {'meta', 'state_dict', 'optimizer_state_dict', 'lr_scheduler_state_dict'}
+    assert len(ck['optimizer_state_dict']['state']) == len(list(a['model'].parameters()))      # torch.optim.SGD layout: momentum per parameter
+    assert ck['meta']['epoch'] == 2
+    # interrupted after epoch 1, resumed from the checkpoint: same end state
+    b = _config(os.path.join(str(tmp_path), 'b'), 2, resume=os.path.join(a['work_dir'], 'epoch_1.pth'))
+    exb = Executor(b)
+    assert b['epoch'] == 1 and b['train_iter'] == 3
+    exb.run()
+    assert b['epoch'] == 2 and b['train_iter'] == 6
+    assert abs(exb.get_current_lr() - ex.get_current_lr()) < 1e-12
+    worst = 0.0
+    for (name, p), (_, q) in zip(a['model'].state_dict().items(), b['model'].state_dict().items()):
+        if p.dtype.is_floating_point:
+            worst = max(worst, float((p.float() - q.float()).abs().max() / p.float().abs().max().clamp(min=1e-6)))
+        else:
+            assert torch.equal(p, q), name
+    assert worst < 2e-3, worst           # bit-exact up to the order of the fp32 atomics in the weight-gradient staging
+
+
+def test_executor_online_evaluation_with_the_coco_evaluator(tmp_path):
+    val = _loader(1, 90)
+    anns, k = [], 1
+    for (x, ann, meta) in val:
+        for (boxes, labels), m in zip(ann, meta):
+            for bx in boxes:
+                anns.append(dict(id=k, image_id=m['image_id'], category_id=1, bbox=[float(v) for v in bx], area=float(bx[2] * bx[3]), iscrowd=0))
+                k += 1
+    path = os.path.join(str(tmp_path), 'instances.json')
+    json.dump(dict(images=[dict(id=m['image_id']) for m in val[0][2]], categories=[dict(id=1)], annotations=anns), open(path, 'w'))
+    ev = COCOEvaluator(path, {0: 1})
+    cfg = _config(os.path.join(str(tmp_path), 'c'), 1, evaluator=ev)
+    cfg['model']._classification_threshold = 0.05
+    Executor(cfg).run()
+    text = ev.get_eval_display_str()
+    assert ('mAP_50' in text) or ('No bboxes detected' in text), text
+
+
+def test_sio_writer_on_jpeg_files(tmp_path):
+    import cv2
+    root = os.path.join(str(tmp_path), 'images')
+    names = []
+    for ev_name, k in (('0--Parade', 2), ('1--Handshaking', 1)):
+        os.makedirs(os.path.join(root, ev_name))
+        for i in range(k):
+            img = synth.synth_image_u8(120 + 16 * i, 200, seed=3 + i)
+            cv2.imwrite(os.path.join(root, ev_name, '%s_%d.jpg' % (ev_name.split('--')[1], i)), img)
+            names.append((ev_name, '%s_%d' % (ev_name.split('--')[1], i)))
+    model, _ = synth_model('WIDERFACE_XS', cls_bias=-1.0)
+    out = os.path.join(str(tmp_path), 'sio')
+    n = SIO_evaluation(model, root, out, classification_threshold=0.3, nms_threshold=0.4, verbose=False)
+    assert n == 3
+    for ev_name, stem in names:
+        lines = open(os.path.join(out, ev_name, stem + '.txt')).read().splitlines()
+        want = model.predict_for_single_image(os.path.join(root, ev_name, stem + '.jpg'), None, classification_threshold=0.3, nms_threshold=0.4,
+                                              class_agnostic=True)
+        assert lines[0] == stem and int(lines[1]) == len(want) + 1 and lines[2] == '0 0 0 0 0.001' and len(lines) == len(want) + 3
+        for ln, r in zip(lines[3:], want):
+            x, y, w, h, s = ln.split()
+            assert int(x) == int(np.floor(r[2])) and int(w) == int(np.ceil(r[4])) and abs(float(s) - min(r[1], 1.0)) < 6e-4

@@ -260,8 +260,9 @@ def test_wgrad_matches_autograd(case, impl):
     assert rel(got, want) < 2e-4, rel(got, want)
 
 
+@pytest.mark.parametrize('path', ['im2col+umma', 'simt'])
 @pytest.mark.parametrize('fmt', ['f32', 'u8'])
-def test_wgrad_stem(fmt):
+def test_wgrad_stem(fmt, path):
     torch.manual_seed(8)
     N, H, W, Cout = 2, 45, 150, 64
     Ho, Wo = conv_out(H, 3, 2), conv_out(W, 3, 2)
@@ -274,12 +275,18 @@ def test_wgrad_stem(fmt):
     dz = bf16r(torch.randn(N, Ho, Wo, Cout))
     ws = Workspace(DEV)
     ws.add('dz', dz.to(torch.bfloat16))
-    ws.add('ds', shape=(9, 3, Cout), dtype=torch.float32)
+    ws.add('ds', shape=(32, Cout), dtype=torch.float32)          # 27 (tap, ci) rows + 5 padding rows of the tensor-core path
+    ws.add('x27', shape=(N, Ho, Wo, 32), dtype=torch.bfloat16)
     ws.finalize()
-    run_top(make_top(nat.TOP_WGRAD_STEM, N=N, H=H, W=W, Cin=3, Ho=Ho, Wo=Wo, Cout=Cout, ksize=3, stride=2, off={1: ws.off('dz'), 5: ws.off('ds')}),
-            ws, input=img.to(DEV).contiguous(), fmt=nat.INPUT_U8_NHWC if fmt == 'u8' else nat.INPUT_F32_NCHW)
+    offs = {1: ws.off('dz'), 5: ws.off('ds')}
+    if path != 'simt':
+        offs[0] = ws.off('x27')
+    run_top(make_top(nat.TOP_WGRAD_STEM, N=N, H=H, W=W, Cin=3, Ho=Ho, Wo=Wo, Cout=Cout, ksize=3, stride=2, impl=nat.WGRAD_SIMT if path == 'simt' else nat.WGRAD_UMMA,
+                     off=offs), ws, input=img.to(DEV).contiguous(), fmt=nat.INPUT_U8_NHWC if fmt == 'u8' else nat.INPUT_F32_NCHW)
     want = torch.nn.grad.conv2d_weight(x, (Cout, 3, 3, 3), dz.permute(0, 3, 1, 2), stride=2, padding=1)
-    got = ws.get('ds').cpu().permute(2, 1, 0).reshape(Cout, 3, 3, 3)
+    stage = ws.get('ds').cpu()
+    assert float(stage[27:].abs().max()) == 0.0
+    got = stage[:27].reshape(9, 3, Cout).permute(2, 1, 0).reshape(Cout, 3, 3, 3)
     assert rel(got, want) < 2e-4, rel(got, want)
 
 

@@ -12,13 +12,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT = os.path.join(HERE, 'liblfd_b200.so')
+OUT = os.environ.get('LFD_B200_OUT') or os.path.join(HERE, 'liblfd_b200.so')      # LFD_B200_OUT / LFD_B200_EXTRA_FLAGS: tuning experiments only
 SOURCES = ['api.cu', 'conv_umma.cu', 'conv_simt.cu', 'postprocess.cu', 'losses.cu', 'train.cu', 'wgrad_umma.cu']
 HEADERS = ['ptx.cuh', 'conv_common.cuh', 'kernels.cuh', 'train.cuh', os.path.join('..', '..', 'include', 'lfd_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr'] + (['-DLFD_B200_TRACE'] if os.environ.get('LFD_B200_TRACE') else []) + \
-        (['-DLFD_B200_TIMELINE'] if os.environ.get('LFD_B200_TIMELINE') else [])
+        (['-DLFD_B200_TIMELINE'] if os.environ.get('LFD_B200_TIMELINE') else []) + os.environ.get('LFD_B200_EXTRA_FLAGS', '').split()
 
 
 def _stale():
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace('.cu', '.o'))
+        o = os.path.join(CSRC, s.replace('.cu', '.o')) if not os.environ.get('LFD_B200_OUT') else os.path.join('/tmp', os.path.basename(OUT) + '.' + s.replace('.cu', '.o'))
         # conv_umma.cu is always compiled with ptxas -v: see _check_stack_frames
         cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if (verbose or s == 'conv_umma.cu') else []) + ['-c', os.path.join(CSRC, s), '-o', o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -224,7 +224,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f; p.tl = tl; p.f16 = o.dtype;
             if ((o.n_cls && !cls) || (o.n_reg && !reg)) return fail(LFD_ERR_INVALID, "head_final needs cls/reg output pointers");
             if (o.n_reg && o.n_reg != 4) return fail(LFD_ERR_INVALID, "head_final n_reg must be 0 or 4");
-            CUDA_TRY(head_final_launch(p, st));
+            CUDA_TRY(head_final_launch(p, sm_count(), st));
             break;
         }
     }
@@ -710,7 +710,7 @@ static int launch_top(const PlannedTop& pt, const void* input, int fmt, uint8_t*
             p.N = t.N; p.HW = t.H * t.W; p.C = t.Cout; p.groups = t.groups; p.n_out = no; p.n_cls = t.n_cls;
             p.P = t.P; p.point_off = t.point_off; p.cls_stride = t.cls_stride; p.eps = t.eps; p.f16 = 0; p.tl = nullptr;
             if ((t.n_cls && !p.cls) || (t.n_reg && !p.reg)) return fail(LFD_ERR_INVALID, "head_final: output pointers missing");
-            CUDA_TRY(head_final_launch(p, st));
+            CUDA_TRY(head_final_launch(p, sm_count(), st));
             break;
         }
         case LFD_TOP_HEAD_FINAL_BWD: {

@@ -206,16 +206,27 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
 #pragma unroll
     for (int j = 0; j < 16; ++j) { ga[j] = gn ? p.gamma[sl * 16 + j] : 1.f; be[j] = gn ? p.beta[sl * 16 + j] : 0.f; }
     const float m0 = gn ? s_mean[2 * sl] : 0.f, r0 = gn ? s_rstd[2 * sl] : 1.f, m1 = gn ? s_mean[2 * sl + 1] : 0.f, r1 = gn ? s_rstd[2 * sl + 1] : 1.f;
-    const int pix0 = blockIdx.x * kHfPixPerBlock + (threadIdx.x >> 3);
+    // persistent over 128-pixel tiles: the raw rows of the NEXT tile are fetched into registers before the current tile is evaluated, so the
+    // loads of tile t+1 fly while tile t computes (one wave of blocks instead of HW / 128 short-lived ones, each paying the weight fetch)
+    const uint4* rows = reinterpret_cast<const uint4*>(p.in + (size_t)n * p.HW * p.C + sl * 16);
+    const int row_u4 = p.C >> 3;                          // uint4 per pixel row
+    uint4 nxt[kHfPpt][2];
+    auto fetch = [&](int tile) {
+#pragma unroll
+        for (int k = 0; k < kHfPpt; ++k) {
+            const int pix = tile * kHfPixPerBlock + (threadIdx.x >> 3) + k * (kHfThreads / 8);
+            nxt[k][0] = make_uint4(0, 0, 0, 0); nxt[k][1] = nxt[k][0];
+            if (pix < p.HW) { nxt[k][0] = rows[(size_t)pix * row_u4]; nxt[k][1] = rows[(size_t)pix * row_u4 + 1]; }
+        }
+    };
+    const int n_tiles = (p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock;
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int pix0 = tile * kHfPixPerBlock + (threadIdx.x >> 3);
     float a[kHfPpt][16];
 #pragma unroll
     for (int k = 0; k < kHfPpt; ++k) {
-        const int pix = pix0 + k * (kHfThreads / 8);
-        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-        if (pix < p.HW) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.in + ((size_t)n * p.HW + pix) * p.C + sl * 16);
-            q0 = src[0]; q1 = src[1];
-        }
+        const uint4 q0 = nxt[k][0], q1 = nxt[k][1];
         float f[16] = {up_lo<F16>(q0.x), up_hi<F16>(q0.x), up_lo<F16>(q0.y), up_hi<F16>(q0.y), up_lo<F16>(q0.z), up_hi<F16>(q0.z), up_lo<F16>(q0.w), up_hi<F16>(q0.w),
                        up_lo<F16>(q1.x), up_hi<F16>(q1.x), up_lo<F16>(q1.y), up_hi<F16>(q1.y), up_lo<F16>(q1.z), up_hi<F16>(q1.z), up_lo<F16>(q1.w), up_hi<F16>(q1.w)};
 #pragma unroll
@@ -225,6 +236,7 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
             a[k][j] = round16<F16>(fmaxf(y, 0.f));        // rounding point Rg
         }
     }
+    if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
     for (int o0 = 0; o0 < p.n_out; o0 += 8) {
         float acc[8][kHfPpt];
 #pragma unroll
@@ -273,10 +285,11 @@ __global__ void __launch_bounds__(kHfThreads) head_final_kernel(const HeadFinalP
             }
         }
     }
+    }
     LFD_TL_END(p.tl);
 }
 
-cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
+cudaError_t head_final_launch(const HeadFinalParams& p, int num_sms, cudaStream_t st) {
     if (p.C != kHfMaxC || (p.groups != 16 && p.groups != 0)) return cudaErrorInvalidValue;   // 128 channels; 16 groups of 8, or no norm
     const size_t smem = ((size_t)p.n_out * p.C + 64) * sizeof(float);
     static bool attr[kMaxDevices] = {};   // per-device function attribute
@@ -289,7 +302,10 @@ cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st) {
         attr[dev] = true;
     }
     if (smem > 64 * 1024) return cudaErrorInvalidValue;
-    const dim3 grid((p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock, p.N);
+    const int tiles = (p.HW + kHfPixPerBlock - 1) / kHfPixPerBlock;
+    int bx = (2 * num_sms + p.N - 1) / p.N;              // about two resident blocks per SM over all images
+    if (bx > tiles) bx = tiles;
+    const dim3 grid(bx < 1 ? 1 : bx, p.N);
     if (p.f16) head_final_kernel<true><<<grid, kHfThreads, smem, st>>>(p);
     else head_final_kernel<false><<<grid, kHfThreads, smem, st>>>(p);
     return cudaGetLastError();

@@ -40,6 +40,13 @@
 namespace lfd {
 
 static constexpr int kProdThreads = 128;
+// The 3x3/s2 layers are bound by the issue latency of the halo copies (561 pixels x Cc/8 scattered 16-byte cp.async per stage, each behind a
+// shared-memory table read).  Measured (profiles/r02_tuning_notes.md): 128 / 192 / 256 producer threads give 0.109 / 0.107 / 0.106 ms for the
+// 64->64 @180x320 layer -- the layer is NOT issue-bound but bound by 64-byte (half-line) segment fetches; four warps stay the default.
+#ifndef LFD_B200_S2_PROD
+#define LFD_B200_S2_PROD 128
+#endif
+template <int MODE> struct ProdThreads { static constexpr int value = (MODE == MODE_3X3S2) ? LFD_B200_S2_PROD : kProdThreads; };
 
 // The role bodies are lambdas that capture ~30 locals by reference.  If the compiler decides NOT to inline one of them (it did,
 // as soon as a lambda had three call sites or a second instantiation of the template existed) the closure is materialised in
@@ -172,11 +179,12 @@ __device__ __forceinline__ constexpr int tap_view(int tap) {  // pixel offset of
 }
 
 template <int MODE, int EPI_WARPS, bool F16>
-__global__ void __launch_bounds__(EPI_WARPS * 32 + 32 + kProdThreads, (EPI_WARPS == 4 ? 2 : 1))
+__global__ void __launch_bounds__(EPI_WARPS * 32 + 32 + ProdThreads<MODE>::value, (EPI_WARPS == 4 ? 2 : 1))
 conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     constexpr int kEpiThreads = EPI_WARPS * 32;
     constexpr int kMmaWarp = EPI_WARPS;
-    constexpr int kThreads = kEpiThreads + 32 + kProdThreads;
+    constexpr int kProd = ProdThreads<MODE>::value;     // producer threads of this instantiation (the stem code below assumes kProdThreads)
+    constexpr int kThreads = kEpiThreads + 32 + kProd;
     constexpr int TAPS = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : (MODE == MODE_STEM ? 3 : 1);
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBarOff);
@@ -209,7 +217,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
     // ------------------------------------------------------------------ one-time setup
     if (tid == 0) {
         for (int i = 0; i < SA; ++i) {
-            mbar_init(&full[i], kProdThreads + (p.b_resident ? 0 : 1));
+            mbar_init(&full[i], kProd + (p.b_resident ? 0 : 1));
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -628,7 +636,7 @@ conv_umma_kernel(const __grid_constant__ UmmaConvParams p) {
         // every thread owns ONE 16-byte channel chunk (cpc divides 128) and walks the halo pixels with a fixed stride
         const int ch = ptid & (cpc - 1);
         const int px0 = ptid >> p.log2_cpc;
-        const int pstep = kProdThreads >> p.log2_cpc;
+        const int pstep = kProd >> p.log2_cpc;
         const uint32_t ch_dst = ch * p.lbo_a;
         const int my_cnt = (p.n_px - px0 + pstep - 1) / pstep;   // halo pixels this thread copies per stage
         uint32_t it = 0;
@@ -959,7 +967,7 @@ static cudaError_t launch_mode_t(const UmmaConvParams& p, size_t smem, int grid,
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(EPI_WARPS * 32 + 32 + kProdThreads);
+    cfg.blockDim = dim3(EPI_WARPS * 32 + 32 + ProdThreads<MODE>::value);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -46,7 +46,7 @@ struct HeadFinalParams {
     int f16;
     unsigned long long* tl;    // debugging time-line slot or null
 };
-cudaError_t head_final_launch(const HeadFinalParams& p, cudaStream_t st);
+cudaError_t head_final_launch(const HeadFinalParams& p, int num_sms, cudaStream_t st);
 
 struct LevelTable {
     int num_levels;

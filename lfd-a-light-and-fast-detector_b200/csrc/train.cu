@@ -413,7 +413,11 @@ cudaError_t norm_bwd_apply_launch(const NormBwdParams& p, int num_sms, cudaStrea
 // ===================================================================================================
 static constexpr int kHbThreads = 256, kHbPpt = 4, kHbPix = (kHbThreads / 8) * kHbPpt;   // 128 pixels per block iteration
 
+// SMALL: n_out <= 5 (every merged WIDERFACE-style head): the weight-gradient partial sums of a thread stay in registers over all its tiles and
+// are flushed once; otherwise (46-class heads) they go through shared-memory atomics per tile.
+template <bool SMALL>
 __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFinalBwdParams p) {
+    constexpr int kPpt = SMALL ? 2 : kHbPpt, kPix = (kHbThreads / 8) * kPpt;   // SMALL: fewer pixels per thread, the register room goes to the weight-gradient sums
     extern __shared__ __align__(16) float hb_smem[];
     const int C = p.C, no = p.n_out;
     float* wsm = hb_smem;                       // [no][C]
@@ -441,11 +445,18 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
     for (int j = 0; j < 16; ++j) { ga[j] = p.gamma[sl * 16 + j]; be[j] = p.beta[sl * 16 + j]; }
     const float m0 = s_mean[2 * sl], r0 = s_rstd[2 * sl], m1 = s_mean[2 * sl + 1], r1 = s_rstd[2 * sl + 1];
     float dscale_acc = 0.f;
-    for (int tile = blockIdx.x; tile * kHbPix < p.HW; tile += gridDim.x) {
-        const int pix0 = tile * kHbPix + (threadIdx.x >> 3);
-        float a[kHbPpt][16], dt[kHbPpt][16];
+    float dwr[SMALL ? 5 : 1][16], dbr[SMALL ? 5 : 1];
 #pragma unroll
-        for (int k = 0; k < kHbPpt; ++k) {
+    for (int o = 0; o < (SMALL ? 5 : 1); ++o) {
+        dbr[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dwr[o][j] = 0.f;
+    }
+    for (int tile = blockIdx.x; tile * kPix < p.HW; tile += gridDim.x) {
+        const int pix0 = tile * kPix + (threadIdx.x >> 3);
+        float a[kPpt][16], dt[kPpt][16];
+#pragma unroll
+        for (int k = 0; k < kPpt; ++k) {
             const int pix = pix0 + k * (kHbThreads / 8);
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
             if (pix < p.HW) {
@@ -462,12 +473,14 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
                 dt[k][j] = 0.f;
             }
         }
-        for (int o = 0; o < no; ++o) {
+#pragma unroll
+        for (int o = 0; o < (SMALL ? 5 : no); ++o) {
+            if (SMALL && o >= no) break;
             const bool is_reg = o >= p.n_cls;
             const float sc = s_scale[o];
-            float g[kHbPpt], h[kHbPpt];
+            float g[kPpt], h[kPpt];
 #pragma unroll
-            for (int k = 0; k < kHbPpt; ++k) {
+            for (int k = 0; k < kPpt; ++k) {
                 const int pix = pix0 + k * (kHbThreads / 8);
                 float gv = 0.f;
                 if (pix < p.HW) {
@@ -479,10 +492,10 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
             const float4* wr = reinterpret_cast<const float4*>(wsm + (size_t)o * C + sl * 16);
             float hsum = 0.f;
 #pragma unroll
-            for (int k = 0; k < kHbPpt; ++k) hsum += h[k];
-            float u[kHbPpt];
+            for (int k = 0; k < kPpt; ++k) hsum += h[k];
+            float u[kPpt];
 #pragma unroll
-            for (int k = 0; k < kHbPpt; ++k) u[k] = 0.f;
+            for (int k = 0; k < kPpt; ++k) u[k] = 0.f;
 #pragma unroll
             for (int v4 = 0; v4 < 4; ++v4) {
                 const float4 w4 = wr[v4];
@@ -492,18 +505,20 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
                     const int j = v4 * 4 + e;
                     float dw = 0.f;
 #pragma unroll
-                    for (int k = 0; k < kHbPpt; ++k) {
+                    for (int k = 0; k < kPpt; ++k) {
                         dt[k][j] = fmaf(h[k], wv[e], dt[k][j]);
                         dw = fmaf(h[k], a[k][j], dw);
                         if (is_reg) u[k] = fmaf(wv[e], a[k][j], u[k]);
                     }
-                    if (dw != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dw);
+                    if (SMALL) dwr[SMALL ? o : 0][j] += dw;
+                    else if (dw != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dw);
                 }
             }
-            if (sl == 0 && hsum != 0.f) atomicAdd(dbs + o, hsum);
+            if (SMALL) dbr[SMALL ? o : 0] += hsum;
+            else if (sl == 0 && hsum != 0.f) atomicAdd(dbs + o, hsum);
             if (is_reg) {   // Scale gradient needs the full dot product: combine the 8 channel slices (warp-uniform branch)
 #pragma unroll
-                for (int k = 0; k < kHbPpt; ++k) {
+                for (int k = 0; k < kPpt; ++k) {
                     float v = u[k];
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -513,7 +528,7 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
             }
         }
 #pragma unroll
-        for (int k = 0; k < kHbPpt; ++k) {
+        for (int k = 0; k < kPpt; ++k) {
             const int pix = pix0 + k * (kHbThreads / 8);
             if (pix >= p.HW) continue;
             uint4* dst = reinterpret_cast<uint4*>(p.dact + ((size_t)n * p.HW + pix) * C + sl * 16);
@@ -522,6 +537,16 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
         }
     }
     if (dscale_acc != 0.f) atomicAdd(dsc, dscale_acc);
+    if (SMALL) {
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+            if (o >= no) break;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (dwr[o][j] != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dwr[o][j]);
+            if (sl == 0 && dbr[o] != 0.f) atomicAdd(dbs + o, dbr[o]);
+        }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < no * C; i += kHbThreads)
         if (dWs[i] != 0.f) atomicAdd(p.dstage + i, dWs[i]);
@@ -538,15 +563,19 @@ cudaError_t head_final_bwd_launch(const HeadFinalBwdParams& p, int num_sms, cuda
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
     if (!attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(head_final_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(head_final_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(head_final_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         if (e != cudaSuccess) return e;
         attr[dev] = true;
     }
-    const int tiles = (p.HW + kHbPix - 1) / kHbPix;
+    const int pix_per_tile = p.n_out <= 5 ? (kHbThreads / 8) * 2 : kHbPix;
+    const int tiles = (p.HW + pix_per_tile - 1) / pix_per_tile;
     int bx = (2 * num_sms + p.N - 1) / p.N;
     if (bx > tiles) bx = tiles;
     if (bx < 1) bx = 1;
-    head_final_bwd_kernel<<<dim3(bx, p.N), kHbThreads, smem, st>>>(p);
+    if (p.n_out > 64) return cudaErrorInvalidValue;
+    if (p.n_out <= 5) head_final_bwd_kernel<true><<<dim3(bx, p.N), kHbThreads, smem, st>>>(p);
+    else head_final_bwd_kernel<false><<<dim3(bx, p.N), kHbThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 

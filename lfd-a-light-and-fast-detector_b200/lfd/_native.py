@@ -10,7 +10,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG, 'liblfd_b200.so')
+LIB_PATH = os.environ.get('LFD_B200_LIB') or os.path.join(_PKG, 'liblfd_b200.so')   # LFD_B200_LIB: an alternative build of the SAME library (tuning experiments)
 MAX_LEVELS = 8
 
 OP_STEM0, OP_CONV, OP_GN_APPLY, OP_HEAD_FINAL = 0, 1, 2, 3

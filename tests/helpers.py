@@ -91,12 +91,12 @@ def assert_same_detections_up_to_margins(got_src, want_src, scores, boxes, thr, 
     oracle post-process): the sets must be identical except for provably borderline decisions.  Every index in the symmetric
     difference must (a) have an oracle score within `score_tol` of the score threshold, or (b) have an IoU within `iou_tol` of
     the NMS threshold against some kept box of its class, or (c) overlap (IoU > iou_thr - iou_tol) another differing index of its
-    class (a borderline flip cascading through the greedy sweep); and there may be at most max(2, max_frac * kept) of them.
+    class (a borderline flip cascading through the greedy sweep); and there may be at most max(4, max_frac * kept) of them.
     (The CUDA post-process on the CUDA outputs is separately required to be EXACTLY the oracle post-process on those outputs.)
     scores: the ORACLE's scores flattened [P*C]; boxes: its decoded boxes [P, 4]; indices are point * C + class."""
     got, want = set(got_src), set(want_src)
     diff = sorted(got ^ want)
-    assert len(diff) <= max(2, int(max_frac * len(want))), (what, 'too many differing detections', len(diff), len(want))
+    assert len(diff) <= max(4, int(max_frac * len(want))), (what, 'too many differing detections', len(diff), len(want))
     if not diff:
         return 0
     C = int(num_classes)

@@ -43,6 +43,12 @@ struct alignas(16) WgradParams {
     int n_px, Cc, log2_cpc, log2_cpo;
     int n_cich, n_tapg, taps_per_group, n_taps, grid_tiles;
     int stages, tmem_cols, interleave;
+    int pair;                   // swizzled 3x3: TWO taps per accumulator -- an M = 128 operand whose second 64-row group (LBO) is the next tap's shifted view
+    int sw;                     // 1: operands in the 128-byte-swizzled MN-major layout ([pixel slot][64 channels = 128 B], 16-byte chunk ^ (slot & 7))
+    int sw_base_mode;           // descriptor base_offset of shifted (tap) views: 1 = 0 (measured correct: the tensor core swizzles on ABSOLUTE shared-memory
+                                // address bits, so a 128-byte-aligned shifted view of a 1024-byte-aligned swizzled buffer needs no phase), 0 = (start >> 7) & 7 (wrong, kept as the experiment)
+    int row_slots;              // pixel slots per halo row (3x3/s1: 16 in the swizzled layout so that every 8-pixel K group starts a swizzle period)
+    uint32_t b_group_bytes;     // swizzled dz tile: bytes between the 64-channel groups
     uint32_t a_plane_pitch, a_row_pitch, a_stage_bytes, stage_bytes;
     uint32_t smem_table_off, smem_ring_off;
 };
@@ -64,6 +70,18 @@ LFD_DEVINL constexpr int wg_tap_view(int tap) {   // pixel-slot offset of tap's 
     return 0;
 }
 
+// 128-byte-swizzled MN-major operand: start>>4 | LBO (64-channel group stride) | SBO (8-pixel group stride) | version | base offset | SWIZZLE_128B
+LFD_DEVINL uint64_t wg_sw_desc(uint32_t start, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((start >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 LFD_DEVINL void red_add_v4(float* addr, const float* v) {
     atomicAdd(reinterpret_cast<float4*>(addr), make_float4(v[0], v[1], v[2], v[3]));
 }
@@ -71,7 +89,7 @@ LFD_DEVINL void red_add_v4(float* addr, const float* v) {
 template <int MODE>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_constant__ WgradParams p) {
     constexpr int TAPS = (MODE == MODE_3X3S1 || MODE == MODE_3X3S2) ? 9 : 1;
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem[];      // 1024 B = the period of the 128-byte swizzle
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* empty = full + kWgMaxStages;
     uint64_t* done = empty + kWgMaxStages;
@@ -130,9 +148,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_
         tc_fence_after_sync();
         // M = 64 accumulators occupy lanes 16q .. 16q+15 of every 32-lane quarter q (row r -> lane (r % 16) + 32 * (r / 16));
         // with `interleave` the odd taps sit in the other half (lanes + 16) of the same columns.
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        if (p.pair) {
+            // M = 128 accumulators: lane = row; rows 0..63 = tap 2a, rows 64..127 = tap 2a + 1 (a trailing single tap uses the M = 64 layout)
+            const int nacc = (ntap + 1) / 2;
+            for (int a = 0; a < nacc; ++a) {
+                const bool single = 2 * a + 1 >= ntap;
+                int t, ci;
+                bool act;
+                if (single) { t = 2 * a; ci = cich * 64 + warp * 16 + (lane & 15); act = lane < 16; }
+                else { t = 2 * a + (warp >> 1); ci = cich * 64 + (warp & 1) * 32 + lane; act = true; }
+                act = act && ci < p.Cin;
+                float* dst = p.dstage + ((size_t)(tap0 + t) * p.Cin + ci) * p.Cout;
+                for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + lane_base + (uint32_t)(a * p.Cout + c0), v);
+                    tmem_ld_wait();
+                    if (act) {
+                        red_add_v4(dst + c0, v); red_add_v4(dst + c0 + 4, v + 4);
+                        red_add_v4(dst + c0 + 8, v + 8); red_add_v4(dst + c0 + 12, v + 12);
+                    }
+                }
+            }
+        } else {
         const int row = warp * 16 + (lane & 15);
         const int ci = cich * 64 + row;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         const int nacc = p.interleave ? (ntap + 1) / 2 : ntap;
         for (int a = 0; a < nacc; ++a) {
             const int t = p.interleave ? 2 * a + (lane >> 4) : a;
@@ -147,6 +187,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_
                     red_add_v4(dst + c0 + 8, v + 8); red_add_v4(dst + c0 + 12, v + 12);
                 }
             }
+        }
         }
         tc_fence_before_sync();
     } else if (warp == 4) {
@@ -167,6 +208,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_
             const uint32_t b_base = a_base + p.a_stage_bytes;
             const uint64_t ad = adesc0 + (a_base >> 4), bd = bdesc0 + (b_base >> 4);
             if (elect_one_sync()) {
+                if (p.sw) {
+                    const uint32_t sbo_a = (uint32_t)p.row_slots * 128u;
+                    for (int kg = 0; kg < 8; ++kg) {
+                        const uint32_t b_start = b_base + (uint32_t)kg * 2048u;
+                        const uint64_t bdesc = wg_sw_desc(b_start, p.b_group_bytes, 1024u, 0u);
+                        if (p.pair) {
+                            for (int q = 0; 2 * q < ntap; ++q) {
+                                const int t0 = tap0 + 2 * q, t1 = t0 + 1;
+                                const bool two = 2 * q + 1 < ntap;
+                                const uint32_t v0 = (uint32_t)((t0 / 3) * p.row_slots + t0 % 3), v1 = (uint32_t)((t1 / 3) * p.row_slots + t1 % 3);
+                                const uint32_t a_start = a_base + (v0 + (uint32_t)(kg * 2 * p.row_slots)) * 128u;
+                                // second 64-row group of the M = 128 operand = the next tap's view of the same halo: LBO = distance of the two views
+                                const uint64_t adesc = wg_sw_desc(a_start, two ? (v1 - v0) * 128u : 16u, sbo_a, 0u);
+                                umma_bf16(tmem_base + (uint32_t)(q * p.Cout), adesc, bdesc, two ? wg_idesc(128, p.Cout) : idesc, (first && kg == 0) ? 0u : 1u);
+                            }
+                            continue;
+                        }
+#pragma unroll
+                        for (int t = 0; t < TAPS; ++t) {
+                            if (t >= ntap) break;
+                            const int tap = tap0 + t;
+                            const uint32_t view = TAPS == 1 ? 0u : (uint32_t)((tap / 3) * p.row_slots + tap % 3);
+                            const uint32_t a_start = a_base + (view + (uint32_t)(kg * 2 * p.row_slots)) * 128u;
+                            const uint64_t adesc = wg_sw_desc(a_start, 16u, sbo_a, p.sw_base_mode ? 0u : (a_start >> 7));
+                            const uint32_t d = p.interleave ? tmem_base + (uint32_t)((t >> 1) * p.Cout) + ((uint32_t)((t & 1) * 16) << 16)
+                                                            : tmem_base + (uint32_t)(t * p.Cout);
+                            umma_bf16(d, adesc, bdesc, idesc, (first && kg == 0) ? 0u : 1u);
+                        }
+                    }
+                } else
                 for (int kg = 0; kg < 8; ++kg) {
                     const uint64_t adk = ad + (uint32_t)(kg * a_kstep), bdk = bd + (uint32_t)(kg * 16);
 #pragma unroll
@@ -233,7 +304,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_
             const bool interior = MODE == MODE_FLAT ? (ix0 + 128 <= HW)
                                                     : (iy0 + kDyMin >= 0 && ix0 + kDxMin >= 0 && iy0 + kDyMax < p.H && ix0 + kDxMax < p.W);
             const uint32_t dst_cc = a_base + ch_dst;
-            if (MODE == MODE_FLAT) {
+            // swizzled layout: slot s, chunk ch at a_base + s * 128 + ((ch ^ (s & 7)) << 4); halo rows of the 3x3/s1 mode are 16 slots apart
+            auto sw_dst = [&](uint32_t slot) -> uint32_t { return a_base + (slot << 7) + (((uint32_t)ch ^ (slot & 7u)) << 4); };
+            if (p.sw && MODE == MODE_FLAT) {
+#pragma unroll 4
+                for (int pxi = px0; pxi < 128; pxi += pstep) {
+                    const int q = ix0 + pxi;
+                    const bool ok = q < HW;
+                    cp_async16(sw_dst((uint32_t)pxi), img + (size_t)(ok ? q : 0) * p.Cin, ok);
+                }
+            } else if (p.sw) {
+#pragma unroll 2
+                for (int pxi = px0; pxi < p.n_px; pxi += pstep) {
+                    const WgDelta pd = delta[pxi];
+                    const int y = iy0 + pd.dy, x = ix0 + pd.dx;
+                    const bool ok = ((unsigned)y < (unsigned)p.H) && ((unsigned)x < (unsigned)p.W);
+                    uint32_t slot = table[pxi].dst_off >> 4;
+                    if (MODE == MODE_3X3S1) slot = (slot / 10u) * 16u + slot % 10u;      // row pitch 10 -> 16
+                    cp_async16(sw_dst(slot), img + (size_t)(ok ? (y * p.W + x) : 0) * p.Cin, ok);
+                }
+            } else if (MODE == MODE_FLAT) {
 #pragma unroll 4
                 for (int pxi = px0; pxi < 128; pxi += pstep) {
                     const int q = ix0 + pxi;
@@ -270,7 +360,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const __grid_
                     ok = oy < p.Ho && ox < p.Wo;
                     q = oy * p.Wo + ox;
                 }
-                cp_async16(b_dst + sl * 16, dzi + (size_t)(ok ? q : 0) * p.Cout, ok);
+                const uint32_t bd_ = p.sw ? a_base + p.a_stage_bytes + (uint32_t)(chb >> 3) * p.b_group_bytes + ((uint32_t)sl << 7) + ((((uint32_t)chb & 7u) ^ ((uint32_t)sl & 7u)) << 4)
+                                          : b_dst + sl * 16;
+                cp_async16(bd_, dzi + (size_t)(ok ? q : 0) * p.Cout, ok);
             }
             cp_async_mbar_arrive(&full[s]);
         }
@@ -342,11 +434,41 @@ int wg_configure(const WgradGeom& g, int num_sms, WgradParams* out, size_t* smem
     // the A stage always provides the 8 planes an M = 64 operand addresses (Cin = 32: the upper 4 are never written, their
     // accumulator rows are never read)
     p.a_stage_bytes = (uint32_t)((8 * (size_t)p.a_plane_pitch + 127) & ~(size_t)127);
-    const uint32_t b_stage = (uint32_t)((((size_t)g.Cout / 8) * kWgBPitch + 127) & ~(size_t)127);
+    uint32_t b_stage = (uint32_t)((((size_t)g.Cout / 8) * kWgBPitch + 127) & ~(size_t)127);
+    p.row_slots = row_slots;
+    // 128-byte-swizzled operands (the transposing read path of the tensor core is bank-conflict free only in the swizzled layouts: the
+    // SWIZZLE_NONE kernel measures ~225 clk per M64 N64 K16 MMA).  Needs 64-channel rows and 8-pixel K groups that start a swizzle period:
+    // flat tiles (8 slots per row) and 3x3/s1 halos re-pitched to 16 slots per row; the 3x3/s2 parity planes (pitch 9) keep SWIZZLE_NONE.
+    static const int use_sw = getenv("LFD_B200_WGRAD_SW") ? atoi(getenv("LFD_B200_WGRAD_SW")) : 1;
+    static const int sw_base = getenv("LFD_B200_WGRAD_SW_BASE") ? atoi(getenv("LFD_B200_WGRAD_SW_BASE")) : 1;
+    p.sw = use_sw && mode != MODE_3X3S2 && g.Cin % 64 == 0 && (g.Cout == 64 || g.Cout == 128);
+    p.sw_base_mode = sw_base;
+    static const int use_pair = getenv("LFD_B200_WGRAD_PAIR") ? atoi(getenv("LFD_B200_WGRAD_PAIR")) : 1;
+    p.pair = p.sw && use_pair && mode == MODE_3X3S1;
+    if (p.pair) {      // two taps per accumulator: regroup the taps (groups start on an even tap)
+        p.interleave = 0;
+        const int acc_cols = 512 / g.Cout;                      // accumulators per CTA
+        p.taps_per_group = 2 * acc_cols < p.n_taps ? 2 * acc_cols : p.n_taps;
+        p.n_tapg = (p.n_taps + p.taps_per_group - 1) / p.taps_per_group;
+        if (p.n_tapg > 1) {                                     // balance: e.g. Cout = 128: 4 accumulators -> groups of 6 + 3 taps
+            p.taps_per_group = ((p.n_taps + p.n_tapg - 1) / p.n_tapg + 1) & ~1;
+            p.n_tapg = (p.n_taps + p.taps_per_group - 1) / p.taps_per_group;
+        }
+        int cols = 32;
+        while (cols < ((p.taps_per_group + 1) / 2) * g.Cout) cols <<= 1;
+        p.tmem_cols = cols;
+    }
+    if (p.sw) {
+        if (mode == MODE_3X3S1) p.row_slots = 16;
+        const int slots = mode == MODE_3X3S1 ? 18 * 16 : 128;
+        p.a_stage_bytes = (uint32_t)(slots * 128);              // multiples of 1024
+        p.b_group_bytes = 128 * 128;
+        b_stage = (uint32_t)(g.Cout / 64) * p.b_group_bytes;
+    }
     p.stage_bytes = p.a_stage_bytes + b_stage;
     p.smem_table_off = 512;
     const size_t table_bytes = mode == MODE_FLAT ? 0 : (((size_t)p.n_px * 10 + 127) & ~(size_t)127);
-    p.smem_ring_off = (uint32_t)(512 + table_bytes);
+    p.smem_ring_off = (uint32_t)((512 + table_bytes + 1023) & ~(size_t)1023);      // 1024-aligned: the swizzle period
     const size_t budget = 226 * 1024;
     int st = (int)((budget - p.smem_ring_off) / p.stage_bytes);
     if (st > kWgMaxStages) st = kWgMaxStages;

@@ -343,6 +343,20 @@ def train_main(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.ncu_step:      # profiling aid (`ncu --profile-from-start off`): warm up, then ONE eager training step between cudaProfilerStart/Stop
+        model.use_cuda_graph_training = False
+        for p_ in model._train_plans.values():
+            p_.use_graph = False
+        for i in range(3):
+            step(i)
+        for p_ in model._train_plans.values():
+            p_.use_graph = False
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(3)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return 0
     for i in range(max(warmup, 3)):           # W warm-up steps (the first ones also capture the forward / backward CUDA graphs)
         lv = step(i)
     sync_all()

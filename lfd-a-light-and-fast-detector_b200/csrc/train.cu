@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnStatsParams p) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
         float f[8];
         unpack8(z[i], f);
@@ -163,11 +163,18 @@ static int elementwise_blocks(size_t chunks, int num_sms) {
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }
+// reductions end with one fp64 atomic per (block, channel, statistic) on a handful of addresses: fewer, longer-running blocks
+static int reduce_blocks(size_t chunks, int num_sms) {
+    size_t b = (chunks + 256 * 8 - 1) / (256 * 8);
+    const size_t cap = (size_t)num_sms * 3;
+    if (b > cap) b = cap;
+    return b < 1 ? 1 : (int)b;
+}
 static bool pow2_chunks(int C) { const int cpr = C >> 3; return C % 8 == 0 && cpr >= 1 && cpr <= 32 && (cpr & (cpr - 1)) == 0; }
 
 cudaError_t bn_stats_launch(const BnStatsParams& p, int num_sms, cudaStream_t st) {
     if (!pow2_chunks(p.C)) return cudaErrorInvalidValue;
-    bn_stats_kernel<<<elementwise_blocks((size_t)p.M * (p.C >> 3), num_sms), 256, 0, st>>>(p);
+    bn_stats_kernel<<<reduce_blocks((size_t)p.M * (p.C >> 3), num_sms), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
     float v[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
         float g[8], zf[8], yf[8];
         unpack8(dy[i], g);
@@ -295,7 +302,7 @@ cudaError_t norm_bwd_reduce_launch(const NormBwdParams& p, int num_sms, cudaStre
         if (bx > cap) bx = cap;
         norm_bwd_reduce_kernel<true><<<dim3(bx, p.N), 256, 0, st>>>(p);
     } else {
-        norm_bwd_reduce_kernel<false><<<elementwise_blocks((size_t)p.N * p.H * p.W * (p.C >> 3), num_sms), 256, 0, st>>>(p);
+        norm_bwd_reduce_kernel<false><<<reduce_blocks((size_t)p.N * p.H * p.W * (p.C >> 3), num_sms), 256, 0, st>>>(p);
     }
     return cudaGetLastError();
 }
@@ -455,6 +462,23 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
     for (int tile = blockIdx.x; tile * kPix < p.HW; tile += gridDim.x) {
         const int pix0 = tile * kPix + (threadIdx.x >> 3);
         float a[kPpt][16], dt[kPpt][16];
+        // SMALL: every upstream gradient of the tile is fetched up front, together with the activation rows (ONE memory round trip per tile
+        // instead of one per output channel)
+        float gpre[SMALL ? 5 : 1][kPpt];
+        if (SMALL) {
+#pragma unroll
+            for (int o = 0; o < 5; ++o)
+#pragma unroll
+                for (int k = 0; k < kPpt; ++k) {
+                    const int pix = pix0 + k * (kHbThreads / 8);
+                    float gv = 0.f;
+                    if (o < no && pix < p.HW) {
+                        const size_t pt = (size_t)n * p.P + p.point_off + pix;
+                        gv = o >= p.n_cls ? p.greg[pt * 4 + (o - p.n_cls)] : p.gcls[pt * p.cls_stride + o];
+                    }
+                    gpre[o][k] = gv;
+                }
+        }
 #pragma unroll
         for (int k = 0; k < kPpt; ++k) {
             const int pix = pix0 + k * (kHbThreads / 8);
@@ -483,7 +507,8 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
             for (int k = 0; k < kPpt; ++k) {
                 const int pix = pix0 + k * (kHbThreads / 8);
                 float gv = 0.f;
-                if (pix < p.HW) {
+                if (SMALL) gv = gpre[SMALL ? o : 0][k];
+                else if (pix < p.HW) {
                     const size_t pt = (size_t)n * p.P + p.point_off + pix;
                     gv = is_reg ? p.greg[pt * 4 + (o - p.n_cls)] : p.gcls[pt * p.cls_stride + o];
                 }
@@ -570,7 +595,7 @@ cudaError_t head_final_bwd_launch(const HeadFinalBwdParams& p, int num_sms, cuda
     }
     const int pix_per_tile = p.n_out <= 5 ? (kHbThreads / 8) * 2 : kHbPix;
     const int tiles = (p.HW + pix_per_tile - 1) / pix_per_tile;
-    int bx = (2 * num_sms + p.N - 1) / p.N;
+    int bx = (4 * num_sms + p.N - 1) / p.N;
     if (bx > tiles) bx = tiles;
     if (bx < 1) bx = 1;
     if (p.n_out > 64) return cudaErrorInvalidValue;

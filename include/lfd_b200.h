@@ -14,6 +14,7 @@
  *                                   LFDHead.forward    lfd/model/head/lfd_head.py:164-185)
  *   lfd_postprocess                LFD._get_results_for_single_image   lfd/model/lfd.py:434-509, predict path :577-641,
  *                                  multiclass_nms / batched_nms        lfd/model/utils/nms.py:119-220
+ *   lfd_multiclass_nms             multiclass_nms / batched_nms        lfd/model/utils/nms.py:119-220 (on explicit boxes)
  *   lfd_nms                        nms_ext.nms                         lfd/model/utils/build/nms/src/nms_ext.cpp:18-29,
  *                                                                      cpu/nms_cpu.cpp:8-75, cuda/nms_kernel.cu:71-138
  *   lfd_sigmoid_focal_loss_forward sigmoid_focal_loss_ext.forward      lfd/model/losses/build/sigmoid_focal_loss/src/sigmoid_focal_loss_ext.cpp:19-34
@@ -162,6 +163,17 @@ size_t lfd_postprocess_workspace_bytes(const lfd_post_cfg* cfg);
 int lfd_postprocess(const lfd_post_cfg* cfg, const float* cls, const float* reg, const float* img_w, const float* img_h,
                     const float* resize_scale, void* workspace, float* dets, int32_t* labels, int32_t* src, int32_t* count,
                     int32_t* overflow, lfd_stream stream);
+
+/* multiclass_nms / batched_nms of lfd/model/utils/nms.py:119-220 on explicit (already decoded) boxes.
+ * labels_in == NULL: boxes float[n][4] (box_per_class = 0) or float[n][C][4] (1), scores float[n][score_stride]: candidate (row i, class c < C)
+ *   when scores[i][c] > score_thr (strict); labels_in != NULL (the batched_nms form): one candidate per row (boxes[i], scores[i], labels_in[i]),
+ *   C = number of label values.  Class-aware suppression reproduces the reference's label * (max coordinate + 1) offsets in fp32.
+ * Outputs (device): dets float[cap][5] = x1,y1,x2,y2,score in kept (score-descending) order, labels int32[cap], src int32[cap] = row * C +
+ * class, count int32[1], overflow int32[1] (1: more than cap candidates). */
+size_t lfd_multiclass_nms_workspace_bytes(int cap);
+int lfd_multiclass_nms(const float* boxes, int box_per_class, const float* scores, int score_stride, const int32_t* labels_in, int n, int C,
+                       float score_thr, float iou_thr, int class_agnostic, int cap, void* workspace, float* dets, int32_t* labels, int32_t* src,
+                       int32_t* count, int32_t* overflow, lfd_stream stream);
 
 size_t lfd_nms_workspace_bytes(int n);
 /* dets device float[n][5]; keep device int64[n] (first *n_keep valid, score-descending); n_keep device int32[1]. */

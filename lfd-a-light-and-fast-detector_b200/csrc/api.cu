@@ -459,6 +459,34 @@ extern "C" int lfd_postprocess(const lfd_post_cfg* c, const float* cls, const fl
     return LFD_OK;
 }
 
+// multiclass_nms / batched_nms on explicit boxes (lfd/model/utils/nms.py:119-220): threshold + class-offset NMS, all on the device
+extern "C" size_t lfd_multiclass_nms_workspace_bytes(int cap) { return cap > 0 ? post_layout(1, cap).total : 256; }
+
+extern "C" int lfd_multiclass_nms(const float* boxes, int box_per_class, const float* scores, int score_stride, const int32_t* labels_in, int n, int C,
+                                  float score_thr, float iou_thr, int class_agnostic, int cap, void* workspace, float* dets, int32_t* labels, int32_t* src,
+                                  int32_t* count, int32_t* overflow, lfd_stream stream) {
+    if (n < 0 || C < 1 || cap < 1 || !workspace || !dets || !labels || !src || !count || !overflow || (n > 0 && (!boxes || !scores)))
+        return fail(LFD_ERR_INVALID, "lfd_multiclass_nms: bad arguments");
+    if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_multiclass_nms: no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    const PostLayout L = post_layout(1, cap);
+    float* cbox = reinterpret_cast<float*>(ws + L.box);
+    float* cscore = reinterpret_cast<float*>(ws + L.score);
+    int* csrc = reinterpret_cast<int*>(ws + L.src);
+    int* ccount = reinterpret_cast<int*>(ws + L.count);
+    CUDA_TRY(cudaMemsetAsync(ccount, 0, 4, st));
+    CUDA_TRY(cudaMemsetAsync(overflow, 0, 4, st));
+    CUDA_TRY(box_candidates_launch(boxes, box_per_class, scores, score_stride, labels_in, n, C, score_thr, cap, cbox, cscore, csrc, ccount, st));
+    NmsParams q;
+    q.cand_box = cbox; q.cand_score = cscore; q.cand_src = csrc; q.cand_count = ccount;
+    q.scratch = ws + L.scratch; q.scratch_stride = L.scratch_stride; q.cap = cap; q.cap_pow2 = L.cap_pow2; q.C = C;
+    q.class_agnostic = class_agnostic; q.iou_thr = iou_thr;
+    q.out_dets = dets; q.out_label = labels; q.out_src = src; q.out_count = count; q.overflow = overflow;
+    CUDA_TRY(nms_launch(q, 1, st));
+    return LFD_OK;
+}
+
 // standalone NMS on raw dets (mirror of nms_ext.nms)
 __global__ void nms_split_kernel(const float* dets, int n, float* box, float* score, int* src, int* count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -95,6 +95,38 @@ __global__ void __launch_bounds__(256) candidates_kernel(const PostParams p) {
     }
 }
 
+// Candidates from explicit (already decoded) boxes: the entry of multiclass_nms / batched_nms (utils/nms.py:119-220).
+//   labels_in == null: rows x classes grid, candidate (i, c) when scores[i * score_stride + c] > score_thr (strict, nms.py:204),
+//                      box = boxes[i] (box_per_class 0) or boxes[i][c]
+//   labels_in != null: one candidate per row: (boxes[i], scores[i], labels_in[i]), no threshold
+__global__ void __launch_bounds__(256) box_candidates_kernel(const float* __restrict__ boxes, int box_per_class, const float* __restrict__ scores,
+                                                             int score_stride, const int* __restrict__ labels_in, int n, int C, float score_thr, int cap,
+                                                             float* cand_box, float* cand_score, int* cand_src, int* cand_count) {
+    const long long total = labels_in ? (long long)n : (long long)n * C;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        int i, c;
+        float sc;
+        if (labels_in) { i = (int)idx; c = labels_in[i]; sc = scores[i]; }
+        else { i = (int)(idx / C); c = (int)(idx % C); sc = scores[(size_t)i * score_stride + c]; if (!(sc > score_thr)) continue; }
+        const int slot = atomicAdd(cand_count, 1);
+        if (slot >= cap) continue;                   // the NMS kernel reports the overflow
+        const float4 b = reinterpret_cast<const float4*>(boxes)[box_per_class ? (size_t)i * C + c : (size_t)i];
+        reinterpret_cast<float4*>(cand_box)[slot] = b;
+        cand_score[slot] = sc;
+        cand_src[slot] = i * C + c;
+    }
+}
+cudaError_t box_candidates_launch(const float* boxes, int box_per_class, const float* scores, int score_stride, const int* labels_in, int n, int C,
+                                  float score_thr, int cap, float* cand_box, float* cand_score, int* cand_src, int* cand_count, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const long long total = labels_in ? (long long)n : (long long)n * C;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2048) blocks = 2048;
+    box_candidates_kernel<<<(int)blocks, 256, 0, st>>>(boxes, box_per_class, scores, score_stride, labels_in, n, C, score_thr, cap, cand_box, cand_score, cand_src,
+                                                      cand_count);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One CTA per image.
 //   cand_*   : unsorted candidates (count K, K <= cap)

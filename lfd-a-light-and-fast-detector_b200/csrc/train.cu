@@ -142,13 +142,19 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnStatsParams p) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
-#pragma unroll 8
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    // batches of 4 independent 16-byte loads per thread before any arithmetic: the kernel is a pure stream and needs ~64 KB in flight per SM
+    auto acc = [&](const uint4 q) {
         float f[8];
-        unpack8(z[i], f);
+        unpack8(q, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { v[j] += f[j]; v[8 + j] = fmaf(f[j], f[j], v[8 + j]); }
+    };
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+        const uint4 q0 = z[i], q1 = z[i + stride], q2 = z[i + 2 * stride], q3 = z[i + 3 * stride];
+        acc(q0); acc(q1); acc(q2); acc(q3);
     }
+    for (; i < total; i += stride) acc(z[i]);
     block_reduce_groups<16>(v, cpr, sh);
     const float* tot = sh + 8 * cpr * 16;
     for (int t = threadIdx.x; t < cpr * 16; t += 256) {
@@ -166,7 +172,7 @@ static int elementwise_blocks(size_t chunks, int num_sms) {
 // reductions end with one fp64 atomic per (block, channel, statistic) on a handful of addresses: fewer, longer-running blocks
 static int reduce_blocks(size_t chunks, int num_sms) {
     size_t b = (chunks + 256 * 8 - 1) / (256 * 8);
-    const size_t cap = (size_t)num_sms * 3;
+    const size_t cap = (size_t)num_sms * 4;
     if (b > cap) b = cap;
     return b < 1 ? 1 : (int)b;
 }
@@ -204,11 +210,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
     const uint4* z = reinterpret_cast<const uint4*>(p.z);
     const uint4* res = reinterpret_cast<const uint4*>(p.res);
     uint4* y = reinterpret_cast<uint4*>(p.y);
-#pragma unroll 4
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    auto apply = [&](size_t i, const uint4 qz, const uint4 qr) {
         float f[8], r[8];
-        unpack8(z[i], f);
-        if (res) unpack8(res[i], r);
+        unpack8(qz, f);
+        if (res) unpack8(qr, r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float o = fmaf(f[j], sc[j], sf[j]);
@@ -216,7 +221,16 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
             f[j] = p.relu ? fmaxf(o, 0.f) : o;
         }
         y[i] = pack8f(f);
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {      // 4 (8 with a residual) independent loads in flight per thread
+        const uint4 z0 = z[i], z1 = z[i + stride], z2 = z[i + 2 * stride], z3 = z[i + 3 * stride];
+        uint4 r0 = zero4, r1 = zero4, r2 = zero4, r3 = zero4;
+        if (res) { r0 = res[i]; r1 = res[i + stride]; r2 = res[i + 2 * stride]; r3 = res[i + 3 * stride]; }
+        apply(i, z0, r0); apply(i + stride, z1, r1); apply(i + 2 * stride, z2, r2); apply(i + 3 * stride, z3, r3);
     }
+    for (; i < total; i += stride) apply(i, z[i], res ? res[i] : zero4);
 }
 
 cudaError_t bn_apply_launch(const BnApplyParams& p, int num_sms, cudaStream_t st) {
@@ -266,12 +280,12 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
     float v[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = 0.f;
-#pragma unroll 4
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const bool need_y = !GN && p.relu;
+    auto acc = [&](const uint4 qdy, const uint4 qz, const uint4 qy) {
         float g[8], zf[8], yf[8];
-        unpack8(dy[i], g);
-        unpack8(z[i], zf);
-        if (!GN && p.relu) unpack8(y[i], yf);
+        unpack8(qdy, g);
+        unpack8(qz, zf);
+        if (need_y) unpack8(qy, yf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float zh = (zf[j] - mu[j]) * rs[j];
@@ -283,7 +297,16 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const NormBwdParam
             v[8 + j] = fmaf(gj, zh, v[8 + j]);   // dgamma
             if (GN) { v[16] = fmaf(gj, ga[j], v[16]); v[17] = fmaf(gj * ga[j], zh, v[17]); }
         }
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {      // two rows x three tensors of independent loads in flight per thread
+        const uint4 a0 = dy[i], a1 = dy[i + stride], b0 = z[i], b1 = z[i + stride];
+        uint4 c0 = zero4, c1 = zero4;
+        if (need_y) { c0 = y[i]; c1 = y[i + stride]; }
+        acc(a0, b0, c0); acc(a1, b1, c1);
     }
+    for (; i < total; i += stride) acc(dy[i], z[i], need_y ? y[i] : zero4);
     block_reduce_groups<NV>(v, cpr, sh);
     const float* tot = sh + 8 * cpr * NV;
     for (int t = threadIdx.x; t < cpr * NV; t += 256) {
@@ -357,12 +380,13 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams
     uint4* dres = reinterpret_cast<uint4*>(p.dres) + base;
     uint4* dzu = reinterpret_cast<uint4*>(p.dz_up);
     const int HW = p.H * p.W;
-#pragma unroll 2
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+    const bool need_y = !GN && p.relu;
+    const bool need_r = p.dres && p.dres_accumulate;
+    auto apply = [&](size_t i, const uint4 qdy, const uint4 qz, const uint4 qy, const uint4 qr) {
         float g[8], zf[8], yf[8], o[8];
-        unpack8(dy[i], g);
-        unpack8(z[i], zf);
-        if (!GN && p.relu) unpack8(y[i], yf);
+        unpack8(qdy, g);
+        unpack8(qz, zf);
+        if (need_y) unpack8(qy, yf);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float zh = (zf[j] - mu[j]) * rs[j];
@@ -376,9 +400,9 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams
         const uint4 ov = pack8f(o);
         dz[i] = ov;
         if (p.dres) {
-            if (p.dres_accumulate) {
+            if (need_r) {
                 float r[8];
-                unpack8(dres[i], r);
+                unpack8(qr, r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) g[j] += r[j];
             }
@@ -390,7 +414,17 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const NormBwdParams
             const int oy = rem / p.W, ox = rem - oy * p.W;
             dzu[(((size_t)nn * p.upH + 2 * oy) * p.upW + 2 * ox) * cpr + cg] = ov;
         }
+    };
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < total; i += 2 * stride) {      // two rows x up to four tensors of independent loads in flight per thread
+        const uint4 a0 = dy[i], a1 = dy[i + stride], b0 = z[i], b1 = z[i + stride];
+        uint4 c0 = zero4, c1 = zero4, r0 = zero4, r1 = zero4;
+        if (need_y) { c0 = y[i]; c1 = y[i + stride]; }
+        if (need_r) { r0 = dres[i]; r1 = dres[i + stride]; }
+        apply(i, a0, b0, c0, r0); apply(i + stride, a1, b1, c1, r1);
     }
+    for (; i < total; i += stride) apply(i, dy[i], z[i], need_y ? y[i] : zero4, need_r ? dres[i] : zero4);
 }
 
 cudaError_t norm_bwd_apply_launch(const NormBwdParams& p, int num_sms, cudaStream_t st) {

@@ -111,6 +111,8 @@ SYMBOLS = {
     'lfd_run_op': (_i, [C.POINTER(Op), _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     'lfd_postprocess_workspace_bytes': (C.c_size_t, [C.POINTER(PostCfg)]),
     'lfd_postprocess': (_i, [C.POINTER(PostCfg)] + [_vp] * 11),
+    'lfd_multiclass_nms_workspace_bytes': (C.c_size_t, [_i]),
+    'lfd_multiclass_nms': (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _f, _f, _i, _i] + [_vp] * 7),
     'lfd_nms_workspace_bytes': (C.c_size_t, [_i]),
     'lfd_nms': (_i, [_vp, _i, _f, _vp, _vp, _vp, _vp]),
     'lfd_assign_targets': (_i, [C.POINTER(Levels), _i, _i, _i, _i, _i, _i] + [_vp] * 8),

@@ -69,10 +69,9 @@ def launches(path, out, title):
 
 
 METRICS = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'dram read'), ('dram__bytes_write.sum', 'dram write'),
-           ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %'), ('sm__inst_executed_pipe_tensor.sum', 'tensor inst'),
-           ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe %'),
-           ('sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'tensor (hmma) %'),
-           ('l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'L1 %'), ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 %'),
+           ('FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM %'), ('dram__bytes.sum.per_second', 'DRAM B/s'), ('sm__inst_executed_pipe_tensor.sum', 'tensor inst'),
+           ('TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor pipe %'),
+           ('SM_A.TriageCompute.l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'L1 %'), ('LTS.TriageCompute.lts__throughput.avg.pct_of_peak_sustained_elapsed', 'L2 %'),
            ('launch__registers_per_thread', 'regs'), ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occupancy %'),
            ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'SM %')]
 

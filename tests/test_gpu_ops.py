@@ -103,3 +103,25 @@ def test_get_loss_matches_reference_golden(name):
         assert rel_err(reg.grad.cpu(), g['grad_reg'])[0] < 1e-4
     else:
         assert float(reg.grad.abs().max()) == 0.0
+
+
+def test_batched_nms_matches_oracle():
+    """batched_nms (utils/nms.py:119-158): the label * (max coordinate + 1) offsets live inside the native NMS kernel; kept indices and
+    rows against the oracle's NMS on the offset boxes."""
+    from lfd.model.utils import batched_nms
+    rng = np.random.RandomState(21)
+    n = 300
+    xy = rng.uniform(0, 120, (n, 2)).astype(np.float32)
+    wh = rng.uniform(8, 50, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = rng.uniform(0.05, 1.0, n).astype(np.float32)
+    labels = rng.randint(0, 4, n).astype(np.int64)
+    dets, keep = batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(), dict(type='nms', iou_thr=0.4))
+    off = labels.astype(np.float32) * np.float32(boxes.max() + np.float32(1))
+    okeep = orc.nms(np.concatenate([boxes + off[:, None], scores[:, None]], 1).astype(np.float32), 0.4)
+    assert keep.cpu().tolist() == list(map(int, okeep))
+    assert np.array_equal(dets[:, :4].cpu().numpy(), boxes[okeep]) and np.array_equal(dets[:, 4].cpu().numpy(), scores[okeep])
+    # class agnostic: plain NMS
+    dets2, keep2 = batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(),
+                               dict(type='nms', iou_thr=0.4, class_agnostic=True))
+    assert keep2.cpu().tolist() == list(map(int, orc.nms(np.concatenate([boxes, scores[:, None]], 1).astype(np.float32), 0.4)))

@@ -120,7 +120,10 @@ def test_batched_nms_matches_oracle():
     off = labels.astype(np.float32) * np.float32(boxes.max() + np.float32(1))
     okeep = orc.nms(np.concatenate([boxes + off[:, None], scores[:, None]], 1).astype(np.float32), 0.4)
     assert keep.cpu().tolist() == list(map(int, okeep))
-    assert np.array_equal(dets[:, :4].cpu().numpy(), boxes[okeep]) and np.array_equal(dets[:, 4].cpu().numpy(), scores[okeep])
+    # like the reference (nms.py:152-156) the returned boxes are (box + offset) - offset in fp32, not the input boxes bit for bit
+    shifted = (boxes + off[:, None]).astype(np.float32)
+    want = (shifted[okeep] - off[okeep][:, None]).astype(np.float32)
+    assert np.array_equal(dets[:, :4].cpu().numpy(), want) and np.array_equal(dets[:, 4].cpu().numpy(), scores[okeep])
     # class agnostic: plain NMS
     dets2, keep2 = batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(),
                                dict(type='nms', iou_thr=0.4, class_agnostic=True))

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define LFD_B200_ABI_VERSION 4
+#define LFD_B200_ABI_VERSION 5
 #define LFD_MAX_LEVELS 8
 #define LFD_MAX_BRANCHES 8
 
@@ -278,6 +278,11 @@ typedef struct lfd_top {
     int32_t impl;         /* WGRAD: LFD_WGRAD_UMMA | LFD_WGRAD_SIMT; CONV: LFD_CONV_UMMA | LFD_CONV_SIMT */
     int32_t frozen;       /* BN_APPLY / NORM_BWD_* (BatchNorm): the module is in eval mode -- normalise with the running statistics
                              (ptr[2..3] of BN_APPLY, ptr[4..5] of NORM_BWD_*), do not update them, no batch-statistics terms in dz */
+    int32_t branch, wait_mask; /* as in lfd_op: branch 0 = the caller's stream, ops of branch b > 0 run on side stream b (forked after the
+                                  main-stream op preceding the branch's first op, joined at the end of the plan); wait_mask bit w = wait for
+                                  everything enqueued so far on branch w.  The per-level neck / head chains of the forward and of the
+                                  backward are independent of the backbone's smaller stages: lfd/_train.py derives the masks from the
+                                  read / write / accumulate role of every off[] entry. */
     int32_t pad_;
     float eps, momentum;
     int64_t off[8];

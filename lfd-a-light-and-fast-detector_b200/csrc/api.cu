@@ -634,6 +634,11 @@ struct lfd_train_plan {
     int64_t workspace_bytes;
     struct GraphEntry { cudaGraphExec_t exec; const void* input; void* ws; int fmt; };
     std::vector<GraphEntry> graphs;
+    // side streams of the independent per-level chains (same fork / wait / join protocol as lfd_plan)
+    cudaStream_t side[LFD_MAX_BRANCHES];
+    cudaEvent_t fork_ev[LFD_MAX_BRANCHES], join_ev[LFD_MAX_BRANCHES];
+    std::vector<cudaEvent_t> dep_ev;
+    int n_branches = 1;
 };
 
 static lfd_op conv_op_of(const lfd_top& t) {
@@ -810,11 +815,31 @@ extern "C" int lfd_train_plan_create(const lfd_top* ops, int n_ops, int64_t work
     if (sm_count() <= 0) return fail(LFD_ERR_CUDA, "lfd_train_plan_create: no CUDA device (there is no CPU fallback)");
     lfd_train_plan* pl = new lfd_train_plan();
     pl->workspace_bytes = workspace_bytes;
+    size_t n_dep = 0;
     for (int i = 0; i < n_ops; ++i) {
         PlannedTop pt;
         int rc = plan_top(ops[i], workspace_bytes, &pt);
         if (rc) { delete pl; return rc; }
+        if (ops[i].branch < 0 || ops[i].branch >= LFD_MAX_BRANCHES || ops[i].wait_mask < 0 || ops[i].wait_mask >= (1 << LFD_MAX_BRANCHES)) {
+            delete pl;
+            return fail(LFD_ERR_INVALID, "training op %d: branch %d / wait_mask 0x%x out of range", i, ops[i].branch, ops[i].wait_mask);
+        }
+        if (ops[i].branch + 1 > pl->n_branches) pl->n_branches = ops[i].branch + 1;
+        n_dep += (size_t)__builtin_popcount((unsigned)ops[i].wait_mask);
         pl->ops.push_back(pt);
+    }
+    const int nb = pl->n_branches;
+    pl->n_branches = 1;
+    for (int b = 1; b < nb; ++b) {
+        if (cudaStreamCreateWithFlags(&pl->side[b], cudaStreamNonBlocking) != cudaSuccess) { lfd_train_plan_destroy(pl); return fail(LFD_ERR_CUDA, "lfd_train_plan_create: cannot create side streams"); }
+        if (cudaEventCreateWithFlags(&pl->fork_ev[b], cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(pl->side[b]); lfd_train_plan_destroy(pl); return fail(LFD_ERR_CUDA, "lfd_train_plan_create: cannot create events"); }
+        if (cudaEventCreateWithFlags(&pl->join_ev[b], cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(pl->side[b]); cudaEventDestroy(pl->fork_ev[b]); lfd_train_plan_destroy(pl); return fail(LFD_ERR_CUDA, "lfd_train_plan_create: cannot create events"); }
+        pl->n_branches = b + 1;
+    }
+    for (size_t i = 0; i < n_dep; ++i) {
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { lfd_train_plan_destroy(pl); return fail(LFD_ERR_CUDA, "lfd_train_plan_create: cannot create dependency events"); }
+        pl->dep_ev.push_back(ev);
     }
     *out = pl;
     return LFD_OK;
@@ -823,6 +848,12 @@ extern "C" int lfd_train_plan_create(const lfd_top* ops, int n_ops, int64_t work
 extern "C" int lfd_train_plan_destroy(lfd_train_plan* plan) {
     if (!plan) return LFD_OK;
     for (auto& g : plan->graphs) cudaGraphExecDestroy(g.exec);
+    for (int b = 1; b < plan->n_branches; ++b) {
+        cudaStreamDestroy(plan->side[b]);
+        cudaEventDestroy(plan->fork_ev[b]);
+        cudaEventDestroy(plan->join_ev[b]);
+    }
+    for (auto ev : plan->dep_ev) cudaEventDestroy(ev);
     delete plan;
     return LFD_OK;
 }
@@ -830,11 +861,36 @@ extern "C" int lfd_train_plan_destroy(lfd_train_plan* plan) {
 extern "C" int lfd_train_plan_num_ops(const lfd_train_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
 
 static int train_enqueue(lfd_train_plan* pl, const void* input, int fmt, uint8_t* ws, cudaStream_t st) {
-    for (size_t i = 0; i < pl->ops.size(); ++i) {
-        int rc = launch_top(pl->ops[i], input, fmt, ws, st);
-        if (rc) return rc;
+    bool started[LFD_MAX_BRANCHES] = {false};
+    int rc = LFD_OK;
+    size_t dep = 0;
+    cudaError_t ce = cudaSuccess;
+    for (size_t i = 0; i < pl->ops.size() && !rc && ce == cudaSuccess; ++i) {
+        const lfd_top& t = pl->ops[i].op;
+        const int b = t.branch;
+        cudaStream_t s = st;
+        if (b > 0) {
+            s = pl->side[b];
+            if (!started[b]) {   // fork: everything enqueued on the main stream so far precedes this branch
+                if ((ce = cudaEventRecord(pl->fork_ev[b], st)) != cudaSuccess || (ce = cudaStreamWaitEvent(s, pl->fork_ev[b], 0)) != cudaSuccess) break;
+                started[b] = true;
+            }
+        }
+        for (int w = 0; w < LFD_MAX_BRANCHES && ce == cudaSuccess; ++w) {
+            if (!((t.wait_mask >> w) & 1)) continue;
+            cudaEvent_t ev = pl->dep_ev[dep++];
+            if (w == b || (w > 0 && (w >= pl->n_branches || !started[w]))) continue;
+            if ((ce = cudaEventRecord(ev, w == 0 ? st : pl->side[w])) == cudaSuccess) ce = cudaStreamWaitEvent(s, ev, 0);
+        }
+        if (ce == cudaSuccess) rc = launch_top(pl->ops[i], input, fmt, ws, s);
     }
-    return LFD_OK;
+    for (int b = 1; b < pl->n_branches; ++b)   // join (also on error paths, so that a stream capture can be closed)
+        if (started[b]) {
+            cudaEventRecord(pl->join_ev[b], pl->side[b]);
+            cudaStreamWaitEvent(st, pl->join_ev[b], 0);
+        }
+    if (!rc && ce != cudaSuccess) rc = fail(LFD_ERR_CUDA, "training plan stream dependencies: %s", cudaGetErrorString(ce));
+    return rc;
 }
 
 extern "C" int lfd_train_plan_run(lfd_train_plan* pl, const void* input, int input_format, void* workspace, int use_graph, lfd_stream stream) {

@@ -477,14 +477,15 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
         dbs[i] = 0.f;
     }
     if (threadIdx.x == 0) dsc[0] = 0.f;
-    if (threadIdx.x < p.groups)
+    const bool gn = p.groups > 0;      // groups == 0: head without norm layers, `raw` is the already activated tensor
+    if (gn && threadIdx.x < p.groups)
         mean_rstd_from_sums(p.stats, n * p.groups + threadIdx.x, (double)p.HW * 8.0, p.eps, &s_mean[threadIdx.x], &s_rstd[threadIdx.x]);
     __syncthreads();
     const int sl = threadIdx.x & 7;
     float ga[16], be[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { ga[j] = p.gamma[sl * 16 + j]; be[j] = p.beta[sl * 16 + j]; }
-    const float m0 = s_mean[2 * sl], r0 = s_rstd[2 * sl], m1 = s_mean[2 * sl + 1], r1 = s_rstd[2 * sl + 1];
+    for (int j = 0; j < 16; ++j) { ga[j] = gn ? p.gamma[sl * 16 + j] : 1.f; be[j] = gn ? p.beta[sl * 16 + j] : 0.f; }
+    const float m0 = gn ? s_mean[2 * sl] : 0.f, r0 = gn ? s_rstd[2 * sl] : 1.f, m1 = gn ? s_mean[2 * sl + 1] : 0.f, r1 = gn ? s_rstd[2 * sl + 1] : 1.f;
     float dscale_acc = 0.f;
     float dwr[SMALL ? 5 : 1][16], dbr[SMALL ? 5 : 1];
 #pragma unroll
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
 }
 
 cudaError_t head_final_bwd_launch(const HeadFinalBwdParams& p, int num_sms, cudaStream_t st) {
-    if (p.C != 128 || p.groups != 16) return cudaErrorInvalidValue;
+    if (p.C != 128 || (p.groups != 16 && p.groups != 0)) return cudaErrorInvalidValue;
     const size_t smem = ((size_t)2 * p.n_out * p.C + 3 * p.n_out + 1 + 64) * sizeof(float);
     if (smem > 100 * 1024) return cudaErrorInvalidValue;
     static bool attr[kMaxDevices] = {};

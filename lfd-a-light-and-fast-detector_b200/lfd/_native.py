@@ -73,6 +73,9 @@ PACK_CONV_FWD, PACK_CONV_DGRAD, PACK_STEM, PACK_ROUND_F32, PACK_SCALE_SHIFT = ra
 UNPACK_CONV, UNPACK_ADD = 0, 1
 
 
+MAX_BRANCHES = 8          # LFD_MAX_BRANCHES
+
+
 class Top(C.Structure):
     _fields_ = [('kind', C.c_int32),
                 ('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('Cin', C.c_int32), ('Ho', C.c_int32), ('Wo', C.c_int32),
@@ -80,7 +83,7 @@ class Top(C.Structure):
                 ('relu', C.c_int32), ('groups', C.c_int32), ('cc', C.c_int32), ('n_cls', C.c_int32), ('n_reg', C.c_int32),
                 ('point_off', C.c_int32), ('P', C.c_int32), ('cls_stride', C.c_int32),
                 ('accumulate', C.c_int32), ('upH', C.c_int32), ('upW', C.c_int32), ('n_desc', C.c_int32), ('max_n', C.c_int32),
-                ('impl', C.c_int32), ('frozen', C.c_int32), ('pad_', C.c_int32), ('eps', C.c_float), ('momentum', C.c_float),
+                ('impl', C.c_int32), ('frozen', C.c_int32), ('branch', C.c_int32), ('wait_mask', C.c_int32), ('pad_', C.c_int32), ('eps', C.c_float), ('momentum', C.c_float),
                 ('off', C.c_int64 * 8), ('ptr', C.c_void_p * 6)]
 
 
@@ -157,7 +160,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.lfd_abi_version() != 4:
+    if L.lfd_abi_version() != 5:
         raise LfdError('liblfd_b200.so ABI version mismatch')
     _lib = L
     return L

@@ -16,6 +16,7 @@ OIHW gradient tensors at the end (UNPACK).
 Rounding points (bf16 training): conv output z (fp32 accumulate) -> bf16; BatchNorm statistics over the stored z (fp64 sums);
 normalised + residual + ReLU output -> bf16; every activation gradient -> bf16; weight / norm-parameter gradients fp32.
 """
+import os
 import ctypes as C
 
 import torch
@@ -113,6 +114,7 @@ class TrainPlan(object):
         self.N, self.H, self.W, self.device = N, H, W, device
         self.model = model
         self.create_native = create_native               # False: host-side planning only (CPU tests of the planner)
+        self.branches = os.environ.get('LFD_B200_TRAIN_BRANCHES', '1') != '0'      # per-level chains on side streams (0: one stream, A/B runs)
         self.flat = flat_parameters(model, allow_cpu=not create_native)
         self._off, self._top = {}, 256                  # workspace regions: name -> byte offset
         self._sizes = {}
@@ -120,6 +122,7 @@ class TrainPlan(object):
         self._layers = []                                # forward records, walked in reverse for the backward
         self._pack, self._unpack = _Table(nat.PackDesc), _Table(nat.UnpackDesc)
         self._wstage, self._gstage, self._hstage = {}, {}, {}
+        self._const = None                               # constant tensors of the no-norm head path
         self._grad_written = set()
         self._zero_fwd, self._zero_bwd = [], []          # (name) regions cleared at the start of the forward / backward
         self._check_supported(model)
@@ -192,7 +195,7 @@ class TrainPlan(object):
             self._fwd.append(dict(kind=nat.TOP_STEM0, off={1: z, 4: wp}, **geo))
             cc = 0
         else:
-            cc = nat.conv_query(self.N, h, w, cin, ho, wo, cout, k, s)['cc']
+            cc = self._query(self.N, h, w, cin, ho, wo, cout, k, s)['cc']
             wp = self._wpack(conv, nat.PACK_CONV_FWD, cc)
             self._fwd.append(dict(kind=nat.TOP_CONV, cc=cc, off={0: x, 1: z, 4: wp}, **geo))
         frozen = int(not norm.training)       # a BatchNorm2d in eval mode inside a training step (norm_eval / frozen stages): running statistics
@@ -207,18 +210,19 @@ class TrainPlan(object):
         return y, ho, wo
 
     def _conv_gn(self, name, conv, norm, x, h, w, last):
-        """1x1 conv -> GroupNorm (statistics from the conv epilogue) -> ReLU; `last`: the apply is fused into HEAD_FINAL."""
-        if conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.bias is not None:
-            raise NotImplementedError('head towers: 1x1 conv without bias followed by GroupNorm (the shipped configs)')
+        """1x1 / 3x3 conv -> GroupNorm (statistics from the conv epilogue) -> ReLU; `last`: the apply is fused into HEAD_FINAL."""
+        k = conv.kernel_size[0]
+        if conv.kernel_size not in ((1, 1), (3, 3)) or conv.stride != (1, 1) or conv.padding != (k // 2, k // 2) or conv.bias is not None:
+            raise NotImplementedError('head towers: 1x1 / 3x3 stride-1 conv without bias followed by GroupNorm')
         if not isinstance(norm, nn.GroupNorm) or norm.num_groups != 16 or norm.num_channels != 128 or not norm.affine:
             raise NotImplementedError('head towers need GroupNorm(16, 128) with affine parameters')
         cin, cout = conv.in_channels, conv.out_channels
         raw = self._act(name + '_raw', h, w, cout)
         stats = self._alloc(name + '_gnstats', self.N * 16 * 2 * 8)
         self._zero_fwd.append(stats)
-        cc = nat.conv_query(self.N, h, w, cin, h, w, cout, 1, 1)['cc']
+        cc = self._query(self.N, h, w, cin, h, w, cout, k, 1)['cc']
         wp = self._wpack(conv, nat.PACK_CONV_FWD, cc)
-        geo = dict(N=self.N, H=h, W=w, Cin=cin, Ho=h, Wo=w, Cout=cout, ksize=1, stride=1)
+        geo = dict(N=self.N, H=h, W=w, Cin=cin, Ho=h, Wo=w, Cout=cout, ksize=k, stride=1)
         self._fwd.append(dict(kind=nat.TOP_CONV, cc=cc, groups=16, off={0: x, 1: raw, 3: stats, 4: wp}, **geo))
         act = None
         if not last:
@@ -227,6 +231,39 @@ class TrainPlan(object):
                                   ptr={0: norm.weight, 1: norm.bias}))
         self._layers.append(dict(type='gn', name=name, conv=conv, norm=norm, x=x, raw=raw, act=act, stats=stats, geo=geo))
         return raw, act, stats
+
+    @staticmethod
+    def _query(*a):
+        try:
+            return nat.conv_query(*a)
+        except nat.LfdError as e:          # e.g. a 16-channel data gradient (FastestBlock bodies below 32 channels)
+            raise NotImplementedError('native training: %s' % e)
+
+    def _conv_bias(self, name, conv, x, h, w):
+        """conv + bias + ReLU of a head tower without norm layers (TrafficLight configs, lfd_head.py norm_cfg=None): evaluated as conv ->
+        'frozen BatchNorm' with constant statistics (mean 0, variance 1 - eps, gamma 1, beta = the conv's bias): y = relu(z + bias), and in the
+        backward dz = g, d bias = sum g -- no extra kernels."""
+        k = conv.kernel_size[0]
+        if conv.kernel_size not in ((1, 1), (3, 3)) or conv.stride != (1, 1) or conv.padding != (k // 2, k // 2) or conv.bias is None:
+            raise NotImplementedError('head towers without norm: 1x1 / 3x3 stride-1 conv with bias')
+        cin, cout = conv.in_channels, conv.out_channels
+        z, y = self._act(name + '_z', h, w, cout), self._act(name, h, w, cout)
+        cc = self._query(self.N, h, w, cin, h, w, cout, k, 1)['cc']
+        wp = self._wpack(conv, nat.PACK_CONV_FWD, cc)
+        geo = dict(N=self.N, H=h, W=w, Cin=cin, Ho=h, Wo=w, Cout=cout, ksize=k, stride=1)
+        self._fwd.append(dict(kind=nat.TOP_CONV, cc=cc, off={0: x, 1: z, 4: wp}, **geo))
+        if self._const is None:
+            dev = self.flat.data.device
+            self._const = dict(ones=torch.ones(256, device=dev), zeros=torch.zeros(256, device=dev), var=torch.full((256,), 1.0 - 1e-5, device=dev),
+                               sink=torch.zeros(256, device=dev))
+        c = self._const
+        bn_geo = dict(N=self.N, H=h, W=w, Cout=cout, eps=1e-5, frozen=1)
+        self._fwd.append(dict(kind=nat.TOP_BN_APPLY, relu=1, momentum=0.0, off={0: z, 1: y}, ptr={0: c['ones'], 1: conv.bias, 2: c['zeros'], 3: c['var']}, **bn_geo))
+        import types
+        fake = types.SimpleNamespace(weight=c['ones'], bias=conv.bias, running_mean=c['zeros'], running_var=c['var'], eps=1e-5)
+        self._layers.append(dict(type='bn', name=name, conv=conv, norm=fake, relu=True, x=x, z=z, y=y, res=None, sums=None, geo=geo, frozen=1,
+                                 dgamma=c['sink'], dbeta=('grad', conv.bias)))
+        return y
 
     def _head_final(self, name, l, raw, stats, norm, convs, n_cls, n_reg, h, w, point_off, scale_param):
         """convs = [final conv, ...] whose outputs are concatenated (classification rows first)."""
@@ -261,9 +298,13 @@ class TrainPlan(object):
             dscale = self._alloc('%s_dscale' % name, 4)
             self._zero_bwd.append(dscale)
             self._unpack.items.append(dict(kind=nat.UNPACK_ADD, n=1, src=dscale, dst=scale_param))
-        geo = dict(N=self.N, H=h, W=w, Cout=Cc, groups=16, n_cls=n_cls, n_reg=n_reg, P=None, point_off=point_off, cls_stride=None, eps=float(norm.eps))
-        self._fwd.append(dict(kind=nat.TOP_HEAD_FINAL, off={0: raw, 3: stats, 4: lst}, ptr={0: norm.weight, 1: norm.bias, 2: 'cls', 3: 'reg'}, **geo))
-        self._layers.append(dict(type='final', name=name, raw=raw, stats=stats, norm=norm, stage=lst, dstage=ds, dscale=dscale, geo=geo))
+        gn = norm is not None          # None: the tower has no norm layers, `raw` is already the activated tensor
+        geo = dict(N=self.N, H=h, W=w, Cout=Cc, groups=16 if gn else 0, n_cls=n_cls, n_reg=n_reg, P=None, point_off=point_off, cls_stride=None,
+                   eps=float(norm.eps) if gn else 1e-5)
+        nptr = {0: norm.weight, 1: norm.bias} if gn else {}
+        self._fwd.append(dict(kind=nat.TOP_HEAD_FINAL, off={0: raw, 3: stats, 4: lst}, ptr={**nptr, 2: 'cls', 3: 'reg'}, **geo))
+        self._layers.append(dict(type='final', name=name, raw=raw, stats=stats, norm=norm, stage=lst, dstage=ds, dscale=dscale, geo=geo,
+                                 dact='d_' + (raw + '_act' if gn else raw)))
 
     # ------------------------------------------------------------------ graph walk (same order as the inference plan)
     def _build(self, model):
@@ -304,7 +345,14 @@ class TrainPlan(object):
                 cur, h, w = x, hh, ww
                 if (si, bi) in taps:
                     l = taps.index((si, bi))
+                    f0, l0 = len(self._fwd), len(self._layers)
                     self._level(neck, head, l, cur, h, w, offs[l])
+                    # the level's neck + head chain depends on the tap only: its own branch (side stream), in the forward and in the backward
+                    br = (1 + l % (nat.MAX_BRANCHES - 1)) if self.branches else 0
+                    for op in self._fwd[f0:]:
+                        op['branch'] = br
+                    for L in self._layers[l0:]:
+                        L['branch'] = br
 
     def _level(self, neck, head, l, fname, fh, fw, point_off):
         conv, norm = neck.level(l)
@@ -315,8 +363,12 @@ class TrainPlan(object):
         def tower(t, tag):
             x = nk
             for ti, (tconv, tnorm) in enumerate(t):
-                raw, act, stats = self._conv_gn('h%d%s%d' % (l, tag, ti), tconv, tnorm, x, fh, fw, last=ti == len(t) - 1)
-                x = act
+                if tnorm is None:
+                    x = self._conv_bias('h%d%s%d' % (l, tag, ti), tconv, x, fh, fw)
+                    raw, stats = x, None
+                else:
+                    raw, act, stats = self._conv_gn('h%d%s%d' % (l, tag, ti), tconv, tnorm, x, fh, fw, last=ti == len(t) - 1)
+                    x = act
             return raw, stats, t[-1][1]
 
         if cls_tower is reg_tower:
@@ -346,7 +398,7 @@ class TrainPlan(object):
         self._bwd.append(dict(kind=nat.TOP_WGRAD, impl=nat.WGRAD_UMMA, off={0: x, 1: dz, 5: gs}, **geo))
         # data gradient = the forward kernel on the transposed / tap-flipped weights (stride 2: on the zero-inserted dz)
         k, s, cin, cout, h, w = geo['ksize'], geo['stride'], geo['Cin'], geo['Cout'], geo['H'], geo['W']
-        cc = nat.conv_query(self.N, h, w, cout, h, w, cin, k, 1)['cc']
+        cc = self._query(self.N, h, w, cout, h, w, cin, k, 1)['cc']
         wp = self._wpack(conv, nat.PACK_CONV_DGRAD, cc)
         dx = self._grad_of(x, h, w, cin)
         acc = dx in self._grad_written
@@ -355,52 +407,133 @@ class TrainPlan(object):
         self._grad_written.add(dx)
 
     def _build_backward(self):
-        for L in reversed(self._layers):
-            geo = L['geo']
-            if L['type'] == 'final':
-                dact = self._grad_of(L['raw'] + '_act', geo['H'], geo['W'], 128)
-                self._bwd.append(dict(kind=nat.TOP_HEAD_FINAL_BWD, off={0: L['raw'], 1: dact, 3: L['stats'], 4: L['stage'], 5: L['dstage'], 6: L['dscale']},
-                                      ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: 'gcls', 3: 'greg'}, **geo))
-                self._grad_written.add(dact)
-            elif L['type'] == 'gn':
-                h, w, cout = geo['H'], geo['W'], geo['Cout']
-                dact = 'd_' + (L['act'] if L['act'] is not None else L['raw'] + '_act')
-                if dact not in self._grad_written:
-                    raise RuntimeError('gradient of %s is never produced' % L['name'])
-                bs = self._alloc(L['name'] + '_bsums', (cout * 2 + self.N * 16 * 2) * 8)
-                self._zero_bwd.append(bs)
-                draw = self._grad_of(L['raw'], h, w, cout)
-                n_geo = dict(N=self.N, H=h, W=w, Cout=cout, groups=16, relu=1, eps=float(L['norm'].eps))
-                offs = {0: dact, 2: L['raw'], 3: L['stats'], 4: bs}
-                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias}, **n_geo))
-                offs[5] = draw
-                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_APPLY, off=offs, ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: ('grad', L['norm'].weight),
-                                                                               3: ('grad', L['norm'].bias)}, **n_geo))
-                self._emit_conv_backward(L, draw, None)
+        # level chains first: they only need the loss gradients, so they start at once on their side streams and are the first writers of
+        # the taps' gradients; the backbone (main stream) accumulates into those and waits for the level's branch there (_assign_waits)
+        order = [L for L in reversed(self._layers) if L.get('branch', 0)] + [L for L in reversed(self._layers) if not L.get('branch', 0)]
+        for L in order:
+            b0 = len(self._bwd)
+            self._backward_of(L)
+            for op in self._bwd[b0:]:
+                op['branch'] = L.get('branch', 0)
+
+    def _backward_of(self, L):
+        geo = L['geo']
+        if L['type'] == 'final':
+            dact = L['dact']
+            acc = dact in self._grad_written          # (never: every tower has its own last tensor)
+            if acc:
+                raise RuntimeError('two head-final ops share one tower output')
+            if dact not in self._sizes:
+                self._act(dact, geo['H'], geo['W'], 128)
+            nptr = {0: L['norm'].weight, 1: L['norm'].bias} if L['norm'] is not None else {}
+            self._bwd.append(dict(kind=nat.TOP_HEAD_FINAL_BWD, off={0: L['raw'], 1: dact, 3: L['stats'], 4: L['stage'], 5: L['dstage'], 6: L['dscale']},
+                                  ptr={**nptr, 2: 'gcls', 3: 'greg'}, **geo))
+            self._grad_written.add(dact)
+        elif L['type'] == 'gn':
+            h, w, cout = geo['H'], geo['W'], geo['Cout']
+            dact = 'd_' + (L['act'] if L['act'] is not None else L['raw'] + '_act')
+            if dact not in self._grad_written:
+                raise RuntimeError('gradient of %s is never produced' % L['name'])
+            bs = self._alloc(L['name'] + '_bsums', (cout * 2 + self.N * 16 * 2) * 8)
+            self._zero_bwd.append(bs)
+            draw = self._grad_of(L['raw'], h, w, cout)
+            n_geo = dict(N=self.N, H=h, W=w, Cout=cout, groups=16, relu=1, eps=float(L['norm'].eps))
+            offs = {0: dact, 2: L['raw'], 3: L['stats'], 4: bs}
+            self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias}, **n_geo))
+            offs[5] = draw
+            self._bwd.append(dict(kind=nat.TOP_NORM_BWD_APPLY, off=offs, ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: ('grad', L['norm'].weight),
+                                                                           3: ('grad', L['norm'].bias)}, **n_geo))
+            self._emit_conv_backward(L, draw, None)
+        else:
+            ho, wo, cout, s = geo['Ho'], geo['Wo'], geo['Cout'], geo['stride']
+            dy = 'd_' + L['y']
+            if dy not in self._grad_written:
+                raise RuntimeError('gradient of %s is never produced' % L['name'])
+            bs = self._alloc(L['name'] + '_bsums', cout * 16)
+            self._zero_bwd.append(bs)
+            dz = self._grad_of(L['z'], ho, wo, cout)
+            need_up = s == 2 and L['x'] is not None
+            dz_up = self._act('d_' + L['z'] + '_up', geo['H'], geo['W'], cout) if need_up else None
+            dres, acc = None, 0
+            if L['res'] is not None:
+                dres = self._grad_of(L['res'], ho, wo, cout)
+                acc = int(dres in self._grad_written)
+                self._grad_written.add(dres)
+            n_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, groups=0, relu=int(L['relu']), eps=float(L['norm'].eps), frozen=L['frozen'])
+            offs = {0: dy, 1: L['y'] if L['relu'] else None, 2: L['z'], 3: L['sums'], 4: bs}
+            rstats = {4: L['norm'].running_mean, 5: L['norm'].running_var}
+            self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias, 4: rstats[4], 5: rstats[5]}, **n_geo))
+            offs.update({5: dz, 6: dz_up, 7: dres})
+            self._bwd.append(dict(kind=nat.TOP_NORM_BWD_APPLY, accumulate=acc, upH=geo['H'] if need_up else 0, upW=geo['W'] if need_up else 0, off=offs,
+                                  ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: L.get('dgamma', ('grad', L['norm'].weight)), 3: L.get('dbeta', ('grad', L['norm'].bias)),
+                                       4: rstats[4], 5: rstats[5]},
+                                  **n_geo))
+            self._emit_conv_backward(L, dz, dz_up)
+
+    # role of every off[] entry (include/lfd_b200.h, lfd_top table): R read, W write / read-modify-write, A atomic accumulation (commutes)
+    _ROLES = {nat.TOP_STEM0: {1: 'W', 3: 'A', 4: 'R'}, nat.TOP_CONV: {0: 'R', 1: 'W', 2: 'R', 3: 'A', 4: 'R'},
+              nat.TOP_BN_STATS: {0: 'R', 3: 'A'}, nat.TOP_BN_APPLY: {0: 'R', 1: 'W', 2: 'R', 3: 'R'}, nat.TOP_GN_APPLY: {0: 'R', 1: 'W', 3: 'R'},
+              nat.TOP_HEAD_FINAL: {0: 'R', 3: 'R', 4: 'R'}, nat.TOP_HEAD_FINAL_BWD: {0: 'R', 1: 'W', 3: 'R', 4: 'R', 5: 'A', 6: 'A'},
+              nat.TOP_NORM_BWD_REDUCE: {0: 'R', 1: 'R', 2: 'R', 3: 'R', 4: 'A'},
+              nat.TOP_NORM_BWD_APPLY: {0: 'R', 1: 'R', 2: 'R', 3: 'R', 4: 'R', 5: 'W', 6: 'W', 7: 'W'},
+              nat.TOP_WGRAD: {0: 'R', 1: 'R', 5: 'A'}, nat.TOP_WGRAD_STEM: {0: 'W', 1: 'R', 5: 'A'}}
+
+    @classmethod
+    def _assign_waits(cls, ops):
+        """wait_mask of every op from the hazards between branches: an op waits for branch w when it touches a tensor that an op of w
+        wrote (or, for a write, read / accumulated into) earlier in the list.  PACK / ZERO / UNPACK (no named tensors) are barriers: they sit
+        on the main stream before the first fork resp. wait for every branch.  (Parameters and their gradients are absolute pointers: read-only
+        resp. atomic accumulations, no ordering needed.)"""
+        seq, synced, state, started = {0: -1}, {}, {}, set()
+        for op in ops:
+            b = op.get('branch', 0)
+            if b and b not in started:
+                started.add(b)
+                seq[b] = -1
+                synced[(b, 0)] = seq[0]
+            need = {}
+
+            def after(entry):
+                if entry is not None and entry[0] != b and synced.get((b, entry[0]), -1) < entry[1]:
+                    need[entry[0]] = max(need.get(entry[0], -1), entry[1])
+            roles = cls._ROLES.get(op['kind'])
+            if roles is None:                                   # PACK / ZERO / UNPACK
+                if b:
+                    raise RuntimeError('PACK / ZERO / UNPACK belong on the main stream')
+                for w in started:
+                    need[w] = seq[w]
             else:
-                ho, wo, cout, s = geo['Ho'], geo['Wo'], geo['Cout'], geo['stride']
-                dy = 'd_' + L['y']
-                if dy not in self._grad_written:
-                    raise RuntimeError('gradient of %s is never produced' % L['name'])
-                bs = self._alloc(L['name'] + '_bsums', cout * 16)
-                self._zero_bwd.append(bs)
-                dz = self._grad_of(L['z'], ho, wo, cout)
-                need_up = s == 2 and L['x'] is not None
-                dz_up = self._act('d_' + L['z'] + '_up', geo['H'], geo['W'], cout) if need_up else None
-                dres, acc = None, 0
-                if L['res'] is not None:
-                    dres = self._grad_of(L['res'], ho, wo, cout)
-                    acc = int(dres in self._grad_written)
-                    self._grad_written.add(dres)
-                n_geo = dict(N=self.N, H=ho, W=wo, Cout=cout, groups=0, relu=int(L['relu']), eps=float(L['norm'].eps), frozen=L['frozen'])
-                offs = {0: dy, 1: L['y'] if L['relu'] else None, 2: L['z'], 3: L['sums'], 4: bs}
-                rstats = {4: L['norm'].running_mean, 5: L['norm'].running_var}
-                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_REDUCE, off=dict(offs), ptr={0: L['norm'].weight, 1: L['norm'].bias, 4: rstats[4], 5: rstats[5]}, **n_geo))
-                offs.update({5: dz, 6: dz_up, 7: dres})
-                self._bwd.append(dict(kind=nat.TOP_NORM_BWD_APPLY, accumulate=acc, upH=geo['H'] if need_up else 0, upW=geo['W'] if need_up else 0, off=offs,
-                                      ptr={0: L['norm'].weight, 1: L['norm'].bias, 2: ('grad', L['norm'].weight), 3: ('grad', L['norm'].bias), 4: rstats[4], 5: rstats[5]},
-                                      **n_geo))
-                self._emit_conv_backward(L, dz, dz_up)
+                touched = {}
+                for j, name in op.get('off', {}).items():
+                    if name is None:
+                        continue
+                    r = roles[j]
+                    touched[name] = 'W' if 'W' in (r, touched.get(name)) else ('A' if 'A' in (r, touched.get(name)) else 'R')
+                for name, r in touched.items():
+                    st = state.setdefault(name, dict(w=None, r={}, a={}))
+                    after(st['w'])
+                    if r in ('W', 'A'):
+                        for e in st['r'].items():
+                            after(e)
+                    if r in ('W', 'R'):
+                        for e in st['a'].items():
+                            after(e)
+            mask = 0
+            for w in need:
+                mask |= 1 << w
+                synced[(b, w)] = seq[w]
+            seq[b] += 1
+            me = seq[b]
+            if roles is not None:
+                for name, r in touched.items():
+                    st = state[name]
+                    if r == 'W':
+                        st['w'], st['r'], st['a'] = (b, me), {}, {}
+                    elif r == 'A':
+                        st['a'][b] = me
+                    else:
+                        st['r'][b] = me
+            op['wait_mask'] = mask
 
     def _layout(self):
         """Byte offsets: [regions cleared before the forward][regions cleared before the backward][everything else]."""
@@ -459,6 +592,9 @@ class TrainPlan(object):
 
         fwd = [dict(kind=nat.TOP_PACK, n_desc=len(self._pack.items), max_n=self._pack.max_n, ptr={0: pack_t})] + zero_ops(self._zero_fwd) + self._fwd
         bwd = zero_ops(self._zero_bwd) + self._bwd + [dict(kind=nat.TOP_UNPACK, n_desc=len(self._unpack.items), max_n=self._unpack.max_n, ptr={0: unpack_t})]
+
+        self._assign_waits(fwd)
+        self._assign_waits(bwd)
 
         def to_array(ops):
             arr = (nat.Top * len(ops))()

@@ -33,7 +33,8 @@ def _pair(cfg, cls_bias=-2.0):
     return a.cuda().train(), b.cuda().train()
 
 
-@pytest.mark.parametrize('cfg,frozen', [('WIDERFACE_XS', False), ('WIDERFACE_L', False), ('TT100K_S', False), ('WIDERFACE_S', True)])
+@pytest.mark.parametrize('cfg,frozen', [('WIDERFACE_XS', False), ('WIDERFACE_L', False), ('TT100K_S', False), ('WIDERFACE_S', True), ('TL_L', False),
+                                        ('TEST_FAST', False)])
 def test_native_train_forward_matches_aten(cfg, frozen):
     """Train-mode forward (batch statistics; `frozen`: BatchNorm modules in eval mode, as with norm_eval): native bf16 plan vs ATen fp32
     on the same weights -- outputs inside the bf16 drift of DESIGN.md gate C, identical wiring / layout, running statistics updated
@@ -60,13 +61,16 @@ def test_native_train_forward_matches_aten(cfg, frozen):
         assert rel_err(a, b)[1] < 3e-2, ('vs bf16-emulated', rel_err(a, b))
         assert rel_err(a, c)[1] < 6e-2, ('vs fp32', rel_err(a, c))
         assert rel_err(a, c)[1] < 2.5 * max(rel_err(b, c)[1], 1e-2), ('drift vs the emulation\'s own drift', rel_err(a, c), rel_err(b, c))
-    worst = 0.0
-    for (name, ba), (_, bb_) in zip(model.named_buffers(), ref.named_buffers()):
+    worst, worst_emu = 0.0, 0.0
+    for (name, ba), (_, bb_), (_, be) in zip(model.named_buffers(), ref.named_buffers(), emu.named_buffers()):
         if ba.dtype.is_floating_point:
             worst = max(worst, float((ba - bb_).abs().max() / bb_.abs().max().clamp(min=1e-6)))
+            worst_emu = max(worst_emu, float((be - bb_).abs().max() / bb_.abs().max().clamp(min=1e-6)))
         else:
             assert torch.equal(ba, bb_), name          # num_batches_tracked
-    assert worst < 2e-2, worst
+    # running statistics: within the drift the bf16-emulated ATen graph itself shows against fp32 (the deepest stage has < 100 samples per
+    # channel at this input size; tests/debug_bn_buffers.py prints the per-buffer table)
+    assert worst < 2.0 * max(worst_emu, 1e-2), (worst, worst_emu)
 
 
 def _teacher_forced_backward_check(cfg, n, h, w):
@@ -127,7 +131,10 @@ def _teacher_forced_backward_check(cfg, n, h, w):
             hh, ww = geo['H'], geo['W']
             raw = nhwc(L['raw'], hh, ww, 128)
             norm = L['norm']
-            t = bf(F.relu(F.group_norm(raw, 16, norm.weight.detach(), norm.bias.detach(), norm.eps))).requires_grad_(True)
+            if norm is None:               # tower without norm layers: raw is the activated tensor
+                t = raw.clone().requires_grad_(True)
+            else:
+                t = bf(F.relu(F.group_norm(raw, 16, norm.weight.detach(), norm.bias.detach(), norm.eps))).requires_grad_(True)
             # the convs / Scale of this level, from the staging the native kernel read (bf16-rounded weights)
             no = geo['n_cls'] + geo['n_reg']
             off = plan._off[L['stage']]
@@ -142,7 +149,7 @@ def _teacher_forced_backward_check(cfg, n, h, w):
             po, HW = geo['point_off'], hh * ww
             up = torch.cat([plan.gcls[:, po:po + HW, :geo['n_cls']], plan.greg[:, po:po + HW, :geo['n_reg']]], -1)
             o.backward(up.permute(0, 2, 1).reshape(n, no, hh, ww))
-            dact = nhwc('d_' + L['raw'] + '_act', hh, ww, 128)
+            dact = nhwc(L['dact'], hh, ww, 128)
             note('head dact', L['name'], rel(dact, t.grad), 1e-2)
             L['_exp'] = (Wm.grad, bias.grad, scale_leaf.grad, sc)
             continue
@@ -163,7 +170,10 @@ def _teacher_forced_backward_check(cfg, n, h, w):
         norm = L['norm']
         z = nhwc(L['z'], ho, wo, c).requires_grad_(True)
         g, b = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
-        yt = F.batch_norm(z, None, None, g, b, training=True, eps=norm.eps)
+        if L.get('frozen'):                # conv + bias + ReLU of a no-norm tower, planned as a frozen BatchNorm with constant statistics
+            yt = F.batch_norm(z, norm.running_mean[:c], norm.running_var[:c], g[:c], b, training=False, eps=norm.eps)
+        else:
+            yt = F.batch_norm(z, None, None, g, b, training=True, eps=norm.eps)
         res = None
         if L['res'] is not None:
             res = nhwc(L['res'], ho, wo, c).requires_grad_(True)
@@ -175,7 +185,8 @@ def _teacher_forced_backward_check(cfg, n, h, w):
         yt.backward(nhwc('d_' + L['y'], ho, wo, c))
         dz = nhwc('d_' + L['z'], ho, wo, c)
         note('bn dz', L['name'], rel(dz, z.grad), 1.2e-2)
-        add_param(norm.weight, g.grad)
+        if not L.get('frozen'):
+            add_param(norm.weight, g.grad)
         add_param(norm.bias, b.grad)
         if res is not None:
             exp_grad[L['res']] = exp_grad.get(L['res'], 0) + res.grad
@@ -211,7 +222,8 @@ def _teacher_forced_backward_check(cfg, n, h, w):
     print('%s teacher-forced backward: %s' % (cfg, {k: '%.1e (%s)' % v for k, v in worst.items()}))
 
 
-@pytest.mark.parametrize('cfg,shape', [('WIDERFACE_XS', (2, 160, 192)), ('WIDERFACE_L', (2, 128, 160)), ('TT100K_S', (2, 160, 160)), ('TT100K_L', (1, 128, 128))])
+@pytest.mark.parametrize('cfg,shape', [('WIDERFACE_XS', (2, 160, 192)), ('WIDERFACE_L', (2, 128, 160)), ('TT100K_S', (2, 160, 160)), ('TT100K_L', (1, 128, 128)),
+                                       ('TL_L', (2, 128, 160)), ('TEST_FAST', (2, 128, 128))])
 def test_native_backward_teacher_forced(cfg, shape):
     _teacher_forced_backward_check(cfg, *shape)
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = nat.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.lfd_abi_version() == 4
+    assert lib.lfd_abi_version() == 5
 
 
 def test_conv_query_is_host_only_and_rejects_unsupported():
@@ -179,3 +179,63 @@ def test_build_guard_rejects_large_stack_frames():
     with pytest.raises(RuntimeError):
         b._check_stack_frames(bad)
     b._check_stack_frames(bad.replace('conv_umma_kernel', 'some_other_kernel'))
+
+
+@pytest.mark.parametrize('name', ['WIDERFACE_L', 'TT100K_S', 'TL_L', 'TEST_FAST'])
+def test_training_plan_branches_order_every_conflict(name):
+    """The training planner puts every level's neck + head chain on its own branch (side stream) and derives the wait masks from the
+    read / write / accumulate role of each operand.  Replay the fork / wait protocol of lfd_train_plan_run with vector clocks and check
+    that every pair of ops that conflict on a workspace tensor (write vs anything, accumulate vs read) is ordered."""
+    from lfd._train import TrainPlan
+    model, _ = synth_model(name)
+    model.train()
+    plan = TrainPlan(model, 2, 128, 160, torch.device('cpu'), create_native=False)
+    assert plan.branches
+    for ops in (plan.fwd_ops, plan.bwd_ops):
+        branches = sorted({op.get('branch', 0) for op in ops})
+        assert branches[0] == 0 and len(branches) == 1 + len(plan.level_sizes) and branches[-1] < nat.MAX_BRANCHES
+        clock, last, seq, info = [], {}, {}, []
+        for i, op in enumerate(ops):
+            b = op.get('branch', 0)
+            if b in last:
+                vc = dict(clock[last[b]])
+            else:
+                vc = dict(clock[last[0]]) if 0 in last else {}       # fork after the preceding main-stream op
+            for w in range(nat.MAX_BRANCHES):
+                if (op['wait_mask'] >> w) & 1 and w in last:
+                    for k, v in clock[last[w]].items():
+                        vc[k] = max(vc.get(k, -1), v)
+            seq[b] = seq.get(b, -1) + 1
+            vc[b] = seq[b]
+            clock.append(vc)
+            last[b] = i
+            roles = TrainPlan._ROLES.get(op['kind'])
+            acc = {}
+            if roles is not None:
+                for j, nm in op.get('off', {}).items():
+                    if nm is not None:
+                        acc.setdefault(nm, set()).add(roles[j])
+            info.append((b, seq[b], acc, roles is None))
+        by_name = {}
+        n_pairs = 0
+        for j, (bj, sj, accj, barrier) in enumerate(info):
+            if barrier:                                              # PACK / ZERO / UNPACK: ordered against everything before
+                for i in range(j):
+                    bi, si = info[i][0], info[i][1]
+                    assert clock[j].get(bi, -1) >= si, (name, 'barrier', i, j)
+                continue
+            for nm, rj in accj.items():
+                for (i, ri) in by_name.get(nm, []):
+                    bi, si = info[i][0], info[i][1]
+                    if bi == bj:
+                        continue
+                    conflict = 'W' in ri or 'W' in rj or (('A' in ri) != ('A' in rj)) or (('A' in ri) and ('R' in ri or 'R' in rj))
+                    if conflict:
+                        n_pairs += 1
+                        assert clock[j].get(bi, -1) >= si, (name, nm, i, j, ops[i]['kind'], ops[j]['kind'])
+                by_name.setdefault(nm, []).append((j, rj))
+        if ops is plan.bwd_ops:
+            assert n_pairs >= len(plan.level_sizes)                  # at least the taps' gradients: level chain writes, backbone accumulates
+    # the backward starts every level chain before the backbone
+    first_main = next(i for i, op in enumerate(plan.bwd_ops) if op.get('branch', 0) == 0 and op['kind'] not in (nat.TOP_ZERO,))
+    assert all(op.get('branch', 0) == 0 for op in plan.bwd_ops[first_main:])

@@ -357,6 +357,12 @@ def train_main(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return 0
+    step(0)                                   # set-up: builds the plans
+    sync_all()
+    tuned = {}
+    if not args.no_autotune and not args.no_graph:
+        for p_ in model._train_plans.values():
+            tuned = p_.autotune()             # set-up: CTA bounds of the side-branch kernels, picked by timing the replayed graphs
     for i in range(max(warmup, 3)):           # W warm-up steps (the first ones also capture the forward / backward CUDA graphs)
         lv = step(i)
     sync_all()
@@ -493,6 +499,7 @@ def train_main(args):
                 scaling='weak', vs_baseline=None, dtype=wl['dtype'], data='synthetic', config=config,
                 impl_detail=dict(timed_blocks=blocks, block_ms=[round(v, 3) for v in block_ms[:16]], timed_s=ms_total / 1e3, loss_first_last=[losses[0], losses[-1]],
                                  cuda_graph=bool(model.use_cuda_graph_training), launches_per_step=launches,
+                                 side_branch_ctas={k: {str(b): c for b, c in v['ctas'].items()} for k, v in tuned.items()},
                                  workspace_gb=plan.workspace_bytes / 1e9, parameters=int(flat.numel),
                                  l2='the %.1f GB activation / gradient workspace is rewritten every step; inputs rotate over %d batches' % (plan.workspace_bytes / 1e9, npool),
                                  label_assign_ms=assign_ms, label_assign_reference_cpu_ms=assign_cpu_ms,
@@ -603,6 +610,7 @@ def main():
     ap.add_argument('--conv-impl', default='umma', choices=['umma', 'simt'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-autotune', action='store_true', help='skip InferencePlan.autotune (CTA bounds of the side-branch convs)')
     ap.add_argument('--min-timed-s', type=float, default=0.5, help='the K-step timed block is repeated until this much time has been timed')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op timing table to stderr')
     ap.add_argument('--ncu-step', action='store_true',
@@ -660,6 +668,8 @@ def main():
     host_pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(npool)]
     plan = model.inference_plan(N, H, W, dev)
+    if not args.no_autotune and not args.no_graph and not args.ncu_step:
+        plan.autotune()                     # set-up: CTA bounds of the side-branch convs, picked by timing the replayed graph
     for i, hw in enumerate(plan.level_sizes):
         model._head_indexes_to_feature_map_sizes[i] = hw
     post = model.post_plan(N, plan.level_sizes, dev)
@@ -693,7 +703,10 @@ def main():
             torch.cuda.profiler.stop()
         return 0
     with torch.no_grad():
-        for i in range(npool):                 # set-up, not warm-up: instantiates one CUDA graph per pool buffer
+        for i in range(npool):                 # set-up, not warm-up: instantiates one CUDA graph per (pool buffer, output slot) pair;
+            step(i)                            # the slots alternate per step, so the pool is walked twice with one step in between
+        step(0)
+        for i in range(npool):
             step(i)
         sync_all()
         # size the number of timed blocks from a short probe so that >= min_timed_s are timed whatever --steps is
@@ -741,8 +754,11 @@ def main():
         sync_all()
         t0 = time.perf_counter()
         pending = []                           # up to depth - 1 batches stay in flight behind the one being submitted
+        host_submit_s = 0.0
         for i in range(e2e_steps):
+            ts = time.perf_counter()
             pending.append(det.submit(host_pool[i % 2]))
+            host_submit_s += time.perf_counter() - ts
             if len(pending) >= det.depth:
                 det.collect(pending.pop(0))
         while pending:
@@ -832,15 +848,17 @@ def main():
                 config=config,
                 impl_detail=dict(score_thr=score_thr, detections_last_step=counts[:N],
                                  timed_blocks=blocks, block_ms=[round(v, 4) for v in block_ms[:16]], timed_s=ms_total / 1e3,
-                                 setup_steps=npool,
+                                 setup_steps=2 * npool + 1,
                                  l2='inputs rotate over a %d-batch pool (%.0f MB > L2); the %.0f MB activation workspace is rewritten every step'
                                     % (npool, npool * N * H * W * 3 / 1e6, plan.workspace_bytes / 1e6),
                                  cuda_graph=model.use_cuda_graph, conv_impl=args.conv_impl, launches_per_step=plan.num_launches + 2,
+                                 side_branch_ctas={str(b): c for b, c in plan.side_ctas.items()},
+                                 autotune=[(k, round(v, 4)) for k, v in getattr(plan, 'autotune_log', [])],
                                  pipelining='post-process of batch i overlaps the forward of batch i+1 (two streams, two output slots)'),
                 clocks=clocks, gpu_launches=(plan.num_launches + 2) * args.steps * blocks,
                 e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=det.h2d_bytes, d2h_bytes_per_step=det.d2h_bytes, steps=e2e_steps,
                          h2d_copy_alone_ms=h2d_ms, h2d_gbps=det.h2d_bytes / (h2d_ms * 1e-3) / 1e9, h2d_gbps_per_rank=h2d_per_rank,
-                         copy_streams=len(det.copy_streams), host_numa_node=numa_node,
+                         copy_streams=len(det.copy_streams), host_numa_node=numa_node, host_submit_ms_per_step=host_submit_s / e2e_steps * 1e3,
                          note='pinned host uint8 frames -> device -> detections -> pinned host; copy / forward / post-process pipelined on three streams'),
                 roofline=roofline)
     if cpu is not None:

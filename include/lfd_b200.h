@@ -49,6 +49,9 @@ typedef void* lfd_stream; /* cudaStream_t */
 typedef struct lfd_plan lfd_plan;
 
 int lfd_abi_version(void);
+/* sizeof of the structs of this header as the library was compiled, for bindings that mirror them field by field (ctypes, cffi):
+ * which = 0 lfd_op, 1 lfd_top, 2 lfd_pack_desc, 3 lfd_unpack_desc; -1 for anything else. */
+int lfd_struct_bytes(int which);
 const char* lfd_last_error(void);
 /* number of SMs of the current device (0 + error when there is no usable device) */
 int lfd_device_sm_count(void);
@@ -107,6 +110,10 @@ typedef struct lfd_op {
      * ds_out_off.  ds_weight = bf16 packed [Cin/8][ds_cout][8] with the BatchNorm scale folded in.  0 = none. */
     int32_t ds_cout;
     int32_t dtype; /* LFD_DTYPE_*: 16-bit type of this op's activations AND packed weights (every op of one plan uses the same) */
+    int32_t max_ctas; /* STEM0 / CONV: upper bound on the persistent CTAs of this layer, 0 = one per SM slot.  The CTAs of a large side-branch
+                         layer hold their SMs for the whole layer; bounding them leaves SMs to the small, latency-bound layers of the
+                         critical path that run concurrently (lfd/_engine.py::InferencePlan.autotune picks the bounds by timing). */
+    int32_t pad_;
     int64_t ds_out_off;
     const void* ds_weight;
     const float* ds_shift;
@@ -283,7 +290,7 @@ typedef struct lfd_top {
                                   everything enqueued so far on branch w.  The per-level neck / head chains of the forward and of the
                                   backward are independent of the backbone's smaller stages: lfd/_train.py derives the masks from the
                                   read / write / accumulate role of every off[] entry. */
-    int32_t pad_;
+    int32_t max_ctas;  /* CONV / WGRAD: upper bound on the persistent CTAs (0 = all), as in lfd_op */
     float eps, momentum;
     int64_t off[8];
     const void* ptr[6];

@@ -69,6 +69,21 @@ struct lfd_plan {
 };
 static constexpr size_t kMaxGraphs = 32;
 
+// Stream the CUDA graphs are captured on: the main chain (the backbone: the critical path of the step) runs two priority levels above
+// the side streams of the per-level chains (created at the default = lowest level) -- captured kernel nodes inherit the level, so when
+// SMs free up the pending CTAs of the critical path are placed first.  The levels above are left to the caller's latency-critical
+// streams (lfd/pipeline.py runs the post-process of the previous batch there).  LFD_B200_GRAPH_PRIO=0 disables it (A/B runs).
+static cudaError_t create_capture_stream(cudaStream_t* cap) {
+    static const bool prio = !(getenv("LFD_B200_GRAPH_PRIO") && atoi(getenv("LFD_B200_GRAPH_PRIO")) == 0);
+    int least = 0, greatest = 0;
+    if (prio && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && greatest < least) {
+        const int level = least - 2 < greatest ? greatest : least - 2;     // numerically lower = higher priority
+        return cudaStreamCreateWithPriority(cap, cudaStreamNonBlocking, level);
+    }
+    return cudaStreamCreateWithFlags(cap, cudaStreamNonBlocking);
+}
+
+
 extern "C" int lfd_debug_set_trace(void* device_buffer) {
     g_trace = reinterpret_cast<long long*>(device_buffer);
     return LFD_OK;
@@ -78,6 +93,15 @@ extern "C" int lfd_debug_set_timeline(void* device_buffer) {
     return LFD_OK;
 }
 extern "C" int lfd_abi_version(void) { return LFD_B200_ABI_VERSION; }
+extern "C" int lfd_struct_bytes(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(lfd_op);
+        case 1: return (int)sizeof(lfd_top);
+        case 2: return (int)sizeof(lfd_pack_desc);
+        case 3: return (int)sizeof(lfd_unpack_desc);
+    }
+    return -1;
+}
 extern "C" const char* lfd_last_error(void) { return g_err; }
 extern "C" int lfd_device_sm_count(void) {
     int n = sm_count();
@@ -151,6 +175,8 @@ static int plan_op(const lfd_op& o, int conv_impl, PlannedOp* out) {
         rc = umma_conv_configure(geom_of(o), sm_count() > 0 ? sm_count() : 148, &out->cp, &out->smem, &out->grid);
         if (rc) return fail(LFD_ERR_UNSUPPORTED, "conv %dx%d s%d Cin=%d Cout=%d unsupported (rc=%d)", o.ksize, o.ksize, o.stride, o.Cin, o.Cout, rc);
         if (o.kind == LFD_OP_CONV && out->cp.Cc != o.cc) return fail(LFD_ERR_INVALID, "weights packed with cc=%d but the kernel needs cc=%d", o.cc, out->cp.Cc);
+        if (o.max_ctas < 0) return fail(LFD_ERR_INVALID, "max_ctas = %d", o.max_ctas);
+        if (o.max_ctas > 0 && out->grid > o.max_ctas) out->grid = o.max_ctas;   // tiles are strided by gridDim: any grid size is valid
     }
     (void)conv_impl;
     return LFD_OK;
@@ -339,7 +365,7 @@ extern "C" int lfd_plan_forward(lfd_plan* pl, const void* input, int input_forma
         pl->graphs.erase(pl->graphs.begin());
     }
     cudaStream_t cap;
-    CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    CUDA_TRY(create_capture_stream(&cap));
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (ce != cudaSuccess) { cudaStreamDestroy(cap); return fail(LFD_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); }
@@ -650,6 +676,7 @@ static lfd_op conv_op_of(const lfd_top& t) {
     o.in_off = t.off[0]; o.out_off = t.off[1]; o.res_off = t.off[2]; o.stats_off = t.off[3];
     o.ds_out_off = -1;
     o.dtype = LFD_DTYPE_BF16;
+    o.max_ctas = t.max_ctas;
     return o;
 }
 
@@ -786,7 +813,7 @@ static int launch_top(const PlannedTop& pt, const void* input, int fmt, uint8_t*
             float* ds = at<float>(ws, t.off[5]);
             if (!x || !dz || !ds) return fail(LFD_ERR_INVALID, "wgrad: missing tensor");
             if (t.impl == LFD_WGRAD_SIMT) CUDA_TRY(wgrad_simt_launch(g, x, dz, ds, st));
-            else CUDA_TRY(wgrad_umma_launch(g, x, dz, ds, sms, st));
+            else CUDA_TRY(wgrad_umma_launch(g, x, dz, ds, t.max_ctas > 0 && t.max_ctas < sms ? t.max_ctas : sms, st));
             break;
         }
         case LFD_TOP_WGRAD_STEM: {
@@ -912,7 +939,7 @@ extern "C" int lfd_train_plan_run(lfd_train_plan* pl, const void* input, int inp
     // The first eager pass already produced this call's results; the graph is captured for the FOLLOWING calls.  Capture does
     // not execute anything, so the state (statistics, staging) is untouched.
     cudaStream_t cap;
-    CUDA_TRY(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    CUDA_TRY(create_capture_stream(&cap));
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
     if (ce != cudaSuccess) { cudaStreamDestroy(cap); return fail(LFD_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(ce)); }

@@ -147,8 +147,8 @@ __device__ __forceinline__ float iou_ref(const float4 a, const float aa, const f
 
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
     extern __shared__ __align__(16) uint8_t nsm[];
-    __shared__ float s_red[32];
-    __shared__ int s_keep;
+    __shared__ float s_red[32], s_red2[32];
+    __shared__ int s_keep, s_scan[33];
     const int n = blockIdx.x;
     const int tid = threadIdx.x;
     int K = p.cand_count[n];
@@ -178,17 +178,22 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
     const int* csrc = p.cand_src + (size_t)n * p.cap;
 
     // 1. max coordinate over the candidate boxes (nms.py:148 `bboxes.max()`)
-    float mx = -3.4e38f;
+    float mx = -3.4e38f, mn = 3.4e38f;
     if (!p.class_agnostic) {
         for (int i = tid; i < K; i += kNmsThreads) {
             const float4 b = cbox[i];
             mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+            mn = fminf(mn, fminf(fminf(b.x, b.y), fminf(b.z, b.w)));
         }
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+        for (int o = 16; o; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if ((tid & 31) == 0) { s_red[tid >> 5] = mx; s_red2[tid >> 5] = mn; }
         __syncthreads();
         mx = s_red[0];
-        for (int i = 1; i < kNmsThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
+        mn = s_red2[0];
+        for (int i = 1; i < kNmsThreads / 32; ++i) { mx = fmaxf(mx, s_red[i]); mn = fminf(mn, s_red2[i]); }
     }
     const float offmul = __fadd_rn(mx, 1.0f);
 
@@ -283,6 +288,118 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
             p.out_src[(size_t)n * p.cap + k] = src;
         }
         if (tid == 0) p.out_count[n] = nkeep;
+        return;
+    }
+
+    // 4c. K > 1024 with several classes: boxes of different classes never suppress each other (after the class offsets they cannot
+    //     overlap when every coordinate is >= 0, which the decode's clamp guarantees), so the greedy sweep factors into one sweep per class
+    //     -- same arithmetic on the same offset boxes, same decisions, but 32 classes at a time (one warp each) instead of K lock-step
+    //     rounds of the whole CTA.  The candidates are re-sorted by (class, global rank); kept boxes are emitted in global rank order.
+    const size_t seg_off = in_smem ? ((L * 29 + 15) & ~(size_t)15) : 0;
+    const size_t seg_cap = ((size_t)kNmsMaskOff + (size_t)kNmsMaskMax * 128 - seg_off) / 4;
+    if (!p.class_agnostic && p.C > 1 && mn >= 0.f && (size_t)K <= seg_cap) {
+        int* seg = reinterpret_cast<int*>(nsm + seg_off);
+        for (int i = tid; i < Kp; i += kNmsThreads)
+            keys[i] = i < K ? (((unsigned long long)(unsigned)(csrc[pay[i]] % p.C) << 32) | (unsigned)i) : ~0ull;
+        __syncthreads();
+        for (int size = 2; size <= Kp; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < (Kp >> 1); i += kNmsThreads) {
+                    const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const unsigned long long a = keys[lo], b = keys[hi];
+                    if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        // segment starts, in order (block-wide exclusive scan of the boundary flags; each thread owns a run of consecutive positions)
+        const int per = (K + kNmsThreads - 1) / kNmsThreads;
+        const int i0 = min(tid * per, K), i1 = min(i0 + per, K);
+        auto block_offset = [&](int v) -> int {          // exclusive prefix of v over the threads; total in s_scan[32]
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += t;
+            }
+            __syncthreads();
+            if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                int w = s_scan[tid], wi = w;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (tid >= o) wi += t;
+                }
+                s_scan[tid] = wi - w;
+                if (tid == 31) s_scan[32] = wi;
+            }
+            __syncthreads();
+            return s_scan[tid >> 5] + incl - v;
+        };
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) cnt += (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
+        int pos = block_offset(cnt);
+        const int nseg = s_scan[32];
+        for (int i = i0; i < i1; ++i)
+            if (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) seg[pos++] = i;
+        __syncthreads();
+        constexpr int kLongSeg = 512;
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int j = warp; j < nseg; j += kNmsThreads / 32) {      // one warp per class
+            const int a = seg[j], b = j + 1 < nseg ? seg[j + 1] : K;
+            if (b - a > kLongSeg) continue;
+            for (int ii = a; ii < b; ++ii) {
+                const int ri = (int)(unsigned)keys[ii];
+                if (removed[ri]) continue;                         // uniform over the warp
+                const float4 bi = sbox[ri];
+                const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                for (int jj = ii + 1 + lane; jj < b; jj += 32) {
+                    const int rj = (int)(unsigned)keys[jj];
+                    if (removed[rj]) continue;
+                    const float4 bj = sbox[rj];
+                    const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                    if (iou_ref(bi, ai, bj, aj) > p.iou_thr) removed[rj] = 1;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int j = 0; j < nseg; ++j) {                           // classes with many candidates: the whole CTA in lock step
+            const int a = seg[j], b = j + 1 < nseg ? seg[j + 1] : K;
+            if (b - a <= kLongSeg) continue;
+            for (int ii = a; ii < b; ++ii) {
+                const int ri = (int)(unsigned)keys[ii];
+                if (removed[ri]) continue;                         // uniform (written only between barriers)
+                const float4 bi = sbox[ri];
+                const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+                for (int jj = ii + 1 + tid; jj < b; jj += kNmsThreads) {
+                    const int rj = (int)(unsigned)keys[jj];
+                    if (removed[rj]) continue;
+                    const float4 bj = sbox[rj];
+                    const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                    if (iou_ref(bi, ai, bj, aj) > p.iou_thr) removed[rj] = 1;
+                }
+                __syncthreads();
+            }
+        }
+        // kept boxes in global rank (score) order
+        cnt = 0;
+        for (int i = i0; i < i1; ++i) cnt += removed[i] ? 0 : 1;
+        int k = block_offset(cnt);
+        for (int i = i0; i < i1; ++i) {
+            if (removed[i]) continue;
+            const int sidx = (int)pay[i];
+            const int src = csrc[sidx];
+            float4 ob = sbox[i];
+            const float off = __fmul_rn((float)(src % p.C), offmul);      // nms.py:155 subtracts the offsets again (fp32 round trip kept)
+            ob.x = __fsub_rn(ob.x, off); ob.y = __fsub_rn(ob.y, off); ob.z = __fsub_rn(ob.z, off); ob.w = __fsub_rn(ob.w, off);
+            float* d = p.out_dets + ((size_t)n * p.cap + k) * 5;
+            d[0] = ob.x; d[1] = ob.y; d[2] = ob.z; d[3] = ob.w; d[4] = cscore[sidx];
+            p.out_label[(size_t)n * p.cap + k] = src % p.C;
+            p.out_src[(size_t)n * p.cap + k] = src;
+            ++k;
+        }
+        if (tid == 0) p.out_count[n] = s_scan[32];
         return;
     }
 

@@ -447,6 +447,7 @@ class InferencePlan(object):
             o.n_cls, o.n_reg, o.point_off, o.cc = op.get('n_cls', 0), op.get('n_reg', 0), op.get('point_off', 0), op.get('cc', 0)
             o.branch = op.get('branch', 0)
             o.wait_mask = op.get('wait_mask', 0)
+            o.max_ctas = op.get('max_ctas', 0)
             o.tail_cout, o.tail_relu = op.get('tail_cout', 0), op.get('tail_relu', 0)
             if op.get('tail_cout'):
                 o.tail_weight = bb + 2 * op['tail_w']
@@ -476,12 +477,87 @@ class InferencePlan(object):
         self.handle = None
         if not self.create_native:
             return
+        self.handle = self._create_handle()
+        self.num_launches = nat.lib().lfd_plan_num_launches(self.handle)
+        self.side_ctas, self.autotuned = {}, False     # branch -> bound on the persistent CTAs of its convs (autotune)
+
+    def _create_handle(self):
         handle = C.c_void_p()
-        with torch.cuda.device(dev):
-            nat.check(nat.lib().lfd_plan_create(arr, len(self._ops), self.N, self.P, self.cls_channels, 0, self.stats_bytes,
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().lfd_plan_create(self._op_array, len(self._ops), self.N, self.P, self.cls_channels, 0, self.stats_bytes,
                                                 self.workspace_bytes, self.conv_impl, C.byref(handle)))
-        self.handle = handle
-        self.num_launches = nat.lib().lfd_plan_num_launches(handle)
+        return handle
+
+    def _set_side_ctas(self, caps):
+        for o, op in zip(self._op_array, self._ops):
+            if op['kind'] == nat.OP_CONV and op.get('branch', 0) > 0:
+                o.max_ctas = int(caps.get(op['branch'], 0))
+
+    def autotune(self, candidates=(96, 64, 48, 32), budget_s=3.0, x=None):
+        """Pick, by timing the replayed CUDA graph on this device, how many persistent CTAs the convs of every side branch (the
+        per-level neck + head chains) may use.  The chains of the large levels run next to the backbone's small, latency-bound deeper
+        stages (the critical path of the step); when their persistent CTAs hold all SMs, every small layer queues behind a whole
+        side-branch layer.  Coordinate descent over the branches (largest first), keeping a bound only when it is measurably faster.
+        Results do not depend on the bound (tiles are independent).  Returns {branch: bound} (0 = unbounded)."""
+        import time
+        if self.handle is None:
+            raise nat.LfdError('this plan was built for host-side inspection only (create_native=False)')
+        if x is None:
+            x = torch.zeros((self.N, self.H, self.W, 3), dtype=torch.uint8, device=self.device)
+        lib = nat.lib()
+
+        def measure(caps):
+            self._set_side_ctas(caps)
+            h = self._create_handle()
+            try:
+                saved, self.handle = self.handle, h
+                with torch.cuda.device(self.device):
+                    self.forward(x, use_graph=True)          # eager pass + capture
+                    self.forward(x, use_graph=True)
+                    torch.cuda.synchronize(self.device)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    self.forward(x, use_graph=True)
+                    e1.record()
+                    torch.cuda.synchronize(self.device)
+                    reps = int(max(3, min(40, 0.01 / max(e0.elapsed_time(e1) * 1e-3, 1e-6))))
+                    best = []
+                    for _ in range(3):
+                        e0.record()
+                        for _ in range(reps):
+                            self.forward(x, use_graph=True)
+                        e1.record()
+                        torch.cuda.synchronize(self.device)
+                        best.append(e0.elapsed_time(e1) / reps)
+                return sorted(best)[1]
+            finally:
+                self.handle = saved
+                lib.lfd_plan_destroy(h)
+
+        t_end = time.time() + budget_s
+        work = {}
+        for op in self._ops:
+            if op['kind'] == nat.OP_CONV and op.get('branch', 0) > 0:
+                work[op['branch']] = work.get(op['branch'], 0) + self.N * op['Ho'] * op['Wo'] * (op['Cin'] + op['Cout'])
+        caps = {b: 0 for b in work}
+        base = measure(caps)
+        log = [('all SMs', base)]
+        for b in sorted(work, key=lambda k: -work[k]):
+            for c in candidates:
+                if time.time() > t_end:
+                    break
+                trial = dict(caps)
+                trial[b] = c
+                t = measure(trial)
+                log.append(('branch %d <= %d CTAs' % (b, c), t))
+                if t < base * 0.995:
+                    base, caps = t, trial
+        self._set_side_ctas(caps)
+        old = self.handle
+        self.handle = self._create_handle()
+        lib.lfd_plan_destroy(old)
+        self.side_ctas, self.autotune_log, self.autotuned = caps, log, True
+        return caps
 
     def outputs(self, slot):
         while len(self._outputs) <= slot:

@@ -39,7 +39,7 @@ class Op(C.Structure):
                 ('gamma', C.c_void_p), ('beta', C.c_void_p),
                 ('tail_cout', C.c_int32), ('tail_relu', C.c_int32),
                 ('tail_weight', C.c_void_p), ('tail_scale', C.c_void_p), ('tail_shift', C.c_void_p),
-                ('ds_cout', C.c_int32), ('dtype', C.c_int32), ('ds_out_off', C.c_int64),
+                ('ds_cout', C.c_int32), ('dtype', C.c_int32), ('max_ctas', C.c_int32), ('pad_', C.c_int32), ('ds_out_off', C.c_int64),
                 ('ds_weight', C.c_void_p), ('ds_shift', C.c_void_p)]
 
 
@@ -83,7 +83,7 @@ class Top(C.Structure):
                 ('relu', C.c_int32), ('groups', C.c_int32), ('cc', C.c_int32), ('n_cls', C.c_int32), ('n_reg', C.c_int32),
                 ('point_off', C.c_int32), ('P', C.c_int32), ('cls_stride', C.c_int32),
                 ('accumulate', C.c_int32), ('upH', C.c_int32), ('upW', C.c_int32), ('n_desc', C.c_int32), ('max_n', C.c_int32),
-                ('impl', C.c_int32), ('frozen', C.c_int32), ('branch', C.c_int32), ('wait_mask', C.c_int32), ('pad_', C.c_int32), ('eps', C.c_float), ('momentum', C.c_float),
+                ('impl', C.c_int32), ('frozen', C.c_int32), ('branch', C.c_int32), ('wait_mask', C.c_int32), ('max_ctas', C.c_int32), ('eps', C.c_float), ('momentum', C.c_float),
                 ('off', C.c_int64 * 8), ('ptr', C.c_void_p * 6)]
 
 
@@ -101,6 +101,7 @@ class UnpackDesc(C.Structure):
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 SYMBOLS = {
     'lfd_abi_version': (_i, []),
+    'lfd_struct_bytes': (_i, [_i]),
     'lfd_last_error': (C.c_char_p, []),
     'lfd_device_sm_count': (_i, []),
     'lfd_conv_query': (_i, [_i] * 11 + [C.POINTER(_i)] * 4 + [C.POINTER(_i64)]),
@@ -162,6 +163,9 @@ def lib():
         fn.argtypes = args
     if L.lfd_abi_version() != 5:
         raise LfdError('liblfd_b200.so ABI version mismatch')
+    for which, st in enumerate((Op, Top, PackDesc, UnpackDesc)):
+        if L.lfd_struct_bytes(which) != C.sizeof(st):
+            raise LfdError('liblfd_b200.so: %s is %d bytes in the library, %d in lfd/_native.py' % (st.__name__, L.lfd_struct_bytes(which), C.sizeof(st)))
     _lib = L
     return L
 

@@ -658,6 +658,95 @@ class TrainPlan(object):
         with torch.cuda.device(self.device):
             nat.check(nat.lib().lfd_train_plan_run(self.bwd_handle, nat.ptr(self._input), self._fmt, nat.ptr(self.workspace), int(bool(use_graph)), nat.stream_ptr()))
 
+    def autotune(self, candidates=(96, 64, 48), budget_s=4.0):
+        """As InferencePlan.autotune: bounds on the persistent CTAs of the side-branch (per-level chain) convs / data-gradient convs /
+        weight-gradient kernels, picked per branch by timing the replayed forward and backward graphs.  Model state touched by the timing
+        runs (BatchNorm running statistics, the flat gradient buffer, the plan's outputs) is saved and restored."""
+        import time
+        if not self.create_native or not self.branches:
+            return {}
+        dev, lib = self.device, nat.lib()
+        saved = [t.clone() for m in self._bn_modules for t in (m.running_mean, m.running_var)]
+        tracked = [t.clone() for t in self._bn_tracked]
+        grad = self.flat.grad.clone() if self.flat.grad is not None else None
+        outs = [t.clone() for t in (self.cls_out, self.reg_out, self.gcls, self.greg)]
+        if self._input is None:
+            self._input = torch.zeros((self.N, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+            self._fmt = nat.INPUT_U8_NHWC
+        tuned = (nat.TOP_CONV, nat.TOP_WGRAD)
+        result = {}
+        t_end = time.time() + budget_s
+        try:
+            for which, arr, ops in (('fwd', self._fwd_arr, self.fwd_ops), ('bwd', self._bwd_arr, self.bwd_ops)):
+                def set_caps(caps):
+                    for o, op in zip(arr, ops):
+                        if op['kind'] in tuned and op.get('branch', 0) > 0:
+                            o.max_ctas = int(caps.get(op['branch'], 0))
+
+                def measure(caps):
+                    set_caps(caps)
+                    h = C.c_void_p()
+                    with torch.cuda.device(dev):
+                        nat.check(lib.lfd_train_plan_create(arr, len(ops), self.workspace_bytes, C.byref(h)))
+                        try:
+                            def run():
+                                nat.check(lib.lfd_train_plan_run(h, nat.ptr(self._input), self._fmt, nat.ptr(self.workspace), 1, nat.stream_ptr()))
+                            run()
+                            run()
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            best = []
+                            for _ in range(3):
+                                e0.record()
+                                for _ in range(3):
+                                    run()
+                                e1.record()
+                                torch.cuda.synchronize(dev)
+                                best.append(e0.elapsed_time(e1) / 3)
+                            return sorted(best)[1]
+                        finally:
+                            lib.lfd_train_plan_destroy(h)
+
+                work = {}
+                for op in ops:
+                    if op['kind'] in tuned and op.get('branch', 0) > 0:
+                        work[op['branch']] = work.get(op['branch'], 0) + op['N'] * op['Ho'] * op['Wo'] * (op['Cin'] + op['Cout'])
+                caps = {b: 0 for b in work}
+                base = measure(caps)
+                log = [('all SMs', base)]
+                for b in sorted(work, key=lambda k: -work[k])[:3]:
+                    for c in candidates:
+                        if time.time() > t_end:
+                            break
+                        trial = dict(caps)
+                        trial[b] = c
+                        t = measure(trial)
+                        log.append(('branch %d <= %d CTAs' % (b, c), t))
+                        if t < base * 0.995:
+                            base, caps = t, trial
+                set_caps(caps)
+                name = which + '_handle'
+                old = getattr(self, name)
+                h = C.c_void_p()
+                with torch.cuda.device(dev):
+                    nat.check(lib.lfd_train_plan_create(arr, len(ops), self.workspace_bytes, C.byref(h)))
+                setattr(self, name, h)
+                lib.lfd_train_plan_destroy(old)
+                result[which] = dict(ctas=caps, log=log)
+        finally:
+            torch.cuda.synchronize(dev)
+            it = iter(saved)
+            for m in self._bn_modules:
+                m.running_mean.copy_(next(it))
+                m.running_var.copy_(next(it))
+            for t, v in zip(self._bn_tracked, tracked):
+                t.copy_(v)
+            if grad is not None:
+                self.flat.grad.copy_(grad)
+            for t, v in zip((self.cls_out, self.reg_out, self.gcls, self.greg), outs):
+                t.copy_(v)
+        self.autotune_result = result
+        return result
+
     def tensor(self, name, h, w, c):
         """Debug view of a workspace activation / gradient as bf16 NHWC."""
         off = self._off[name]

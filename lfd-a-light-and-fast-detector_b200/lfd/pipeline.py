@@ -7,6 +7,7 @@ forward of batch i+1.  This is the serving-side
 counterpart of the reference's `predict_for_single_image` (lfd/model/lfd.py:544-655), which moves one image at a time
 and synchronises after every stage.
 """
+import os
 import torch
 
 from . import _native as nat
@@ -48,18 +49,22 @@ class ForwardPostPipeline(object):
         dev = plan.device
         with torch.cuda.device(dev):
             self.fwd_stream = torch.cuda.Stream(device=dev)
-            self.post_stream = torch.cuda.Stream(device=dev)
-        self.fwd_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self.post_done = [torch.cuda.Event(), torch.cuda.Event()]
+            # highest priority the device offers (torch maps out-of-range values to it): the post-process kernels are tiny and
+            # latency-bound; with a priority above the forward graph's nodes their CTAs are placed at the first kernel boundary of the
+            # NEXT batch's forward instead of queueing behind its persistent CTAs
+            self.post_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get('LFD_B200_POST_PRIO', '-100')))
+        self.n_slots = int(os.environ.get('LFD_B200_OUT_SLOTS', '2'))
+        self.fwd_done = [torch.cuda.Event() for _ in range(self.n_slots)]
+        self.post_done = [torch.cuda.Event() for _ in range(self.n_slots)]
         self.k = 0
 
     def enqueue(self, x, wait_for=None, consume=None):
         """x: device input of the plan; wait_for: optional event the forward has to wait for (e.g. the H2D copy of x)."""
-        slot = self.k % 2
+        slot = self.k % self.n_slots
         with torch.cuda.stream(self.fwd_stream):
             if wait_for is not None:
                 self.fwd_stream.wait_event(wait_for)
-            if self.k >= 2:
+            if self.k >= self.n_slots:
                 self.fwd_stream.wait_event(self.post_done[slot])
             cls, reg = self.plan.forward(x, use_graph=self.model.use_cuda_graph, slot=slot)
             self.fwd_done[slot].record(self.fwd_stream)
@@ -89,6 +94,8 @@ class StreamingDetector(object):
             self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(int(copy_streams), batch)))]
             self.copy_stream = self.copy_streams[0]
         self.plan = model.inference_plan(batch, height, width, dev)
+        if getattr(model, 'use_cuda_graph', True) and not self.plan.autotuned:
+            self.plan.autotune()
         for i, hw in enumerate(self.plan.level_sizes):
             model._head_indexes_to_feature_map_sizes[i] = hw
         self.post = model.post_plan(batch, self.plan.level_sizes, dev)

@@ -315,3 +315,24 @@ def test_streaming_detector_matches_synchronous_path():
             total += k
             assert torch.equal(rd[i, :k], gd[i, :k]) and torch.equal(rl[i, :k].int(), gl[i, :k].int()), (b, i)
     assert total > 0
+
+
+def test_autotune_bounds_side_branch_ctas_without_changing_the_outputs():
+    """InferencePlan.autotune only changes how many persistent CTAs the side-branch convs use (tiles are independent): same outputs,
+    a bound per branch recorded, and the plan keeps working with CUDA graphs afterwards."""
+    model, _ = synth_model('WIDERFACE_S')
+    model.cuda().eval()
+    x = torch.randint(0, 256, (2, 256, 320, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(5)).cuda()
+    plan = model.inference_plan(2, 256, 320, torch.device('cuda', 0))
+    with torch.no_grad():
+        cls0, reg0 = (t.clone() for t in plan.forward(x, use_graph=True))
+        caps = plan.autotune(candidates=(64, 16), budget_s=2.0)
+        assert plan.autotuned and set(caps) == {b for b in range(1, 1 + len(plan.level_sizes))} and plan.autotune_log[0][0] == 'all SMs'
+        for forced in ({b: 16 for b in caps}, caps):        # a bound that certainly bites, then the tuned ones
+            plan._set_side_ctas(forced)
+            old, plan.handle = plan.handle, plan._create_handle()
+            nat.lib().lfd_plan_destroy(old)
+            for use_graph in (False, True, True):
+                cls1, reg1 = plan.forward(x, use_graph=use_graph)
+                # (the GroupNorm statistics are fp64 atomics: their order, not their value to bf16 precision, depends on the grid)
+                assert rel_err(cls1, cls0)[0] < 1e-3 and rel_err(reg1, reg0)[0] < 1e-3

@@ -128,3 +128,28 @@ def test_batched_nms_matches_oracle():
     dets2, keep2 = batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(),
                                dict(type='nms', iou_thr=0.4, class_agnostic=True))
     assert keep2.cpu().tolist() == list(map(int, orc.nms(np.concatenate([boxes, scores[:, None]], 1).astype(np.float32), 0.4)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,n_cls,skew', [(3000, 45, False), (6000, 12, True), (1500, 2, True)])
+def test_batched_nms_many_candidates_several_classes(n, n_cls, skew):
+    """More than 1024 candidates with several classes take the per-class sweeps of nms_kernel (one warp per class, whole CTA for classes
+    with > 512 candidates): same kept set, order and rows as the oracle's single NMS over the class-offset boxes (nms.py:141-156)."""
+    from lfd.model.utils import batched_nms
+    rng = np.random.RandomState(n + n_cls)
+    xy = rng.uniform(0, 900, (n, 2)).astype(np.float32)
+    wh = rng.uniform(10, 120, (n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = rng.uniform(0.05, 1.0, n).astype(np.float32)
+    scores[rng.randint(0, n, n // 20)] = np.float32(0.5)                 # score ties: resolved by the input index in both
+    if skew:                                                             # one class holds most of the boxes (> 512: the CTA-wide sweep)
+        labels = np.where(rng.uniform(size=n) < 0.7, 0, rng.randint(0, n_cls, n)).astype(np.int64)
+    else:
+        labels = rng.randint(0, n_cls, n).astype(np.int64)
+    dets, keep = batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), torch.from_numpy(labels).cuda(), dict(type='nms', iou_thr=0.45))
+    off = labels.astype(np.float32) * np.float32(boxes.max() + np.float32(1))
+    shifted = (boxes + off[:, None]).astype(np.float32)
+    okeep = orc.nms(np.concatenate([shifted, scores[:, None]], 1).astype(np.float32), 0.45)
+    assert keep.cpu().tolist() == list(map(int, okeep))
+    want = (shifted[okeep] - off[okeep][:, None]).astype(np.float32)
+    assert np.array_equal(dets[:, :4].cpu().numpy(), want) and np.array_equal(dets[:, 4].cpu().numpy(), scores[okeep])

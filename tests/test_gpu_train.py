@@ -344,3 +344,30 @@ def test_ddp_two_ranks_match_one_rank_on_the_full_batch():
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert 'DDP_OK' in r.stdout, r.stdout[-3000:]
+
+
+def test_train_plan_autotune_restores_the_model_state():
+    """TrainPlan.autotune replays the forward / backward graphs to pick CTA bounds for the side-branch kernels; BatchNorm running
+    statistics, num_batches_tracked, the gradient buffer and the plan outputs must come back bit-exact, and the next step must agree with
+    an untuned twin."""
+    model, twin = _pair('WIDERFACE_XS')
+    x = synth.synth_input(2, 160, 192).cuda()
+    ann = synth.synth_annotations(2, 160, 192, model._num_classes, seed=3)
+    for m in (model, twin):
+        m.get_loss(m(x), ann)['loss'].backward()
+    torch.cuda.synchronize()
+    plan = list(model._train_plans.values())[0]
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    g_before = model._flat_parameters.grad.clone()
+    res = plan.autotune(candidates=(64,), budget_s=2.0)
+    assert set(res) == {'fwd', 'bwd'}
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    assert torch.equal(model._flat_parameters.grad, g_before)
+    for m in (model, twin):
+        m.zero_grad(set_to_none=False)
+        m._flat_parameters.grad.zero_()
+        m.get_loss(m(x), ann)['loss'].backward()
+    torch.cuda.synchronize()
+    a, b = model._flat_parameters.grad, twin._flat_parameters.grad
+    assert float((a - b).norm() / b.norm()) < 2e-2           # (atomics order + bf16 re-rounding, as between any two runs)

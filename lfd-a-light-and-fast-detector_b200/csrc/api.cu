@@ -165,6 +165,12 @@ static int check_op(const lfd_op& o) {
     return LFD_OK;
 }
 
+// GN_APPLY / HEAD_FINAL size their grids from the SM count: a max_ctas bound (side-branch layers, see lfd_op) scales them the same way
+static int bounded_sms(int max_ctas) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    return max_ctas > 0 && max_ctas < sms ? max_ctas : sms;
+}
+
 static int plan_op(const lfd_op& o, int conv_impl, PlannedOp* out) {
     int rc = check_op(o);
     if (rc) return rc;
@@ -237,7 +243,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             p.in = reinterpret_cast<const __nv_bfloat16*>(ws + o.in_off); p.out = reinterpret_cast<__nv_bfloat16*>(ws + o.out_off);
             p.stats = reinterpret_cast<const double*>(ws + o.stats_off); p.gamma = o.gamma; p.beta = o.beta;
             p.N = o.N; p.HW = o.H * o.W; p.C = o.Cin; p.groups = o.gn_groups; p.eps = 1e-5f; p.tl = tl; p.f16 = o.dtype;
-            CUDA_TRY(gn_apply_launch(p, sm_count(), st));
+            CUDA_TRY(gn_apply_launch(p, bounded_sms(o.max_ctas), st));
             break;
         }
         case LFD_OP_HEAD_FINAL: {
@@ -250,7 +256,7 @@ static int launch_op(const PlannedOp& po, size_t index, const void* input, int i
             p.P = P; p.point_off = o.point_off; p.cls_stride = cls_channels; p.eps = 1e-5f; p.tl = tl; p.f16 = o.dtype;
             if ((o.n_cls && !cls) || (o.n_reg && !reg)) return fail(LFD_ERR_INVALID, "head_final needs cls/reg output pointers");
             if (o.n_reg && o.n_reg != 4) return fail(LFD_ERR_INVALID, "head_final n_reg must be 0 or 4");
-            CUDA_TRY(head_final_launch(p, sm_count(), st));
+            CUDA_TRY(head_final_launch(p, bounded_sms(o.max_ctas), st));
             break;
         }
     }
@@ -475,7 +481,7 @@ extern "C" int lfd_postprocess(const lfd_post_cfg* c, const float* cls, const fl
     p.cand_src = reinterpret_cast<int*>(ws + L.src); p.cand_count = reinterpret_cast<int*>(ws + L.count);
     CUDA_TRY(cudaMemsetAsync(p.cand_count, 0, (size_t)c->N * 4, st));
     CUDA_TRY(cudaMemsetAsync(overflow, 0, 4, st));
-    CUDA_TRY(candidates_launch(p, st));
+    CUDA_TRY(candidates_launch(p, sm_count(), st));
     NmsParams q;
     q.cand_box = p.cand_box; q.cand_score = p.cand_score; q.cand_src = p.cand_src; q.cand_count = p.cand_count;
     q.scratch = ws + L.scratch; q.scratch_stride = L.scratch_stride; q.cap = c->cap; q.cap_pow2 = L.cap_pow2; q.C = c->C;

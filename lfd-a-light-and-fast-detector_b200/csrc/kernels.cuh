@@ -69,7 +69,7 @@ struct PostParams {
     int* cand_src;             // [N][cap]
     int* cand_count;           // [N]
 };
-cudaError_t candidates_launch(const PostParams& p, cudaStream_t st);
+cudaError_t candidates_launch(const PostParams& p, int num_sms, cudaStream_t st);
 
 struct NmsParams {
     const float* cand_box;

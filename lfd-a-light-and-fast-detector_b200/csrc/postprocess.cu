@@ -28,16 +28,55 @@ __device__ __forceinline__ uint32_t desc_key(float f) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// distance2bbox (+ clamp to the image, / resize scale) of one point: lfd.py:468-488
+__device__ __forceinline__ void decode_point(const PostParams& p, int n, int pt, float* box) {
+    int level = 0;
+    for (int l = 1; l < p.num_levels; ++l)
+        if (pt >= p.level_off[l]) level = l;
+    const int local = pt - p.level_off[level];
+    const float4 r = *reinterpret_cast<const float4*>(p.reg + ((size_t)n * p.P + pt) * 4);
+    const int W = p.level_w[level];
+    const float px = (float)((local % W) * p.level_stride[level]);
+    const float py = (float)((local / W) * p.level_stride[level]);
+    float d[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (p.bbox_mode == 0) d[k] = __fmul_rn(sigmoid_f(d[k]), p.level_hi[level]);   // lfd.py:481-486
+        else if (p.bbox_mode == 1) d[k] = expf(d[k]);                                  // :478-480
+        else d[k] = __fmul_rn(d[k], p.level_hi[level]);                                // 'independent' :468-476
+    }
+    const float iw = p.img_w[n], ih = p.img_h[n], rs = p.resize_scale[n];
+    box[0] = __fdiv_rn(fminf(fmaxf(__fsub_rn(px, d[0]), 0.f), iw), rs);
+    box[1] = __fdiv_rn(fminf(fmaxf(__fsub_rn(py, d[1]), 0.f), ih), rs);
+    box[2] = __fdiv_rn(fminf(fmaxf(__fadd_rn(px, d[2]), 0.f), iw), rs);
+    box[3] = __fdiv_rn(fminf(fmaxf(__fadd_rn(py, d[3]), 0.f), ih), rs);
+}
+
+// warp-aggregated slot claim in the image's candidate list
+__device__ __forceinline__ void claim_candidate(const PostParams& p, int n, bool pass, const float* box, float score, int src) {
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(p.cand_count + n, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) {
+        const int slot = base + __popc(m & ((1u << lane) - 1));
+        if (slot < p.cap) {
+            const size_t o = (size_t)n * p.cap + slot;
+            reinterpret_cast<float4*>(p.cand_box)[o] = make_float4(box[0], box[1], box[2], box[3]);
+            p.cand_score[o] = score;
+            p.cand_src[o] = src;
+        }
+    }
+}
+
+// One thread per point, looping over the classes: single-class heads (the face configs) and the softmax head (needs the row).
 __global__ void __launch_bounds__(256) candidates_kernel(const PostParams p) {
     const int n = blockIdx.y;
     const int pt = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = pt < p.P;
-    int level = 0, local = 0;
-    if (active) {
-        for (int l = 1; l < p.num_levels; ++l)
-            if (pt >= p.level_off[l]) level = l;
-        local = pt - p.level_off[level];
-    }
     float box[4] = {0, 0, 0, 0};
     bool decoded = false;
     const float* cls = p.cls + ((size_t)n * p.P + (active ? pt : 0)) * p.cls_stride;
@@ -56,42 +95,73 @@ __global__ void __launch_bounds__(256) candidates_kernel(const PostParams p) {
             pass = score > p.score_thr;
         }
         if (pass && !decoded) {
-            const float4 r = *reinterpret_cast<const float4*>(p.reg + ((size_t)n * p.P + pt) * 4);
-            const int W = p.level_w[level];
-            const float px = (float)((local % W) * p.level_stride[level]);
-            const float py = (float)((local / W) * p.level_stride[level]);
-            float d[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (p.bbox_mode == 0) d[k] = __fmul_rn(sigmoid_f(d[k]), p.level_hi[level]);   // lfd.py:481-486
-                else if (p.bbox_mode == 1) d[k] = expf(d[k]);                                  // :478-480
-                else d[k] = __fmul_rn(d[k], p.level_hi[level]);                                // 'independent' :468-476
-            }
-            const float iw = p.img_w[n], ih = p.img_h[n], rs = p.resize_scale[n];
-            box[0] = __fdiv_rn(fminf(fmaxf(__fsub_rn(px, d[0]), 0.f), iw), rs);
-            box[1] = __fdiv_rn(fminf(fmaxf(__fsub_rn(py, d[1]), 0.f), ih), rs);
-            box[2] = __fdiv_rn(fminf(fmaxf(__fadd_rn(px, d[2]), 0.f), iw), rs);
-            box[3] = __fdiv_rn(fminf(fmaxf(__fadd_rn(py, d[3]), 0.f), ih), rs);
+            decode_point(p, n, pt, box);
             decoded = true;
         }
-        // warp-aggregated slot claim
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(p.cand_count + n, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (pass) {
-                const int slot = base + __popc(m & ((1u << lane) - 1));
-                if (slot < p.cap) {
-                    const size_t o = (size_t)n * p.cap + slot;
-                    reinterpret_cast<float4*>(p.cand_box)[o] = make_float4(box[0], box[1], box[2], box[3]);
-                    p.cand_score[o] = score;
-                    p.cand_src[o] = pt * p.C + c;
-                }
+        claim_candidate(p, n, pass, box, score, pt * p.C + c);
+    }
+}
+
+// Softmax heads (TT100K: 45 classes + background): one thread per point as above, but the block's 128 logit rows are first brought into
+// shared memory with coalesced loads (thread-per-row loads touch 32 different rows of C + 1 floats per instruction).
+static constexpr int kRowsPts = 128;
+__global__ void __launch_bounds__(kRowsPts) candidates_rows_kernel(const PostParams p) {
+    extern __shared__ float rows[];
+    const int n = blockIdx.y;
+    const int pt0 = blockIdx.x * kRowsPts;
+    const int npts = min(kRowsPts, p.P - pt0);
+    const float* src = p.cls + ((size_t)n * p.P + pt0) * p.cls_stride;
+    for (int i = threadIdx.x; i < npts * p.cls_stride; i += kRowsPts) rows[i] = src[i];
+    __syncthreads();
+    const bool active = (int)threadIdx.x < npts;
+    const int pt = pt0 + threadIdx.x;
+    const float* cls = rows + (active ? threadIdx.x : 0) * p.cls_stride;
+    float box[4] = {0, 0, 0, 0};
+    bool decoded = false;
+    float smax = 0.f, sden = 1.f;
+    if (active && p.cls_mode == 1) {  // softmax over C+1 logits, background (last) dropped (lfd.py:450-452)
+        smax = cls[0];
+        for (int c = 1; c <= p.C; ++c) smax = fmaxf(smax, cls[c]);
+        sden = 0.f;
+        for (int c = 0; c <= p.C; ++c) sden += expf(cls[c] - smax);
+    }
+    for (int c = 0; c < p.C; ++c) {
+        float score = 0.f;
+        bool pass = false;
+        if (active) {
+            score = p.cls_mode == 1 ? expf(cls[c] - smax) / sden : sigmoid_f(cls[c]);
+            pass = score > p.score_thr;
+        }
+        if (pass && !decoded) {
+            decode_point(p, n, pt, box);
+            decoded = true;
+        }
+        claim_candidate(p, n, pass, box, score, pt * p.C + c);
+    }
+}
+
+// Sigmoid heads with several classes (TT100K: 45): one thread per (point, class) logit, so that a warp reads 128 contiguous bytes of the
+// (N, P, C) score tensor per load instead of 32 rows of C floats; the box is decoded only for the few logits that pass.
+__global__ void __launch_bounds__(256) candidates_flat_kernel(const PostParams p) {
+    const int n = blockIdx.y;
+    const long long total = (long long)p.P * p.cls_stride;
+    const float* cls = p.cls + (size_t)n * total;
+    const long long rounds = (total + (long long)gridDim.x * 256 - 1) / ((long long)gridDim.x * 256);
+    for (long long r = 0; r < rounds; ++r) {      // every lane of a warp runs the same number of rounds (the claim is warp-collective)
+        const long long e = (r * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        float score = 0.f, box[4] = {0, 0, 0, 0};
+        bool pass = false;
+        int pt = 0, c = 0;
+        if (e < total) {
+            pt = (int)(e / p.cls_stride);
+            c = (int)(e - (long long)pt * p.cls_stride);
+            if (c < p.C) {
+                score = sigmoid_f(cls[e]);
+                pass = score > p.score_thr;
             }
         }
+        if (pass) decode_point(p, n, pt, box);
+        claim_candidate(p, n, pass, box, score, pt * p.C + c);
     }
 }
 
@@ -433,8 +503,18 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const NmsParams p) {
     if (tid == 0) p.out_count[n] = s_keep;
 }
 
-cudaError_t candidates_launch(const PostParams& p, cudaStream_t st) {
-    candidates_kernel<<<dim3((p.P + 255) / 256, p.N), 256, 0, st>>>(p);
+cudaError_t candidates_launch(const PostParams& p, int num_sms, cudaStream_t st) {
+    if (p.cls_mode == 0 && p.C > 1) {
+        const long long total = (long long)p.P * p.cls_stride;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)(num_sms > 0 ? num_sms : 148) * 8;     // grid-stride beyond 8 blocks per SM and image
+        if (blocks > cap) blocks = cap;
+        candidates_flat_kernel<<<dim3((unsigned)blocks, p.N), 256, 0, st>>>(p);
+    } else if (p.cls_stride > 1 && (size_t)kRowsPts * p.cls_stride * 4 <= 48 * 1024) {
+        candidates_rows_kernel<<<dim3((p.P + kRowsPts - 1) / kRowsPts, p.N), kRowsPts, (size_t)kRowsPts * p.cls_stride * 4, st>>>(p);
+    } else {
+        candidates_kernel<<<dim3((p.P + 255) / 256, p.N), 256, 0, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -74,6 +74,13 @@ LFD_DEVINL void cp_async16_full(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 LFD_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+LFD_DEVINL void cp_async4(uint32_t dst_smem, const void* src, bool valid) {   // 4 bytes, zero fill when !valid
+    const uint32_t sz = valid ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+LFD_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+LFD_DEVINL void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // The mbarrier receives one arrival (counted against its expected-arrival count, hence .noinc) once ALL cp.async
 // operations issued so far by this thread have completed -- the thread itself does not wait.
 LFD_DEVINL void cp_async_mbar_arrive(uint64_t* bar) {
@@ -215,6 +222,11 @@ LFD_DEVINL uint32_t pack_bf16x2_relu(float lo, float hi) {
 }
 LFD_DEVINL void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+LFD_DEVINL float lds32f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
 }
 LFD_DEVINL uint4 lds128(uint32_t addr) {
     uint4 v;

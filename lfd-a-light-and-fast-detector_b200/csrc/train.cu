@@ -494,9 +494,46 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
 #pragma unroll
         for (int j = 0; j < 16; ++j) dwr[o][j] = 0.f;
     }
-    for (int tile = blockIdx.x; tile * kPix < p.HW; tile += gridDim.x) {
+    // SMALL: the activation rows and the upstream gradients of a tile come through a 3-stage cp.async ring (two tiles in flight while one
+    // is computed): with ~190 registers per thread only one block fits an SM, so the loads have to be hidden inside the block.
+    constexpr int kStages = 3, kStageBytes = kPix * 256 + 5 * kPix * 4;
+    const uint32_t ring = (smem_u32(s_rstd + 32) + 15u) & ~15u;
+    auto issue = [&](int tile, int stage) {
+        if (tile * kPix < p.HW) {
+            const uint32_t base = ring + (uint32_t)stage * kStageBytes;
+#pragma unroll
+            for (int q = 0; q < kPix * 16 / kHbThreads; ++q) {
+                const int chunk = threadIdx.x + q * kHbThreads, px = chunk >> 4, part = chunk & 15;
+                const int pix = tile * kPix + px;
+                const bool ok = pix < p.HW;
+                cp_async16(base + px * 256 + part * 16, p.raw + ((size_t)n * p.HW + (ok ? pix : 0)) * C + part * 8, ok);
+            }
+            for (int idx = threadIdx.x; idx < 5 * kPix; idx += kHbThreads) {
+                const int o = idx / kPix, px = idx - o * kPix;
+                const int pix = tile * kPix + px;
+                const bool ok = o < no && pix < p.HW;
+                const size_t pt = (size_t)n * p.P + p.point_off + (ok ? pix : 0);
+                const float* src = !ok ? p.w : (o >= p.n_cls ? p.greg + pt * 4 + (o - p.n_cls) : p.gcls + pt * p.cls_stride + o);
+                cp_async4(base + kPix * 256 + idx * 4, src, ok);
+            }
+        }
+        cp_async_commit();       // (an empty group past the last tile keeps the group count uniform)
+    };
+    int t_idx = 0;
+    if (SMALL) {
+        issue(blockIdx.x, 0);
+        issue(blockIdx.x + gridDim.x, 1);
+    }
+    for (int tile = blockIdx.x; tile * kPix < p.HW; tile += gridDim.x, ++t_idx) {
         const int pix0 = tile * kPix + (threadIdx.x >> 3);
         float a[kPpt][16], dt[kPpt][16];
+        uint32_t stage_base = 0;
+        if (SMALL) {
+            cp_async_wait_group<1>();      // this tile's stage has landed (the next tile's may still be in flight)
+            __syncthreads();               // ... for every thread, and everybody is done with the stage about to be refilled
+            issue(tile + 2 * gridDim.x, (t_idx + 2) % kStages);
+            stage_base = ring + (uint32_t)(t_idx % kStages) * kStageBytes;
+        }
         // SMALL: every upstream gradient of the tile is fetched up front, together with the activation rows (ONE memory round trip per tile
         // instead of one per output channel)
         float gpre[SMALL ? 5 : 1][kPpt];
@@ -505,20 +542,17 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
             for (int o = 0; o < 5; ++o)
 #pragma unroll
                 for (int k = 0; k < kPpt; ++k) {
-                    const int pix = pix0 + k * (kHbThreads / 8);
-                    float gv = 0.f;
-                    if (o < no && pix < p.HW) {
-                        const size_t pt = (size_t)n * p.P + p.point_off + pix;
-                        gv = o >= p.n_cls ? p.greg[pt * 4 + (o - p.n_cls)] : p.gcls[pt * p.cls_stride + o];
-                    }
-                    gpre[o][k] = gv;
+                    gpre[o][k] = lds32f(stage_base + kPix * 256 + (o * kPix + (threadIdx.x >> 3) + k * (kHbThreads / 8)) * 4);   // zero-filled past the map / n_out
                 }
         }
 #pragma unroll
         for (int k = 0; k < kPpt; ++k) {
             const int pix = pix0 + k * (kHbThreads / 8);
             uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-            if (pix < p.HW) {
+            if (SMALL) {
+                const uint32_t row = stage_base + ((threadIdx.x >> 3) + k * (kHbThreads / 8)) * 256 + sl * 32;
+                q0 = lds128(row); q1 = lds128(row + 16);      // (rows past the map were zero-filled)
+            } else if (pix < p.HW) {
                 const uint4* src = reinterpret_cast<const uint4*>(p.raw + ((size_t)n * p.HW + pix) * C + sl * 16);
                 q0 = src[0]; q1 = src[1];
             }
@@ -571,11 +605,19 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
                         if (is_reg) u[k] = fmaf(wv[e], a[k][j], u[k]);
                     }
                     if (SMALL) dwr[SMALL ? o : 0][j] += dw;
-                    else if (dw != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dw);
+                    else {      // the warp's 4 pixel rows first (shuffles), then ONE shared-memory atomic per warp and element (a CAS loop)
+                        dw += __shfl_xor_sync(0xffffffffu, dw, 8);
+                        dw += __shfl_xor_sync(0xffffffffu, dw, 16);
+                        if ((threadIdx.x & 31) < 8 && dw != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dw);
+                    }
                 }
             }
             if (SMALL) dbr[SMALL ? o : 0] += hsum;
-            else if (sl == 0 && hsum != 0.f) atomicAdd(dbs + o, hsum);
+            else {
+                hsum += __shfl_xor_sync(0xffffffffu, hsum, 8);
+                hsum += __shfl_xor_sync(0xffffffffu, hsum, 16);
+                if ((threadIdx.x & 31) == 0 && hsum != 0.f) atomicAdd(dbs + o, hsum);
+            }
             if (is_reg) {   // Scale gradient needs the full dot product: combine the 8 channel slices (warp-uniform branch)
 #pragma unroll
                 for (int k = 0; k < kPpt; ++k) {
@@ -596,17 +638,48 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
             dst[1] = pack8f(dt[k] + 8);
         }
     }
-    if (dscale_acc != 0.f) atomicAdd(dsc, dscale_acc);
     if (SMALL) {
+        // Block-level reduction of the per-thread weight-gradient sums WITHOUT shared-memory atomics (a float atomicAdd on shared memory is a
+        // compare-and-swap loop; with 32 threads per address the old flush cost ~25 us per block, most of the kernel for the small levels):
+        // the 4 pixel rows of a warp are combined with two shuffles, the 8 warps through the (now idle) tile ring.
+        cp_async_wait_all();
+        __syncthreads();
+        uint8_t* rb = reinterpret_cast<uint8_t*>(s_rstd + 32);
+        rb += (16u - (smem_u32(rb) & 15u)) & 15u;
+        float* red = reinterpret_cast<float*>(rb);           // [8 warps][kRedStride]: no * C weight sums, no bias sums, 1 Scale sum
+        constexpr int kRedStride = 5 * 128 + 8;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
         for (int o = 0; o < 5; ++o) {
             if (o >= no) break;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (dwr[o][j] != 0.f) atomicAdd(dWs + (size_t)o * C + sl * 16 + j, dwr[o][j]);
-            if (sl == 0 && dbr[o] != 0.f) atomicAdd(dbs + o, dbr[o]);
+            for (int j = 0; j < 16; ++j) {
+                float v = dwr[o][j];
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane < 8) red[warp * kRedStride + o * C + sl * 16 + j] = v;
+            }
+            float b = dbr[o];                                 // identical in the 8 channel-slice lanes of a pixel: take slice 0
+            b += __shfl_xor_sync(0xffffffffu, b, 8);
+            b += __shfl_xor_sync(0xffffffffu, b, 16);
+            if (lane == 0) red[warp * kRedStride + no * C + o] = b;
         }
+        float d = dscale_acc;                                 // only the slice-0 lanes carry it
+        d += __shfl_xor_sync(0xffffffffu, d, 8);
+        d += __shfl_xor_sync(0xffffffffu, d, 16);
+        if (lane == 0) red[warp * kRedStride + no * C + no] = d;
+        __syncthreads();
+        for (int i = threadIdx.x; i < no * C + no + 1; i += kHbThreads) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < kHbThreads / 32; ++w) sum += red[w * kRedStride + i];
+            if (sum == 0.f) continue;
+            if (i < no * C + no) atomicAdd(p.dstage + i, sum);           // [n_out][C] weights, then [n_out] biases: contiguous in the staging
+            else if (p.dscale) atomicAdd(p.dscale, sum);
+        }
+        return;
     }
+    if (dscale_acc != 0.f) atomicAdd(dsc, dscale_acc);
     __syncthreads();
     for (int i = threadIdx.x; i < no * C; i += kHbThreads)
         if (dWs[i] != 0.f) atomicAdd(p.dstage + i, dWs[i]);
@@ -617,7 +690,8 @@ __global__ void __launch_bounds__(kHbThreads) head_final_bwd_kernel(const HeadFi
 
 cudaError_t head_final_bwd_launch(const HeadFinalBwdParams& p, int num_sms, cudaStream_t st) {
     if (p.C != 128 || (p.groups != 16 && p.groups != 0)) return cudaErrorInvalidValue;
-    const size_t smem = ((size_t)2 * p.n_out * p.C + 3 * p.n_out + 1 + 64) * sizeof(float);
+    size_t smem = ((size_t)2 * p.n_out * p.C + 3 * p.n_out + 1 + 64) * sizeof(float);
+    if (p.n_out <= 5) smem = ((smem + 15) & ~(size_t)15) + 3 * ((kHbThreads / 8) * 2 * 256 + 5 * (kHbThreads / 8) * 2 * 4) + 16;   // + the 3-stage tile ring
     if (smem > 100 * 1024) return cudaErrorInvalidValue;
     static bool attr[kMaxDevices] = {};
     int dev = 0;

@@ -490,7 +490,7 @@ class InferencePlan(object):
 
     def _set_side_ctas(self, caps):
         for o, op in zip(self._op_array, self._ops):
-            if op['kind'] == nat.OP_CONV and op.get('branch', 0) > 0:
+            if op.get('branch', 0) > 0:      # convs: persistent CTAs; GN_APPLY / HEAD_FINAL: the SM count their grids are sized from
                 o.max_ctas = int(caps.get(op['branch'], 0))
 
     def autotune(self, candidates=(96, 64, 48, 32), budget_s=3.0, x=None):
@@ -552,12 +552,17 @@ class InferencePlan(object):
                 log.append(('branch %d <= %d CTAs' % (b, c), t))
                 if t < base * 0.995:
                     base, caps = t, trial
+        self.apply_side_ctas(caps)
+        self.autotune_log = log
+        return caps
+
+    def apply_side_ctas(self, caps):
+        """Re-creates the native plan with the given {branch: CTA bound} (e.g. the result of another plan's autotune for the same shape)."""
         self._set_side_ctas(caps)
         old = self.handle
         self.handle = self._create_handle()
-        lib.lfd_plan_destroy(old)
-        self.side_ctas, self.autotune_log, self.autotuned = caps, log, True
-        return caps
+        nat.lib().lfd_plan_destroy(old)
+        self.side_ctas, self.autotuned = dict(caps), True
 
     def outputs(self, slot):
         while len(self._outputs) <= slot:

@@ -1,7 +1,8 @@
 # -*- coding: utf-8 -*-
 """Debug aid: true start / end of every plan op INSIDE a CUDA-graph replay (%globaltimer stamps written by the kernels).
 
-Needs a trace build:   LFD_B200_TIMELINE=1 python lfd-a-light-and-fast-detector_b200/build.py --force
+Needs a trace build:   LFD_B200_TIMELINE=1 LFD_B200_OUT=$PWD/build_variants/lib_timeline.so python lfd-a-light-and-fast-detector_b200/build.py --force
+                       then run with LFD_B200_LIB=build_variants/lib_timeline.so (TUNE=1: after InferencePlan.autotune)
 usage: python tests/debug_timeline.py [config] [batch] [H] [W]
 """
 import os
@@ -21,6 +22,8 @@ def main():
     model, _ = synth_model(cfg)
     model.cuda()
     plan = model.inference_plan(n, h, w, torch.device('cuda', 0))
+    if os.environ.get('TUNE'):
+        print('autotune: side-branch CTA bounds', plan.autotune())
     rows = plan.describe()
     k = len(rows)
     buf = torch.zeros((k, 2), dtype=torch.int64, device='cuda')

@@ -13,8 +13,15 @@ model, _ = synth_model(cfg)
 model.to(dev).eval()
 g = torch.Generator().manual_seed(1)
 pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(6)]
+first = InferencePlan(model, N, H, W, dev, model.conv_impl, act_dtype=model.act_dtype)
+caps = first.autotune() if os.environ.get('TUNE', '1') != '0' else {}
+print('side-branch CTA bounds', caps)
+del first
 for lanes in (1, 2, 3):
     plans = [InferencePlan(model, N, H, W, dev, model.conv_impl, act_dtype=model.act_dtype) for _ in range(lanes)]
+    for pl in plans:
+        if caps:
+            pl.apply_side_ctas(caps)
     streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
     with torch.no_grad():
         for r in range(2):

@@ -215,7 +215,7 @@ class InferencePlan(object):
         if cache is not None and key in cache:
             w_off, sc_off, sh_off = cache[key]
         else:
-            if gn_groups:
+            if gn_groups and tail is None:     # (with a fused tail the GroupNorm statistics belong to the TAIL's output)
                 if conv.bias is not None:
                     raise NotImplementedError('conv followed by GroupNorm is expected to have no bias')
                 scale, shift = torch.ones(cout), torch.zeros(cout)
@@ -226,7 +226,7 @@ class InferencePlan(object):
                 cache[key] = (w_off, sc_off, sh_off)
         op = dict(kind=nat.OP_CONV, H=h, W=w, Cin=cin, Ho=ho, Wo=wo, Cout=cout, ksize=k, stride=s, relu=int(relu),
                   gn_groups=gn_groups, cc=cc, inp=in_name, res=res,
-                  w_bf16=w_off, shift=sh_off, query=q, modules=(conv, None if gn_groups else norm))
+                  w_bf16=w_off, shift=sh_off, query=q, modules=(conv, None if (gn_groups and tail is None) else norm))
         if tail is not None:
             op.update(self._tail_fields(tail, cout))
         if shortcut is not None:      # (conv1x1/s2, norm, output name): same input, computed by the same kernel
@@ -325,8 +325,17 @@ class InferencePlan(object):
     def _emit_level(self, neck, head, l, fname, fh, fw, point_off, cache):
         conv, norm = neck.level(l)
         nk = 'neck%d' % l
-        self._emit_conv(conv, norm, True, fname, nk, fh, fw)
         cls_tower, reg_tower, fin_cls, fin_reg = head.level_paths(l)
+        # merged heads: the neck's 1x1 conv (+BN+ReLU) has ONE consumer, the tower's first 1x1 conv -- run the pair as one kernel (the
+        # 128-channel neck output never reaches HBM; the GroupNorm statistics are taken on the fused kernel's output as usual)
+        t0 = cls_tower[0] if len(cls_tower) else None
+        fuse_neck = (self.fuse_tails and not os.environ.get('LFD_B200_NO_NECK_TAIL') and cls_tower is reg_tower and t0 is not None
+                     and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.groups == 1 and conv.out_channels == 128
+                     and t0[0].kernel_size == (1, 1) and t0[0].stride == (1, 1) and t0[0].groups == 1 and t0[0].bias is None
+                     and t0[0].in_channels == 128 and t0[0].out_channels == 128
+                     and isinstance(t0[1], nn.GroupNorm) and t0[1].num_channels == t0[1].num_groups * 8)
+        if not fuse_neck:
+            self._emit_conv(conv, norm, True, fname, nk, fh, fw)
         scale_l = float(head._scales[l]._scale.detach()) if head.uses_scale else 1.0
 
         def run_tower(tower, tag):
@@ -347,7 +356,10 @@ class InferencePlan(object):
                 if not isinstance(tnorm, nn.GroupNorm) or tnorm.num_channels != tnorm.num_groups * 8:
                     raise NotImplementedError('head towers need GroupNorm with 8 channels per group (or no norm at all)')
                 raw = 'h%d%s_raw%d' % (l, tag, ti)
-                self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
+                if ti == 0 and fuse_neck:
+                    self._emit_conv(conv, norm, True, fname, raw, fh, fw, gn_groups=tnorm.num_groups, tail=(tconv, None, False))
+                else:
+                    self._emit_conv(tconv, None, False, x, raw, fh, fw, gn_groups=tnorm.num_groups, cache=cache)
                 stats_id = self._ops[-1]['stats']
                 if ti == len(tower) - 1:
                     return raw, stats_id, tnorm

@@ -135,8 +135,7 @@ class Executor(object):
                 predict_outputs = cfg['model'](self._to_device(image_batch))
                 loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
             cfg.update(loss=loss_dict['loss'])
-            for name, value in loss_dict['loss_values'].items():
-                cfg['train_average_meter'].update(name, value, cfg['batch_size'])
+            cfg['train_average_meter'].update_all(loss_dict['loss_values'], cfg['batch_size'])     # read when the logger asks
             cfg['train_iter'] += 1
             self._call_hooks('after_train_iter')
         cfg['epoch'] += 1
@@ -156,8 +155,7 @@ class Executor(object):
                 predict_outputs = cfg['model'](self._to_device(image_batch))
                 loss_dict = cfg['model'].get_loss(predict_outputs, annotation_batch, meta_batch)
                 predict_results = cfg['model'].get_results(predict_outputs, meta_batch)
-            for name, value in loss_dict['loss_values'].items():
-                cfg['val_average_meter'].update(name, value, cfg['batch_size'])
+            cfg['val_average_meter'].update_all(loss_dict['loss_values'], cfg['batch_size'])
             cfg.update(eval_results=(predict_results, meta_batch))
             self._call_hooks('after_val_iter')
         self._call_hooks('after_val_epoch')

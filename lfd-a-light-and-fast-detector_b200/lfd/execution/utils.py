@@ -108,13 +108,27 @@ class AverageMeter(object):
     def reset(self):
         self._sum = defaultdict(float)
         self._count = defaultdict(float)
+        self._pending = []
 
     def update(self, name, value, n=1):
         self._sum[name] += float(value) * n
         self._count[name] += n
 
+    def update_all(self, values, n=1):
+        """values: a mapping name -> number that may still be on its way from the device (lfd.model.lfd.LossValues): it is only read
+        when an average is asked for, so that logging never stalls the training loop."""
+        self._pending.append((values, n))
+
+    def _fold(self):
+        pending, self._pending = self._pending, []
+        for values, n in pending:
+            for name, value in values.items():
+                self.update(name, value, n)
+
     def average(self, name):
+        self._fold()
         return self._sum[name] / max(self._count[name], 1e-12)
 
     def averages(self):
+        self._fold()
         return OrderedDict((k, self.average(k)) for k in self._sum)

@@ -17,6 +17,8 @@ B200 path) and raises.
 import ctypes as C
 
 import numpy
+from collections.abc import Mapping
+
 import torch
 import torch.nn as nn
 
@@ -38,6 +40,46 @@ class _DetectionLossFn(torch.autograd.Function):
     def backward(ctx, g):
         grad_cls, grad_reg = ctx.saved_tensors
         return grad_cls * g, grad_reg * g, None, None, None
+
+
+class LossValues(Mapping):
+    """`loss_values` of get_loss: the reference returns python floats (three `.item()` calls = three device synchronisations between the
+    loss and `loss.backward()`).  Here the three numbers travel to a pinned host buffer with an asynchronous copy and become floats on first
+    access -- the training loop can enqueue the backward pass and the optimizer step before anything waits for the device."""
+    _names = ('loss', 'classification_loss', 'regression_loss')
+
+    def __init__(self, device_values):
+        self._host = torch.empty(3, dtype=torch.float32).pin_memory() if device_values.is_cuda else None
+        self._event = None
+        self._vals = None
+        if self._host is None:
+            self._vals = [float(v) for v in device_values.tolist()]
+        else:
+            self._host.copy_(device_values, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record(torch.cuda.current_stream(device_values.device))
+
+    def _values(self):
+        if self._vals is None:
+            self._event.synchronize()
+            self._vals = [float(v) for v in self._host.tolist()]
+        return self._vals
+
+    def __getitem__(self, key):
+        return self._values()[self._names.index(key)] if key in self._names else self._missing(key)
+
+    @staticmethod
+    def _missing(key):
+        raise KeyError(key)
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self):
+        return 3
+
+    def __repr__(self):
+        return repr(dict(zip(self._names, self._values())))
 
 
 class LFD(nn.Module):
@@ -198,16 +240,38 @@ class LFD(nn.Module):
             if l.size and (int(l.min()) < 0 or int(l.max()) >= self._num_classes):
                 raise IndexError('gt label out of range [0, %d): %s' % (self._num_classes, sorted(set(l.tolist()))[:8]))
         gmax = max([int(b.shape[0]) for b in gt_bboxes_list] + [1])
-        boxes = torch.zeros((N, gmax, 4), dtype=torch.float32)
-        labels = torch.zeros((N, gmax), dtype=torch.int32)
-        counts = torch.zeros((N,), dtype=torch.int32)
+        # boxes | labels | counts of the batch in ONE pinned staging buffer and one asynchronous copy (three pageable `.to(device)` calls
+        # would each block the host until the stream -- i.e. the forward pass -- has drained); a small ring of staging buffers, each
+        # guarded by the event of its last copy
+        n_words = N * gmax * 4 + N * gmax + N
+        ring = self.__dict__.setdefault('_ann_ring', [])
+        slot = self.__dict__.get('_ann_slot', 0)
+        self.__dict__['_ann_slot'] = (slot + 1) % 4
+        while len(ring) < 4:
+            ring.append([None, None])
+        if ring[slot][0] is None or ring[slot][0].numel() < n_words:
+            ring[slot] = [torch.empty(max(n_words, 1024), dtype=torch.int32).pin_memory(), None]
+        elif ring[slot][1] is not None:
+            ring[slot][1].synchronize()
+        host = ring[slot][0][:n_words]
+        host.zero_()
+        hb = host[:N * gmax * 4].view(torch.float32).view(N, gmax, 4)
+        hl = host[N * gmax * 4:N * gmax * 5].view(N, gmax)
+        hc = host[N * gmax * 5:]
         for i, (b, l) in enumerate(zip(gt_bboxes_list, gt_labels_list)):
             g = int(b.shape[0])
-            counts[i] = g
+            hc[i] = g
             if g:
-                boxes[i, :g] = torch.as_tensor(b, dtype=torch.float32).reshape(g, 4)
-                labels[i, :g] = torch.as_tensor(l).reshape(g).to(torch.int32)
-        boxes, labels, counts = boxes.to(device), labels.to(device), counts.to(device)
+                hb[i, :g] = torch.as_tensor(b, dtype=torch.float32).reshape(g, 4)
+                hl[i, :g] = torch.as_tensor(l).reshape(g).to(torch.int32)
+        dev = torch.empty(n_words, dtype=torch.int32, device=device)
+        dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        ring[slot][1] = ev
+        boxes = dev[:N * gmax * 4].view(torch.float32).view(N, gmax, 4)
+        labels = dev[N * gmax * 4:N * gmax * 5].view(N, gmax)
+        counts = dev[N * gmax * 5:]
         C_ = self._num_classes
         cls_t = torch.empty((N, P, C_), dtype=torch.float32, device=device)
         reg_t = torch.empty((N, P, 4), dtype=torch.float32, device=device)
@@ -294,8 +358,7 @@ class LFD(nn.Module):
         vals = torch.stack([total, cls_loss, reg_loss])
         if self.loss_globally_normalised:   # logged values = the GLOBAL batch's losses (per-rank sums over the global positive count add up)
             torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.SUM)
-        vals = vals.tolist()                # one D2H sync instead of the reference's three
-        return dict(loss=loss, loss_values=dict(loss=vals[0], classification_loss=vals[1], regression_loss=vals[2]))
+        return dict(loss=loss, loss_values=LossValues(vals))      # floats on first access (asynchronous D2H), see LossValues
 
     def _data_parallel(self):
         return self.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
@@ -312,8 +375,7 @@ class LFD(nn.Module):
             torch.distributed.all_reduce(counters, op=torch.distributed.ReduceOp.SUM)
             self.loss_globally_normalised = True
             torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.SUM)
-        vals = vals.tolist()
-        return dict(loss=None, loss_values=dict(loss=vals[0], classification_loss=vals[1], regression_loss=vals[2]))
+        return dict(loss=None, loss_values=LossValues(vals))
 
     # ------------------------------------------------------------------ post-process
     def _post_cfg(self, N, sizes, score_thr, iou_thr, class_agnostic):

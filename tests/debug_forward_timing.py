@@ -14,6 +14,8 @@ model.to(dev).eval()
 g = torch.Generator().manual_seed(1)
 pool = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(6)]
 plan = model.inference_plan(N, H, W, dev)
+if os.environ.get('TUNE'):
+    print('autotune', plan.autotune())
 with torch.no_grad():
     for r in range(3):
         for x in pool:

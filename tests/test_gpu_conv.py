@@ -73,6 +73,9 @@ TAIL_CASES = [   # (N, H, W, Cin, Cmid, k, stride, Cout2, residual on the tail o
     (1, 37, 29, 64, 64, 3, 1, 128, True, 0),
     (2, 23, 31, 32, 32, 1, 1, 64, False, 0),
     (1, 33, 41, 64, 64, 1, 1, 128, False, 16),
+    (2, 45, 80, 64, 128, 1, 1, 128, False, 16),  # neck conv (64 -> 128, BN + ReLU) + first tower conv (128 -> 128, GroupNorm statistics)
+    (3, 12, 20, 128, 128, 1, 1, 128, False, 16),
+    (1, 23, 40, 32, 128, 1, 1, 128, False, 16),
 ]
 
 

@@ -75,8 +75,9 @@ def test_arena_reuses_and_coalesces():
     assert a.alloc(10) == o3 + 256
 
 
-# stem 1x1 convs are fused tails, the 4 shortcut convs are fused into their block's first conv
-@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 1 + 2 * 11 + 0 + 5 + 10), ('TT100K_L', 0 + 2 * 12 + 0 + 4 + 16)])
+# stem 1x1 convs are fused tails, the 4 shortcut convs are fused into their block's first conv; merged heads: the neck conv and the first
+# tower conv of every level run as one kernel (5 levels: 5 + 10 convs -> 10)
+@pytest.mark.parametrize('name,n_conv', [('WIDERFACE_S', 1 + 2 * 11 + 0 + 10), ('TT100K_L', 0 + 2 * 12 + 0 + 4 + 16)])
 def test_planner_builds_expected_graph(name, n_conv):
     model, _ = synth_model(name)
     plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
@@ -84,6 +85,8 @@ def test_planner_builds_expected_graph(name, n_conv):
     kinds = [r['kind'] for r in rows]
     assert kinds[0] == 'stem0' and kinds.count('stem0') == 1 and rows[0]['tail_cout'] == 64
     assert kinds.count('conv') == n_conv
+    levels_fused = [r for r in rows if r['kind'] == 'conv' and r['ksize'] == 1 and r['tail_cout'] == 128 and r['Cout'] == 128]
+    assert len(levels_fused) == (len(plan.level_sizes) if name.startswith('WIDERFACE') else 0)
     assert len([r for r in rows if r['ds_cout']]) == 4
     levels = len(plan.level_sizes)
     merged = name.startswith('WIDERFACE')
@@ -160,7 +163,7 @@ def test_planner_accepts_every_block_mode(mode, n_fused):
     per_block = {'fast': 3, 'faster': 2, 'fastest': 2}[mode]
     n_blocks = 5
     n_short = 4 - n_fused
-    assert sum(1 for r in rows if r['kind'] == 'conv') == n_blocks * per_block + n_short + 4 + 2 * 4   # + necks + tower convs
+    assert sum(1 for r in rows if r['kind'] == 'conv') == n_blocks * per_block + n_short + 2 * 4   # + (neck + first tower conv, one kernel) + second tower conv
     for o in plan._ops:
         if o.get('wait_mask') == 1 << 7:
             assert o['res'] is not None and o['branch'] == 0

@@ -80,7 +80,7 @@ class ForwardPostPipeline(object):
 
 class StreamingDetector(object):
 
-    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None, depth=3, copy_streams=2):
+    def __init__(self, model, batch, height, width, score_thr, iou_thr, max_out=1024, device=None, depth=3, copy_streams=4):
         self.model = model
         self.depth = max(2, int(depth))     # batches in flight: copy of i+2 | forward of i+1 | post-process + read-back of i
         self.device = device if device is not None else next(model.parameters()).device
@@ -89,8 +89,9 @@ class StreamingDetector(object):
         self.max_out = min(int(max_out), int(model.max_detections_per_image))
         dev = self.device
         with torch.cuda.device(dev):
-            # the batch goes up in `copy_streams` chunks on as many streams: two DMA engines in flight fill the PCIe link better
-            # than one 22 MB copy (measured in bench.py: e2e.h2d_gbps)
+            # the batch goes up in `copy_streams` chunks on as many streams: several DMA transfers in flight fill the PCIe link better
+            # than one 22 MB copy (measured in bench.py: e2e.h2d_gbps; 1 / 2 / 4 streams: 0.606 / 0.609 / 0.597 ms per step end to end.
+            # The copy itself costs the forward ~8 %: 0.561 ms per step with the input copy left out, tests/debug_e2e_timeline.py)
             self.copy_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(int(copy_streams), batch)))]
             self.copy_stream = self.copy_streams[0]
         self.plan = model.inference_plan(batch, height, width, dev)

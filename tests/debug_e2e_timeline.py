@@ -17,7 +17,16 @@ model.max_detections_per_image = 8192
 g = torch.Generator().manual_seed(1)
 host = [torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
 depth = int(os.environ.get('DEPTH', '3'))
-det = StreamingDetector(model, N, H, W, 0.476, 0.3, max_out=1024, device=dev, depth=depth)
+det = StreamingDetector(model, N, H, W, 0.476, 0.3, max_out=1024, device=dev, depth=depth, copy_streams=int(os.environ.get('COPY_STREAMS', '2')))
+if os.environ.get('NO_H2D'):          # diagnostic: leave the input copy out (the slots keep their first frames)
+    for i in range(det.depth):
+        det.stage_input(i, host[0])
+    torch.cuda.synchronize()
+    def _no_copy(slot, frames):
+        s_ = det.slots[slot]
+        with torch.cuda.stream(det.copy_stream):
+            s_['h2d'].record(det.copy_stream)
+    det.stage_input = _no_copy
 pipe = det.pipe
 orig = pipe.plan.forward
 marks = []
@@ -36,7 +45,7 @@ with torch.no_grad():
     for i in range(12):
         det.infer(host[i % 2])
     torch.cuda.synchronize()
-    for mode in ('plain', 'marked'):
+    for mode in (('plain',) if os.environ.get('PLAIN_ONLY') else ('plain', 'marked')):
         if mode == 'marked':
             pipe.plan.forward = forward
         marks.clear()
@@ -52,6 +61,8 @@ with torch.no_grad():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         print('%s depth %d: %.4f ms per step, %.0f img/s' % (mode, depth, dt / steps * 1e3, N * steps / dt))
+    if not marks:
+        sys.exit(0)
     durs = [a.elapsed_time(b) for a, b in marks[20:]]
     gaps = [marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(20, len(marks) - 1)]
     print('forward on the device: mean %.4f ms (min %.4f max %.4f); gap to the next forward: mean %.4f ms (min %.4f max %.4f)'

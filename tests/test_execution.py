@@ -204,3 +204,27 @@ def test_gloo_world2_broadcast_empty_shard_and_evaluation_gather():
     for r in (r0, r1):
         (results, meta), = r['seen']
         assert [m['image_id'] for m in meta] == [10, 11] and [res[0][1] for res in results] == [0.5, 1.5] and r['done'] == 1
+
+
+def test_loss_values_are_a_lazy_mapping_and_the_meter_folds_them_on_read():
+    """get_loss returns `loss_values` as a Mapping whose three numbers reach the host asynchronously (lfd/model/lfd.py::LossValues; on the
+    CPU they are materialised at once); AverageMeter.update_all keeps such mappings pending until an average is asked for."""
+    import torch
+    from lfd.model.lfd import LossValues
+    from lfd.execution.utils import AverageMeter
+    lv = LossValues(torch.tensor([3.0, 1.0, 2.0]))
+    assert list(lv) == ['loss', 'classification_loss', 'regression_loss'] and len(lv) == 3
+    assert lv['loss'] == 3.0 and dict(lv.items()) == dict(loss=3.0, classification_loss=1.0, regression_loss=2.0)
+    assert 'missing' not in lv and lv.get('missing', 7) == 7
+    with pytest.raises(KeyError):
+        lv['missing']
+    m = AverageMeter()
+    m.update_all(lv, 2)
+    m.update_all(LossValues(torch.tensor([6.0, 2.0, 4.0])), 1)
+    assert m._pending and not m._sum                       # nothing has been read yet
+    assert abs(m.average('loss') - (3.0 * 2 + 6.0) / 3) < 1e-12
+    assert abs(m.averages()['regression_loss'] - (2.0 * 2 + 4.0) / 3) < 1e-12
+    m.update('loss', 9.0, 1)                               # the reference's eager update still works
+    assert abs(m.average('loss') - (3.0 * 2 + 6.0 + 9.0) / 4) < 1e-12
+    m.reset()
+    assert not m._pending and not m.averages()

@@ -164,6 +164,43 @@ def op_algorithmic(row, N, input_bytes_per_px):
     return px_in * cin * 2 + px_out * cout * 4, 2.0 * px_out * cout * cin   # head_final
 
 
+def op_read_write(row, N, input_bytes_per_px):
+    """(read bytes, written bytes) of op_algorithmic's byte count."""
+    b, _ = op_algorithmic(row, N, input_bytes_per_px)
+    px_out = N * row['Ho'] * row['Wo']
+    if row['kind'] in ('stem0', 'conv'):
+        w = px_out * ((row.get('tail_cout', 0) or row['Cout']) + row.get('ds_cout', 0)) * 2
+    elif row['kind'] == 'gn_apply':
+        w = b // 2
+    else:
+        w = px_out * row['Cout'] * 4
+    return b - w, w
+
+
+def directional_peaks(dev):
+    """HBM ceilings for one-directional streams, measured here (best of 5, CUDA events): a layer that mostly writes (the stem: 22 MB in,
+    236 MB out) or mostly reads cannot reach the copy figure the roofline divides by, which is half reads and half writes."""
+    n = 1 << 27                                 # 512 MB of fp32
+    a = torch.empty(n, dtype=torch.float32, device=dev)
+
+    def best(fn):
+        fn()
+        torch.cuda.synchronize()
+        t = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        return 4.0 * n / (min(t) * 1e-3) / 1e9
+    w = best(lambda: a.fill_(1.0))
+    r = best(lambda: a.sum())
+    del a
+    return dict(write_only_gbs=w, read_only_gbs=r, how='torch fill_ / sum over 512 MB fp32, best of 5')
+
+
 def op_name(row):
     return '%s %dx%d/s%d %d->%d @%dx%d' % (row['kind'], row['ksize'], row['ksize'], row['stride'], row['Cin'], row['Cout'], row['Ho'], row['Wo'])
 
@@ -819,6 +856,13 @@ def main():
     conv_ms = float(sum(r['ms'] for r in table if r['row']['kind'] == 'conv'))
     net_bound_ms = float(sum(r['t_bound_ms'] for r in table))
     total_bytes, total_flops = sum(r['bytes'] for r in table), sum(r['flops'] for r in table)
+    dp = directional_peaks(dev)
+    dir_bound_ms = 0.0
+    for r in table:
+        rd, wr = op_read_write(r['row'], N, 3)
+        r['t_dir_ms'] = 1e3 * max(r['flops'] / (pk['bf16_tflops'] * 1e12), (rd + wr) / (pk['hbm_gbs'] * 1e9), rd / (dp['read_only_gbs'] * 1e9),
+                                  wr / (dp['write_only_gbs'] * 1e9))
+        dir_bound_ms += r['t_dir_ms']
     kname = op_name(top['row'])
     roofline = dict(bound='hbm' if hbm_bound else 'tensor', achieved=achieved, peak=peak, unit=unit, frac=achieved / peak,
                     traffic=ncu_traffic(args.config, dtype, kname),
@@ -827,6 +871,9 @@ def main():
                     kernel_ms=top['ms'], kernel_share_of_step=top['ms'] / sum_ms, algorithmic_bytes=top['bytes'], algorithmic_flops=top['flops'],
                     net=dict(layerwise_bound_ms=net_bound_ms, forward_ms_eager_sum=sum_ms, frac_of_layerwise_bound=net_bound_ms / sum_ms,
                              frac_of_layerwise_bound_in_graph=net_bound_ms / ms_step,
+                             directional_peaks=dp, directional_bound_ms=dir_bound_ms, frac_of_directional_bound_in_graph=dir_bound_ms / ms_step,
+                             directional_note='per layer max(flops / peak, (R + W) / copy peak, R / read-only peak, W / write-only peak): the bound '
+                                              'a layer with a lopsided read / write mix can actually reach',
                              conv_share=conv_ms / sum_ms, algorithmic_gb=total_bytes / 1e9, algorithmic_gflop=total_flops / 1e9,
                              hbm_view=total_bytes / (ms_step * 1e-3) / 1e9 / pk['hbm_gbs'],
                              tensor_view=total_flops / (ms_step * 1e-3) / 1e12 / pk['bf16_tflops']))

@@ -1,7 +1,3 @@
-python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 600 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 3 python -m pytest tests/test_gpu_ops.py tests/test_gpu_train_ops.py -q -m gpu -x -k "nms or postprocess or head_final or batched or multiclass or loss" > gpurun_out/memcheck_r02_ops.log 2>&1; echo "memcheck ops rc=$?"; tail -3 gpurun_out/memcheck_r02_ops.log
-python bench.py --steps 50 --warmup 5 > gpurun_out/final3_WIDERFACE_S.json 2> gpurun_out/final3_WIDERFACE_S.err; python -c "
-import json;d=json.loads(open('gpurun_out/final3_WIDERFACE_S.json').read().strip().splitlines()[-1]);print('WIDERFACE_S',round(d['value']),d['ms_per_step'],round(d['e2e']['value']),round(d['roofline']['frac'],3),d['roofline']['kernel'],d['roofline']['traffic'], d.get('cpu_baseline',{}).get('value'), d['impl_detail'].get('side_branch_ctas'), d['roofline']['net']['frac_of_layerwise_bound_in_graph'])"
-python bench.py --config WIDERFACE_L_train --steps 10 --warmup 3 > gpurun_out/final3_train.json 2> gpurun_out/final3_train.err; python -c "
-import json;d=json.loads(open('gpurun_out/final3_train.json').read().strip().splitlines()[-1]);print('train',round(d['value']),d['ms_per_step'],round(d['e2e']['value']),d['roofline']['kernel'],round(d['roofline']['frac'],3),d.get('cpu_baseline',{}).get('value'), d['roofline']['net']['frac_of_layerwise_bound_in_step'])"
-python bench.py --config WIDERFACE_L_train --steps 5 --warmup 3 --no-cpu-baseline --profile-ops 2> gpurun_out/final3_ops_train.txt > /dev/null; grep -c "" gpurun_out/final3_ops_train.txt
+python profiles/microbench/rw_peaks.py 2>&1 | tail -4
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/b_dir.json 2> gpurun_out/b_dir.err; tail -2 gpurun_out/b_dir.err; python -c "
+import json;d=json.loads(open('gpurun_out/b_dir.json').read().strip().splitlines()[-1]);n=d['roofline']['net'];print(round(d['value']),d['ms_per_step'],round(d['e2e']['value']),n['directional_peaks'],n['layerwise_bound_ms'],n['directional_bound_ms'],n['frac_of_layerwise_bound_in_graph'],n['frac_of_directional_bound_in_graph'])"

@@ -52,8 +52,8 @@ class ForwardPostPipeline(object):
             # highest priority the device offers (torch maps out-of-range values to it): the post-process kernels are tiny and
             # latency-bound; with a priority above the forward graph's nodes their CTAs are placed at the first kernel boundary of the
             # NEXT batch's forward instead of queueing behind its persistent CTAs
-            self.post_stream = torch.cuda.Stream(device=dev, priority=int(os.environ.get('LFD_B200_POST_PRIO', '-100')))
-        self.n_slots = int(os.environ.get('LFD_B200_OUT_SLOTS', '2'))
+            self.post_stream = torch.cuda.Stream(device=dev, priority=-100)
+        self.n_slots = 2                # output pairs of the plan: 2 and 3 measured alike (profiles/r02_tuning_notes.md)
         self.fwd_done = [torch.cuda.Event() for _ in range(self.n_slots)]
         self.post_done = [torch.cuda.Event() for _ in range(self.n_slots)]
         self.k = 0

@@ -242,3 +242,22 @@ def test_training_plan_branches_order_every_conflict(name):
     # the backward starts every level chain before the backbone
     first_main = next(i for i, op in enumerate(plan.bwd_ops) if op.get('branch', 0) == 0 and op['kind'] not in (nat.TOP_ZERO,))
     assert all(op.get('branch', 0) == 0 for op in plan.bwd_ops[first_main:])
+
+
+def test_side_branch_cta_bounds_touch_only_side_branch_ops():
+    """InferencePlan._set_side_ctas (what autotune / apply_side_ctas write into the op array): every op of a side branch gets its branch's
+    bound (convs: persistent CTAs; GN_APPLY / HEAD_FINAL: the SM count their grids are sized from), main-stream ops stay unbounded."""
+    model, _ = synth_model('WIDERFACE_S')
+    plan = InferencePlan(model, 2, 184, 248, torch.device('cpu'), create_native=False)
+    caps = {b: 16 * b for b in range(1, len(plan.level_sizes) + 1)}
+    plan._set_side_ctas(caps)
+    seen = set()
+    for o, op in zip(plan._op_array, plan._ops):
+        if op['branch'] == 0:
+            assert o.max_ctas == 0
+        else:
+            assert o.max_ctas == caps[op['branch']]
+            seen.add(op['kind'])
+    assert seen == {nat.OP_CONV, nat.OP_GN_APPLY, nat.OP_HEAD_FINAL}
+    plan._set_side_ctas({})
+    assert all(o.max_ctas == 0 for o in plan._op_array)
